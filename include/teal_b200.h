@@ -1,0 +1,105 @@
+/*
+ * teal_b200 -- C ABI of the B200-native activation-sparse decode path.
+ *
+ * This header is the drop-in boundary.  The reference (FasterDecoding/TEAL) has no C ABI: its
+ * boundary is two torch.library ops backed by Triton.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root).  Everything is
+ * plain pointers + sizes; no torch types.  All device pointers are CUDA device pointers on the
+ * current device, all launches are asynchronous on `stream` (a cudaStream_t passed as void*),
+ * nothing allocates or synchronises, so every call is CUDA-graph-capturable.
+ *
+ * Conventions
+ *   - return value: 0 on success, negative teal_status otherwise; teal_last_error() gives the
+ *     message for the calling thread.
+ *   - "wt" weights are the reference's "column major" layout (gpt-fast/generate.py:296-317,
+ *     asserted at kernels/sparse_gemv.py:106,210): logical [N, Z] with stride (1, ldw), i.e.
+ *     storage [Z][ldw] fp16 with the N output columns of one input lane contiguous.
+ *   - thresholds are the reference's Python floats; the library rounds them to fp16
+ *     (round-to-nearest-even) so that the survivor set equals the reference's
+ *     `x.abs().gt(threshold)` on an fp16 tensor (utils/utils.py:51-52).  A lane survives iff
+ *     |x| > fp16(threshold); NaN lanes are also gathered so that NaN poisons the output exactly
+ *     as `mask * x` does in the reference.
+ *   - workspace: teal_workspace_bytes() bytes of device memory, zeroed ONCE with
+ *     teal_workspace_init(); kernels leave it zeroed again on exit.  One workspace must not be
+ *     used by two streams at the same time.
+ */
+#ifndef TEAL_B200_H_
+#define TEAL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum teal_status {
+  TEAL_OK = 0,
+  TEAL_ERR_BAD_ARG = -1,     /* null pointer, negative size */
+  TEAL_ERR_ALIGNMENT = -2,   /* pointer / leading dimension not 16-byte aligned, N or Z % 8 != 0 */
+  TEAL_ERR_UNSUPPORTED = -3, /* shape outside compiled limits (Z > 65536, ...) */
+  TEAL_ERR_WORKSPACE = -4,   /* workspace too small */
+  TEAL_ERR_CUDA = -5         /* CUDA runtime error (message has the cudaError string) */
+} teal_status;
+
+#define TEAL_B200_ABI_VERSION 1
+
+int teal_abi_version(void);
+const char* teal_last_error(void);
+
+/* Number of SMs the library will spread work over / compiled-for arch (100). */
+int teal_device_sm_count(void);
+int teal_compiled_arch(void);
+
+/* Bytes of workspace needed for any call whose total number of output columns
+ * (N, or 2*I for the fused gate/up call) is <= max_out_cols. */
+size_t teal_workspace_bytes(int max_out_cols);
+int teal_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+/* y[n] = sum_{m : |x[m]| > fp16(threshold)} wt[m][n] * x[m]          (fp32 accumulate, one fp16 round)
+ * Replaces torch.ops.teal.sparse_gemv's decode branch: splitk_sparse_gemv()
+ * kernels/sparse_gemv.py:87-142 + splitk_sparse_gemv_kernel :45-83 (incl. its Y.zero_() pre-hook).
+ * x: fp16[Z], wt: fp16[Z][ldw], y: fp16[N]. */
+int teal_sparse_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw,
+                         double threshold, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused QKV with one threshold per output region: columns [0, N - 2*kv_size) use threshold_q,
+ * the next kv_size use threshold_k, the last kv_size threshold_v -- selected per column exactly.
+ * Replaces torch.ops.teal.sparse_qkv_gemv's decode branch: qkv_gemv() kernels/sparse_gemv.py:196-237
+ * + qkv_kernel :147-194. */
+int teal_sparse_qkv_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw,
+                             int kv_size, double threshold_q, double threshold_k,
+                             double threshold_v, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* h[i] = fp16(silu(gate[i])) * up[i] with gate = sparse_gemv(x, w1t, threshold_gate) and
+ * up = sparse_gemv(x, w3t, threshold_up), both rounded to fp16 first -- the first half of
+ * _new_ffn_forward (gpt-fast/model.py:258-259): two gemv1 calls + the SiLU*mul, in one kernel.
+ * x: fp16[Z], w1t/w3t: fp16[Z][ldw*], h: fp16[I]. */
+int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, void* h, int Z, int I,
+                            int64_t ldw1, int64_t ldw3, double threshold_gate,
+                            double threshold_up, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* Survivor set of one threshold, produced by the same device code the GEMV kernels use
+ * (parity hook: "surviving-index set bit-exact").  idx_out: int32[Z] (sorted ascending, first
+ * *count_out entries valid), count_out: int32[1].  Both device pointers. */
+int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out,
+                       int32_t* count_out, void* stream);
+
+/* Independent slow cross-check of teal_sparse_gemv_f16 (one warp per 256 columns, no K split,
+ * no workspace); used by tests to triage, never by the decode path. */
+int teal_sparse_gemv_f16_simple(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw,
+                                double threshold, void* stream);
+
+/* Tuning knob for benchmarks: selects the tile configuration (0 = library default per shape). */
+int teal_set_config(int config_id);
+
+/* Profiling hook: when non-null, every CTA of the GEMV kernels writes 16 int64 phase timestamps
+ * (clock64 / globaltimer) to device_buf[blockIdx.x * 16 ...]; pass NULL to switch it off. */
+int teal_set_debug_timestamps(void* device_buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEAL_B200_H_ */

@@ -1,0 +1,91 @@
+"""ctypes binding of libteal_b200.so -- the only way Python reaches the CUDA kernels.
+
+There is no CPU fallback: if the shared library is missing or was not built for sm_100a this
+module raises at import of the symbol table, and every op raises at call time.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libteal_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "teal_b200.h")
+
+_c = ctypes
+_SIGS = {
+    "teal_abi_version": (_c.c_int, []),
+    "teal_last_error": (_c.c_char_p, []),
+    "teal_device_sm_count": (_c.c_int, []),
+    "teal_compiled_arch": (_c.c_int, []),
+    "teal_workspace_bytes": (_c.c_size_t, [_c.c_int]),
+    "teal_workspace_init": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "teal_sparse_gemv_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
+                                        _c.c_double, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "teal_sparse_qkv_gemv_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
+                                            _c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_void_p,
+                                            _c.c_size_t, _c.c_void_p]),
+    "teal_sparse_gate_up_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                           _c.c_int64, _c.c_int64, _c.c_double, _c.c_double, _c.c_void_p,
+                                           _c.c_size_t, _c.c_void_p]),
+    "teal_survivors_f16": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "teal_sparse_gemv_f16_simple": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                               _c.c_int64, _c.c_double, _c.c_void_p]),
+    "teal_set_config": (_c.c_int, [_c.c_int]),
+    "teal_set_debug_timestamps": (_c.c_int, [_c.c_void_p]),
+}
+
+_lib = None
+
+
+class TealLibraryError(RuntimeError):
+    pass
+
+
+def declared_symbols() -> List[str]:
+    """Every function include/teal_b200.h declares (used by the CPU-side export test)."""
+    with open(HEADER) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(teal_[a-z0-9_]+)\s*\(", text)))
+
+
+def register_signatures(sigs: Dict[str, tuple]) -> None:
+    _SIGS.update(sigs)
+    if _lib is not None:
+        _bind(_lib)
+
+
+def _bind(lib) -> None:
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def load():
+    """Loads (building in-tree if the sources are newer) and returns the ctypes library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # fail loudly: there is no fallback path
+        raise TealLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    _bind(lib)
+    if lib.teal_abi_version() != 1:
+        raise TealLibraryError("libteal_b200 ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().teal_last_error().decode()
+        if rc in (-1, -2):
+            raise AssertionError(f"{what}: {msg}")  # reference raises AssertionError on shape/layout
+        raise TealLibraryError(f"{what} failed ({rc}): {msg}")

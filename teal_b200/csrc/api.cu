@@ -1,0 +1,169 @@
+// extern "C" boundary of libteal_b200 (see include/teal_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace teal {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return TEAL_ERR_CUDA;
+}
+
+const DeviceInfo& device_info() {
+  static thread_local int cached_dev = -1;
+  static thread_local DeviceInfo di = {cudaSuccess, 0, 0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { di.err = e; return di; }
+  if (dev != cached_dev) {
+    di.err = cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (di.err == cudaSuccess)
+      di.err = cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (di.err == cudaSuccess) cached_dev = dev;
+  }
+  return di;
+}
+
+// Round-to-nearest-even to fp16, like torch demoting a Python scalar to an fp16 tensor's dtype.
+float round_threshold_fp16(double t) {
+  if (t != t) return t;  // NaN threshold: every compare false -> everything "survives" as in `!(a <= t)`
+  __half h = __double2half(t);
+  return __half2float(h);
+}
+
+static int fill_common(GemvParams& p, const void* x, void* y, int Z) {
+  memset(&p, 0, sizeof(p));
+  if (!x) return set_error(TEAL_ERR_BAD_ARG, "x is null");
+  p.x = reinterpret_cast<const __half*>(x);
+  p.y = reinterpret_cast<__half*>(y);
+  p.Z = Z;
+  return TEAL_OK;
+}
+
+// Assign threshold slots, merging equal thresholds so that the scan runs once per distinct value.
+static int slot_for(GemvParams& p, float thr) {
+  for (int k = 0; k < p.nthr; ++k)
+    if (p.thr[k] == thr) return k;
+  p.thr[p.nthr] = thr;
+  return p.nthr++;
+}
+
+}  // namespace teal
+
+using namespace teal;
+
+extern "C" {
+
+int teal_abi_version(void) { return TEAL_B200_ABI_VERSION; }
+const char* teal_last_error(void) { return g_err; }
+int teal_compiled_arch(void) { return 100; }
+int teal_device_sm_count(void) {
+  const DeviceInfo& di = device_info();
+  if (di.err != cudaSuccess) return set_cuda_error(di.err, "device query");
+  return di.sm_count;
+}
+size_t teal_workspace_bytes(int max_out_cols) { return workspace_bytes(max_out_cols < 8 ? 8 : max_out_cols); }
+
+int teal_workspace_init(void* workspace, size_t workspace_bytes_, void* stream) {
+  if (!workspace) return set_error(TEAL_ERR_BAD_ARG, "workspace is null");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync");
+  return TEAL_OK;
+}
+
+int teal_set_config(int config_id) { return set_config(config_id); }
+int teal_set_debug_timestamps(void* device_buf) {
+  set_debug_timestamps(reinterpret_cast<long long*>(device_buf));
+  return TEAL_OK;
+}
+
+int teal_sparse_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, double threshold,
+                         void* workspace, size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, y, Z)) return rc;
+  if (!wt || !y || N <= 0 || ldw < N) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / N / ldw");
+  p.mode = kModePlain;
+  p.nseg = 1;
+  p.seg[0].w = reinterpret_cast<const __half*>(wt);
+  p.seg[0].ldw = ldw;
+  p.seg[0].ncols = N;
+  p.seg[0].out_col0 = 0;
+  p.seg[0].thr_slot = slot_for(p, round_threshold_fp16(threshold));
+  return launch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_sparse_qkv_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, int kv_size,
+                             double threshold_q, double threshold_k, double threshold_v, void* workspace,
+                             size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, y, Z)) return rc;
+  if (!wt || !y || N <= 0 || ldw < N || kv_size < 0 || 2 * (int64_t)kv_size > N)
+    return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / N / ldw / kv_size");
+  const int n_q = N - 2 * kv_size;  // kernels/sparse_gemv.py:212
+  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k),
+              tv = round_threshold_fp16(threshold_v);
+  p.mode = kModePlain;
+  const __half* w = reinterpret_cast<const __half*>(wt);
+  if (tq == tk && tk == tv) {  // uniform sparsity: one region, one survivor list
+    p.nseg = 1;
+    p.seg[0] = GemvSeg{w, ldw, N, 0, slot_for(p, tq), 0, 0, 0};
+  } else {
+    const int cols[3] = {n_q, kv_size, kv_size};
+    const float thr[3] = {tq, tk, tv};
+    int c0 = 0;
+    for (int r = 0; r < 3; ++r) {
+      if (cols[r] == 0) continue;
+      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, slot_for(p, thr[r]), 0, 0, 0};
+      c0 += cols[r];
+    }
+  }
+  return launch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, void* h, int Z, int I, int64_t ldw1,
+                            int64_t ldw3, double threshold_gate, double threshold_up, void* workspace,
+                            size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, h, Z)) return rc;
+  if (!w1t || !w3t || !h || I <= 0 || ldw1 < I || ldw3 < I) return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / h / I / ldw");
+  p.mode = kModePairSilu;
+  p.nseg = 2;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
+  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, slot_for(p, round_threshold_fp16(threshold_up)), 0, 0, 0};
+  return launch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out, int32_t* count_out, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, nullptr, Z)) return rc;
+  if (!idx_out || !count_out) return set_error(TEAL_ERR_BAD_ARG, "null output");
+  p.mode = kModeSurvivors;
+  p.nseg = 0;
+  p.nthr = 0;
+  slot_for(p, round_threshold_fp16(threshold));
+  p.dbg_idx = idx_out;
+  p.dbg_cnt = count_out;
+  return launch_gemv(p, nullptr, 0, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_sparse_gemv_f16_simple(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, double threshold,
+                                void* stream) {
+  if (!x || !wt || !y || Z <= 0 || N <= 0 || ldw < N) return set_error(TEAL_ERR_BAD_ARG, "bad argument");
+  if ((ldw & 7) || (reinterpret_cast<uintptr_t>(wt) & 15)) return set_error(TEAL_ERR_ALIGNMENT, "wt alignment");
+  return launch_simple(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(wt),
+                       reinterpret_cast<__half*>(y), Z, N, ldw, round_threshold_fp16(threshold),
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

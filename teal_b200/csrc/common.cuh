@@ -1,0 +1,183 @@
+// Shared device helpers (inline PTX for sm_100a) and host-side plumbing for libteal_b200.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/teal_b200.h"
+
+namespace teal {
+
+constexpr int kConsumerThreads = 512;             // 16 consumer warps
+constexpr int kProducerWarps = 4;                 // TMA-issuing warps
+constexpr int kThreads = kConsumerThreads + 32 * kProducerWarps;
+constexpr int kMaxSeg = 4;                        // column regions per call (q,k,v / gate,up)
+constexpr int kMaxThr = 4;                        // distinct thresholds per call
+constexpr int kMaxStages = 32;
+constexpr int kMaxPieces = 8;
+constexpr int kMaxCounters = 4096;                // column tiles per call
+
+enum { kModePlain = 0, kModePairSilu = 1, kModeSurvivors = 2 };
+
+struct GemvSeg {
+  const __half* w;   // fp16 [Z][ldw], first column of the region
+  long long ldw;     // elements
+  int ncols;         // columns in the region
+  int out_col0;      // first column in y / accumulator space
+  int thr_slot;      // index into GemvParams::thr
+  int ntiles;        // filled by the launcher
+  int tile0;         // filled by the launcher (first completion counter)
+  int pad;
+};
+
+struct GemvParams {
+  const __half* x;
+  __half* y;
+  float* acc;          // fp32 accumulators (workspace), zero on entry and on exit
+  unsigned* counters;  // per-tile completion counters (workspace), zero on entry and on exit
+  int* dbg_idx;
+  int* dbg_cnt;
+  long long* dbg_time;  // optional [grid][16] phase timestamps (profiling builds of the bench tools)
+  int Z, nseg, nthr, mode;
+  int nstages, list_cap, chunk, xs_elems;
+  float thr[kMaxThr];  // fp16-representable thresholds
+  GemvSeg seg[kMaxSeg];
+};
+
+// ---------------------------------------------------------------------------------- host
+struct DeviceInfo {
+  cudaError_t err;
+  int sm_count;
+  int smem_optin;
+};
+const DeviceInfo& device_info();
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* where);
+float round_threshold_fp16(double t);
+
+size_t workspace_bytes(int max_out_cols);
+int set_config(int id);
+void set_debug_timestamps(long long* buf);
+int launch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream);
+int launch_simple(const __half* x, const __half* wt, __half* y, int Z, int N, long long ldw, float thr,
+                  cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------- device
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Spin with a watchdog: a protocol bug traps after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (((++spins) & 0xfffu) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void consumer_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_cg_f4(float* p, float4 v) {
+  asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// fp32 vector reduction into global memory (performed at L2, no return value).
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// fp16(silu(fp16(g))) * fp16(u), rounded like the reference's `F.silu(gate) * up` on fp16 tensors
+// (gpt-fast/model.py:259): gate and up are fp16 op outputs, silu rounds to fp16, the product rounds
+// to fp16.
+__device__ __forceinline__ __half silu_mul_f16(float gate_acc, float up_acc) {
+  const float g = __half2float(__float2half_rn(gate_acc));
+  const float u = __half2float(__float2half_rn(up_acc));
+  const float s = __half2float(__float2half_rn(g / (1.0f + expf(-g))));
+  return __float2half_rn(s * u);
+}
+#endif  // __CUDACC__
+
+}  // namespace teal

@@ -1,0 +1,225 @@
+"""Operator surface of the sparse decode path: ``torch.ops.teal.sparse_gemv`` and
+``torch.ops.teal.sparse_qkv_gemv`` backed by libteal_b200 (hand-written sm_100a CUDA).
+
+Mirrors the reference's op layer so that its call sites keep working unchanged:
+
+* ``SparseGEMV`` / ``SparseQKVGEMV`` with ``initialize(name, target)``, ``.operator(compiled)``,
+  ``.meta``, ``.forward``, ``.register()`` -- kernels/sparse_gemv.py:249-298 and
+  kernels/compile_wrapper.py:124-208 (``BaseKernel``) in the reference.
+* schemas are exactly the strings compile_wrapper.py:151-162 infers (tests/golden/op_schemas.txt).
+* S == 1 -> fused threshold + gather-GEMV kernel; S > 1 (prefill) -> dense ``x @ W.T`` with no
+  sparsification (kernels/sparse_gemv.py:271,298).
+* weights must be the "column major" view (stride(1) > 1, kernels/sparse_gemv.py:106,210).
+
+There is no Triton, no autotune warm-up and no CPU fallback: a CUDA tensor is required and the
+shared library must load, otherwise the op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from operator import attrgetter
+from typing import Callable, Dict, Tuple
+
+import torch
+
+from . import _lib
+
+NAMESPACE = "teal"  # kernels/compile_wrapper.py:19
+
+_MAX_OUT_COLS = 1 << 17
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(device: torch.device, stream_ptr: int) -> torch.Tensor:
+    """Per (device, stream) accumulator/counter workspace; zeroed once, kernels keep it zeroed."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
+    ws = _workspaces.get(key)
+    if ws is None:
+        lib = _lib.load()
+        nbytes = lib.teal_workspace_bytes(_MAX_OUT_COLS)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_x(x: torch.Tensor, Z: int) -> torch.Tensor:
+    if not x.is_cuda:
+        raise _lib.TealLibraryError("teal_b200 ops need CUDA tensors (there is no CPU fallback)")
+    assert x.dim() == 3 and x.shape[2] == Z, "hidden size mismatch"       # sparse_gemv.py:103,207
+    assert x.shape[0] == 1, "batch/beam must be 1 (sparse_gemv.py:73)"
+    return x.contiguous()                                                   # sparse_gemv.py:104
+
+
+def _check_w(weight: torch.Tensor) -> int:
+    assert weight.dim() == 2 and weight.stride(1) > 1 and weight.stride(0) == 1, \
+        "weight should be column major"                                     # sparse_gemv.py:106,210
+    assert weight.dtype == torch.float16, "weights must be fp16 (README.md:108)"
+    return weight.stride(1)
+
+
+def _finish(out: torch.Tensor, x_dtype: torch.dtype) -> torch.Tensor:
+    if x_dtype is not torch.float16:                                        # sparse_gemv.py:138-140
+        print("Warning: incuring dtype conversion overhead since input dtype is not torch.float16. "
+              f"Detected dtype: {x_dtype}. ")
+        return out.to(dtype=x_dtype)
+    return out
+
+
+def splitk_sparse_gemv(x: torch.Tensor, weight: torch.Tensor, threshold: float, sparsity_bin: int = 0) -> torch.Tensor:
+    """Decode-time ``y = sparse(x) @ weight.T`` (name kept from kernels/sparse_gemv.py:87).
+    x [1,1,Z] fp16, weight logical [N,Z] with stride (1, ldw).  ``sparsity_bin`` is accepted and
+    ignored (it only keyed the reference's Triton autotune cache)."""
+    N, Z = weight.shape
+    x = _check_x(x, Z)
+    ldw = _check_w(weight)
+    xin = x if x.dtype is torch.float16 else x.to(torch.float16)
+    out = torch.empty(x.shape[0], x.shape[1], N, device=x.device, dtype=torch.float16)
+    sp = _stream_ptr()
+    ws = workspace(x.device, sp)
+    rc = _lib.load().teal_sparse_gemv_f16(xin.data_ptr(), weight.data_ptr(), out.data_ptr(), Z, N, ldw,
+                                          float(threshold), ws.data_ptr(), ws.numel(), sp)
+    _lib.check(rc, "teal_sparse_gemv_f16")
+    return _finish(out, x.dtype)
+
+
+def qkv_gemv(x: torch.Tensor, weight: torch.Tensor, threshold_q: float, threshold_k: float, threshold_v: float,
+             sparsity_bin: int, kv_size: int) -> torch.Tensor:
+    """Fused QKV decode GEMV with a threshold per output region (kernels/sparse_gemv.py:196-237)."""
+    N, Z = weight.shape
+    x = _check_x(x, Z)
+    ldw = _check_w(weight)
+    xin = x if x.dtype is torch.float16 else x.to(torch.float16)
+    out = torch.empty(x.shape[0], x.shape[1], N, device=x.device, dtype=torch.float16)
+    sp = _stream_ptr()
+    ws = workspace(x.device, sp)
+    rc = _lib.load().teal_sparse_qkv_gemv_f16(xin.data_ptr(), weight.data_ptr(), out.data_ptr(), Z, N, ldw,
+                                              int(kv_size), float(threshold_q), float(threshold_k),
+                                              float(threshold_v), ws.data_ptr(), ws.numel(), sp)
+    _lib.check(rc, "teal_sparse_qkv_gemv_f16")
+    return _finish(out, x.dtype)
+
+
+def sparse_gate_up(x: torch.Tensor, w1: torch.Tensor, w3: torch.Tensor, threshold_gate: float,
+                   threshold_up: float) -> torch.Tensor:
+    """``silu(gemv1(x, w1, t_gate)) * gemv1(x, w3, t_up)`` in one kernel (gpt-fast/model.py:259)."""
+    I, Z = w1.shape
+    assert w3.shape == w1.shape
+    x = _check_x(x, Z)
+    assert x.shape[1] == 1 and x.dtype is torch.float16
+    ld1, ld3 = _check_w(w1), _check_w(w3)
+    out = torch.empty(1, 1, I, device=x.device, dtype=torch.float16)
+    sp = _stream_ptr()
+    ws = workspace(x.device, sp)
+    rc = _lib.load().teal_sparse_gate_up_f16(x.data_ptr(), w1.data_ptr(), w3.data_ptr(), out.data_ptr(), Z, I,
+                                             ld1, ld3, float(threshold_gate), float(threshold_up),
+                                             ws.data_ptr(), ws.numel(), sp)
+    _lib.check(rc, "teal_sparse_gate_up_f16")
+    return out
+
+
+def survivors(x: torch.Tensor, threshold: float) -> torch.Tensor:
+    """Sorted surviving lane indices, computed by the device compaction code (parity hook)."""
+    xf = x.reshape(-1).contiguous()
+    assert xf.is_cuda and xf.dtype is torch.float16
+    idx = torch.empty(xf.numel(), dtype=torch.int32, device=x.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=x.device)
+    rc = _lib.load().teal_survivors_f16(xf.data_ptr(), xf.numel(), float(threshold), idx.data_ptr(), cnt.data_ptr(),
+                                        _stream_ptr())
+    _lib.check(rc, "teal_survivors_f16")
+    return idx[: int(cnt.item())]
+
+
+def sparse_gemv_simple(x: torch.Tensor, weight: torch.Tensor, threshold: float) -> torch.Tensor:
+    N, Z = weight.shape
+    x = _check_x(x, Z)
+    ldw = _check_w(weight)
+    out = torch.empty(1, 1, N, device=x.device, dtype=torch.float16)
+    rc = _lib.load().teal_sparse_gemv_f16_simple(x.data_ptr(), weight.data_ptr(), out.data_ptr(), Z, N, ldw,
+                                                 float(threshold), _stream_ptr())
+    _lib.check(rc, "teal_sparse_gemv_f16_simple")
+    return out
+
+
+def to_column_major(weight: torch.Tensor) -> torch.Tensor:
+    """``W.T.contiguous().T``: the re-layout gpt-fast/generate.py:296-317 applies to every sparse
+    projection (storage becomes [Z][N], N contiguous)."""
+    return weight.T.contiguous().T
+
+
+# ------------------------------------------------------------------------------------ op classes
+@dataclass
+class BaseKernel:
+    """Registration helper with the reference's public surface (compile_wrapper.py:124-208)."""
+    name: str
+    target: str
+    schema: str
+
+    SCHEMA = ""
+
+    @classmethod
+    def initialize(cls, name: str, target: str, **kwargs) -> "BaseKernel":
+        return cls(name, target, cls.schematize())
+
+    @classmethod
+    def schematize(cls) -> str:
+        return cls.SCHEMA
+
+    @property
+    def is_registered(self) -> bool:
+        return hasattr(getattr(torch.ops, NAMESPACE), self.name)
+
+    def operator(self, compiled: bool = False) -> Callable:
+        if compiled:
+            self.register()
+            return attrgetter(f"{NAMESPACE}.{self.name}")(torch.ops)
+        return self.forward
+
+    def meta(self, *args, **kwargs):
+        raise NotImplementedError(f"abstract implementation `meta` in {self.__class__.__name__} required for registration")
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(f"concrete implementation `forward` in {self.__class__.__name__} required for registration")
+
+    def register(self) -> None:
+        if not self.is_registered:
+            qualname = f"{NAMESPACE}::{self.name}"
+            torch.library.define(qualname, self.schema)
+            torch.library.register_fake(qualname, self.meta)
+            torch.library.impl(qualname, self.target, func=self.forward)
+
+
+class SparseGEMV(BaseKernel):
+    """kernels/sparse_gemv.py:249-271."""
+    SCHEMA = "(Tensor hidden_states, Tensor weights, float threshold, int sparsity_bin) -> Tensor"
+
+    def meta(self, hidden_states, weights, threshold, sparsity_bin):
+        return hidden_states.new_empty((hidden_states.size(0), hidden_states.size(1), weights.size(0)))
+
+    def forward(self, hidden_states, weights, threshold, sparsity_bin):
+        if hidden_states.shape[1] == 1:
+            return splitk_sparse_gemv(hidden_states, weights, threshold, sparsity_bin)
+        return torch.matmul(hidden_states, weights.T)  # prefill: dense, no sparsification
+
+
+class SparseQKVGEMV(BaseKernel):
+    """kernels/sparse_gemv.py:274-298."""
+    SCHEMA = ("(Tensor x, Tensor weight, float threshold_q, float threshold_k, float threshold_v, "
+              "int sparsity_bin, int kv_size) -> Tensor")
+
+    def meta(self, x, weight, threshold_q, threshold_k, threshold_v, sparsity_bin, kv_size):
+        return x.new_empty(x.shape[0], x.shape[1], weight.shape[0])
+
+    def forward(self, x, weight, threshold_q, threshold_k, threshold_v, sparsity_bin, kv_size):
+        if x.shape[1] == 1:
+            return qkv_gemv(x, weight, threshold_q, threshold_k, threshold_v, sparsity_bin, kv_size)
+        return torch.matmul(x, weight.T)
+
+
+def set_config(config_id: int) -> None:
+    """Benchmark knob: force a tile configuration (0 = default heuristic)."""
+    _lib.check(_lib.load().teal_set_config(int(config_id)), "teal_set_config")
