@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- decode tok/s, batch 1, Llama-3-8B-shaped random-init model at 50 % activation sparsity.
+
+One "step" = one decoded token through the whole hot path (160 fused sparse-GEMV launches +
+attention + lm_head + arg-max), replayed from one captured CUDA graph.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload llama-3-8b] [--sparsity 0.5]
+    python bench.py --impl reference ...      # the reference's CPU threshold+matmul (oracle port)
+
+Prints ONE JSON line (see README / DESIGN.md section 7 for the fields).  For N > 1 launch with
+torchrun; the model is tensor-parallel (gpt-fast/tp.py topology) => "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {"llama-3-8b": "llama-3-8b", "llama-2-7b": "7B", "mistral-7b": "Mistral-7B", "llama-2-70b": "70B",
+             "llama-3-70b": "llama-3-70b", "tiny": "tiny"}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference(args_model, sparsity, reps, threads=None):
+    """The reference's CPU path for this workload: SparsifyFn.apply + F.linear per projection
+    (utils/utils.py:51-52; it masks, it does not skip rows), timed on ONE layer + the lm_head and scaled
+    by the layer count.  Uses the oracle port (oracle/teal_oracle.py) -- the checker, never the product."""
+    import torch
+    from oracle import teal_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    a = args_model
+    kv = a.n_local_heads * a.head_dim
+    g = torch.Generator().manual_seed(0)
+    shapes = {"qkv": (a.dim + 2 * kv, a.dim), "o": (a.dim, a.dim), "gate": (a.intermediate_size, a.dim),
+              "up": (a.intermediate_size, a.dim), "down": (a.dim, a.intermediate_size)}
+    W = {k: (torch.randn(n, z, generator=g) * 0.02).half() for k, (n, z) in shapes.items()}
+    lm = (torch.randn(a.vocab_size, a.dim, generator=g) * 0.02).half()
+    x = torch.randn(1, 1, a.dim, generator=g).half()
+    h = torch.randn(1, 1, a.intermediate_size, generator=g).half()
+    tx = float(x.abs().float().flatten().kthvalue(max(1, int(a.dim * sparsity))).values)
+    th = float(h.abs().float().flatten().kthvalue(max(1, int(a.intermediate_size * sparsity))).values)
+
+    def layer_once():
+        O.qkv_sparse_linear(x, W["qkv"], tx, tx, tx, kv)
+        O.sparse_linear(x, W["o"], tx)
+        O.sparse_linear(torch.nn.functional.silu(O.sparse_linear(x, W["gate"], tx)) * O.sparse_linear(x, W["up"], tx),
+                        W["down"], th)
+
+    layer_once()
+    torch.nn.functional.linear(x, lm)
+    per_step = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        layer_once()
+        t1 = time.perf_counter()
+        torch.nn.functional.linear(x, lm)
+        t2 = time.perf_counter()
+        per_step.append((t1 - t0) * a.n_layer + (t2 - t1))
+    per_step.sort()
+    sec = per_step[len(per_step) // 2]
+    return {"value": 1.0 / sec, "unit": "tok/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{reps} x (one layer: qkv,o,gate,up,down threshold+F.linear fp16) x {a.n_layer} layers + lm_head, "
+                      f"median; reference CPU path masks then runs the dense matmul"}, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="teal_b200", choices=["teal_b200", "reference"])
+    ap.add_argument("--workload", default="llama-3-8b", choices=sorted(WORKLOADS))
+    ap.add_argument("--sparsity", type=float, default=0.5)
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense baselines")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", type=int, default=0, help="teal_set_config id (tuning)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    from teal_b200.model import ModelArgs
+    margs = ModelArgs.from_name(WORKLOADS[args.workload])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = f"decode tok/s batch=1 {args.workload} @{int(args.sparsity * 100)}% sparsity"
+    config = {"workload": f"{args.workload} full decode step (random-init fp16, synthetic-calibrated thresholds)",
+              "sparsity": args.sparsity, "context": "positions 0..steps (short context, generate.py:171)",
+              "sampling": "greedy", "parallelism": f"tp{world}" if world > 1 else "single",
+              "l2": "weights (>= 8 GB per GPU) far exceed the 126 MB L2; every step streams them from HBM"}
+
+    # ------------------------------------------------------------------ reference arm: CPU threshold+matmul
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        reps = max(1, min(args.steps, 8))
+        base, sec = cpu_reference(margs, args.sparsity, reps)
+        for _ in range(min(args.warmup, 1)):
+            pass
+        line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": "tok/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+        pg = dist.group.WORLD
+    from teal_b200 import ops
+    from teal_b200.model import SparseDecoder
+    ops.set_config(args.config)
+    K, Wm = args.steps, args.warmup
+    max_seq = max(256, K + Wm + 16)
+    dec = SparseDecoder(margs, device=f"cuda:{local_rank}", max_seq=max_seq, rank=rank, world=world, process_group=pg,
+                        out_cap=max_seq)
+    thr = dec.calibrate(args.sparsity, n_tokens=8)
+    lib = dec.lib
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(mode, steps, warmup, e2e=False):
+        dec.capture(mode)
+        dec.reset(1)
+        host_in = torch.ones(1, dtype=torch.int32).pin_memory()
+        host_out = torch.zeros(1, dtype=torch.int32).pin_memory()
+        with torch.cuda.stream(dec.stream):
+            for _ in range(warmup):
+                dec.graph.replay()
+            dec.stream.synchronize()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_wall = time.perf_counter()
+            e0.record(dec.stream)
+            for _ in range(steps):
+                if e2e:  # public-API loop: token H2D from pinned memory, step, sampled token D2H
+                    dec.token.copy_(host_in, non_blocking=True)
+                    dec.graph.replay()
+                    host_out.copy_(dec.token, non_blocking=True)
+                    dec.stream.synchronize()
+                    host_in.copy_(host_out)
+                else:
+                    dec.graph.replay()
+            e1.record(dec.stream)
+            dec.stream.synchronize()
+            wall = time.perf_counter() - t_wall
+            barrier()
+        ms = e0.elapsed_time(e1)
+        if e2e:
+            ms = max(ms, wall * 1e3)
+        if world > 1:
+            t = torch.tensor([ms], device=dec.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+    probe = torch.zeros(2, dtype=torch.int64, device=dec.dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step = timed("sparse", K, Wm)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed("sparse", K, Wm, e2e=True)
+    kernels_per_step = dec.kernels_per_step
+    launches = kernels_per_step * K
+
+    # measured kept fraction / algorithmic bytes of one step (eager, outside the timed region)
+    lib.teal_set_bytes_probe(probe.data_ptr())
+    dec.reset(1)
+    for _ in range(4):
+        dec._enqueue_step("sparse")
+    torch.cuda.synchronize()
+    lib.teal_set_bytes_probe(None)
+    gathered, dense_eq = (int(v) / 4 for v in probe.tolist())
+    layer_bytes, head_bytes = dec.weight_bytes()
+
+    dense = {}
+    if not args.no_dense:
+        for mode in ("dense_own", "dense_cublas"):
+            try:
+                dense[mode] = 1e3 / timed(mode, max(16, K // 2), 4)
+            except Exception as e:  # keep the headline even if a baseline variant fails
+                dense[mode] = None
+                if rank == 0:
+                    print(f"[bench] {mode} failed: {e}", file=sys.stderr)
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    # fused RMSNorm + gate/up gather-GEMV + SiLU*mul, timed alone with CUDA events on the launching stream,
+    # rotating over all layers' weights (n_layer x ~117 MB >> L2) with the decoder's real activations.
+    peak, peak_kind = measured_peak()
+    a = margs
+    rf = None
+    if rank == 0:
+        ws = ops.workspace(dec.dev, dec.stream.cuda_stream)
+        probe.zero_()
+        t_l = [t for t in thr]
+        reps = max(1, 96 // a.n_layer)
+        with torch.cuda.stream(dec.stream):
+            def gate_up_all():
+                for li, Wl in enumerate(dec.layers):
+                    lib.teal_norm_sparse_gate_up_f16(dec.x.data_ptr(), Wl["ffn_norm"].data_ptr(), a.norm_eps,
+                                                     Wl["w1"].data_ptr(), Wl["w3"].data_ptr(), dec.h.data_ptr(), None,
+                                                     a.dim, dec.inter_l, Wl["w1"].stride(1), Wl["w3"].stride(1),
+                                                     t_l[li]["gate"], t_l[li]["up"], ws.data_ptr(), ws.numel(),
+                                                     dec.stream.cuda_stream)
+            gate_up_all()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=dec.stream):
+                gate_up_all()
+            lib.teal_set_bytes_probe(probe.data_ptr())
+            gate_up_all()
+            dec.stream.synchronize()
+            lib.teal_set_bytes_probe(None)
+            for _ in range(2):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(dec.stream)
+            for _ in range(reps):
+                g.replay()
+            e1.record(dec.stream)
+            dec.stream.synchronize()
+        n_l = reps * a.n_layer
+        us = e0.elapsed_time(e1) * 1e3 / n_l
+        alg = int(probe[0]) / a.n_layer + a.dim * 2 + dec.inter_l * 2  # gathered rows + x + h per launch
+        rf = {"bound": "hbm", "kernel": "gather_gemv_kernel (fused RMSNorm + gate/up + SiLU*mul)", "achieved": alg / us / 1e3,
+              "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": None, "peak_kind": f"of {peak_kind}",
+              "us_per_launch": us, "alg_bytes_per_launch": alg, "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),
+              "timing": "CUDA events on the launching stream, graph of n_layer launches over distinct weights (L2 defeated)"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            cpu, _ = cpu_reference(margs, args.sparsity, 3)
+        except Exception as e:
+            cpu = {"value": None, "unit": "tok/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        tok_s = 1e3 / ms_step
+        best_dense = max([v for v in dense.values() if v] or [0.0])
+        step_bytes = gathered + head_bytes  # algorithmic weight bytes of one token on this rank
+        line = {"metric": metric, "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic", "config": config,
+                "e2e": {"value": 1e3 / ms_e2e, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "clocks": clocks, "roofline": rf, "cpu_baseline": cpu,
+                "dense_tok_s": dense, "speedup_vs_dense": (tok_s / best_dense) if best_dense else None,
+                "kept_fraction": gathered / max(1.0, dense_eq),
+                "step_weight_bytes": step_bytes, "step_hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                "kernels_per_step": kernels_per_step}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

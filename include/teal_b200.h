@@ -81,6 +81,46 @@ int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, voi
                             double threshold_up, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+/* ---- fused variants used by the decode pipeline (one launch per projection group) ---------------
+ * RMSNorm (gpt-fast/model.py:286-291: fp32 norm, fp16 cast, fp16 multiply by norm_w) of the fp16
+ * residual stream x is computed in the kernel prologue, then thresholded; `xn_out` (nullable)
+ * receives the normalised vector.  Replaces attention_norm + gemv1 (model.py:159,168) ... */
+int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps, const void* wt,
+                                  void* y, void* xn_out, int Z, int N, int64_t ldw, int kv_size,
+                                  double threshold_q, double threshold_k, double threshold_v,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+/* ... ffn_norm + gemv1(gate) + gemv1(up) + SiLU*mul (model.py:161,259) ... */
+int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, const void* w1t,
+                                 const void* w3t, void* h, void* xn_out, int Z, int I, int64_t ldw1,
+                                 int64_t ldw3, double threshold_gate, double threshold_up,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+/* ... and gemv2 + residual add: y = resid + fp16(sparse_gemv(x, wt)) in fp16
+ * (model.py:160-161,188,259).  y may alias resid. */
+int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y, int Z,
+                                  int N, int64_t ldw, double threshold, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
+/* ---- the rest of one batch-1 decode step -----------------------------
+ * All of them read the token / position from device memory so a captured CUDA graph replays for
+ * every token.
+ * x[dim] = tok_embeddings[*token]  (gpt-fast/model.py:137). */
+int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, int dim, void* stream);
+/* RoPE(q, k) with the fp16 (cos, sin) table freqs_cis[max_seq][head_dim/2][2], KV-cache append at
+ * *pos, attention of the one query token over positions [0, *pos], heads concatenated
+ * (gpt-fast/model.py:170-186).  qkv: fp16 [n_head*hd | n_kv*hd | n_kv*hd]; caches fp16
+ * [n_kv][max_seq][hd] (the reference's [1, H_kv, S, D], model.py:84); out: fp16 [n_head*hd]. */
+int teal_attn_decode_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache,
+                         const int32_t* pos, void* out, int n_head, int n_kv_head, int head_dim,
+                         int max_seq, void* stream);
+/* Dense row-major GEMV y[v] = sum_z w[v][z] * xn[z] for the never-sparsified lm_head
+ * (gpt-fast/model.py:141-142); xn = RMSNorm(x) with norm_w when norm_w != NULL, else x.
+ * argmax_packed (nullable, uint64[1], zero before the call) receives the packed arg-max. */
+int teal_dense_gemv_f16(const void* x, const void* norm_w, double eps, const void* w, void* y,
+                        void* argmax_packed, int Z, int V, int64_t ldw, void* stream);
+/* Greedy step bookkeeping: *token = arg-max index, out_tokens[*pos] = *token, ++*pos, reset cell. */
+int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap,
+                 void* stream);
+
 /* Survivor set of one threshold, produced by the same device code the GEMV kernels use
  * (parity hook: "surviving-index set bit-exact").  idx_out: int32[Z] (sorted ascending, first
  * *count_out entries valid), count_out: int32[1].  Both device pointers. */
@@ -92,8 +132,17 @@ int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out,
 int teal_sparse_gemv_f16_simple(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw,
                                 double threshold, void* stream);
 
-/* Tuning knob for benchmarks: selects the tile configuration (0 = library default per shape). */
+/* Tuning knob for benchmarks: 0 = library default (gather_gemv, cp.async per-warp rings);
+ * 1..6 = TMA-bulk-ring variants; 10+T = gather_gemv with T column tiles per matrix. */
 int teal_set_config(int config_id);
+
+/* Launch the GEMV kernels with programmatic dependent launch (prologue overlaps the previous
+ * kernel's tail).  Off by default; the decode pipeline switches it on. */
+int teal_set_pdl(int enabled);
+
+/* Measurement hook: when non-null (device uint64[2]) every sparse GEMV launch adds its gathered
+ * weight bytes (nnz * N * 2) to [0] and the dense equivalent (Z * N * 2) to [1]. */
+int teal_set_bytes_probe(void* device_u64x2);
 
 /* Profiling hook: when non-null, every CTA of the GEMV kernels writes 16 int64 phase timestamps
  * (clock64 / globaltimer) to device_buf[blockIdx.x * 16 ...]; pass NULL to switch it off. */

@@ -30,10 +30,27 @@ _SIGS = {
     "teal_sparse_gate_up_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                            _c.c_int64, _c.c_int64, _c.c_double, _c.c_double, _c.c_void_p,
                                            _c.c_size_t, _c.c_void_p]),
+    "teal_norm_sparse_qkv_gemv_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p,
+                                                 _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_double,
+                                                 _c.c_double, _c.c_double, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "teal_norm_sparse_gate_up_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p,
+                                                _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64,
+                                                _c.c_double, _c.c_double, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "teal_sparse_gemv_residual_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                                 _c.c_int, _c.c_int64, _c.c_double, _c.c_void_p, _c.c_size_t,
+                                                 _c.c_void_p]),
+    "teal_embed_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "teal_attn_decode_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                        _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "teal_dense_gemv_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                       _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p]),
+    "teal_advance": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "teal_survivors_f16": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "teal_sparse_gemv_f16_simple": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                                _c.c_int64, _c.c_double, _c.c_void_p]),
     "teal_set_config": (_c.c_int, [_c.c_int]),
+    "teal_set_pdl": (_c.c_int, [_c.c_int]),
+    "teal_set_bytes_probe": (_c.c_int, [_c.c_void_p]),
     "teal_set_debug_timestamps": (_c.c_int, [_c.c_void_p]),
 }
 

@@ -83,6 +83,14 @@ int teal_workspace_init(void* workspace, size_t workspace_bytes_, void* stream) 
 }
 
 int teal_set_config(int config_id) { return set_config(config_id); }
+int teal_set_bytes_probe(void* device_u64x2) {
+  set_bytes_probe(reinterpret_cast<unsigned long long*>(device_u64x2));
+  return TEAL_OK;
+}
+int teal_set_pdl(int enabled) {
+  set_pdl(enabled != 0);
+  return TEAL_OK;
+}
 int teal_set_debug_timestamps(void* device_buf) {
   set_debug_timestamps(reinterpret_cast<long long*>(device_buf));
   return TEAL_OK;
@@ -100,7 +108,7 @@ int teal_sparse_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, i
   p.seg[0].ncols = N;
   p.seg[0].out_col0 = 0;
   p.seg[0].thr_slot = slot_for(p, round_threshold_fp16(threshold));
-  return launch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_sparse_qkv_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, int kv_size,
@@ -128,7 +136,7 @@ int teal_sparse_qkv_gemv_f16(const void* x, const void* wt, void* y, int Z, int 
       c0 += cols[r];
     }
   }
-  return launch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, void* h, int Z, int I, int64_t ldw1,
@@ -141,7 +149,97 @@ int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, voi
   p.nseg = 2;
   p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
   p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, slot_for(p, round_threshold_fp16(threshold_up)), 0, 0, 0};
-  return launch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- fused variants used by the decode pipeline --------------------------------------------------
+int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps, const void* wt, void* y, void* xn_out,
+                                  int Z, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
+                                  double threshold_v, void* workspace, size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, y, Z)) return rc;
+  if (!wt || !y || !norm_w || N <= 0 || ldw < N || kv_size < 0 || 2 * (int64_t)kv_size > N)
+    return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / norm_w / N / ldw / kv_size");
+  const int n_q = N - 2 * kv_size;
+  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k),
+              tv = round_threshold_fp16(threshold_v);
+  p.mode = kModePlain;
+  p.in_mode = kInRmsNorm;
+  p.norm_w = reinterpret_cast<const __half*>(norm_w);
+  p.eps = (float)eps;
+  p.x_out = reinterpret_cast<__half*>(xn_out);
+  const __half* w = reinterpret_cast<const __half*>(wt);
+  if (tq == tk && tk == tv) {
+    p.nseg = 1;
+    p.seg[0] = GemvSeg{w, ldw, N, 0, slot_for(p, tq), 0, 0, 0};
+  } else {
+    const int cols[3] = {n_q, kv_size, kv_size};
+    const float thr[3] = {tq, tk, tv};
+    int c0 = 0;
+    for (int r = 0; r < 3; ++r) {
+      if (cols[r] == 0) continue;
+      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, slot_for(p, thr[r]), 0, 0, 0};
+      c0 += cols[r];
+    }
+  }
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, const void* w1t, const void* w3t,
+                                 void* h, void* xn_out, int Z, int I, int64_t ldw1, int64_t ldw3,
+                                 double threshold_gate, double threshold_up, void* workspace,
+                                 size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, h, Z)) return rc;
+  if (!w1t || !w3t || !h || !norm_w || I <= 0 || ldw1 < I || ldw3 < I)
+    return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / h / norm_w / I / ldw");
+  p.mode = kModePairSilu;
+  p.in_mode = kInRmsNorm;
+  p.norm_w = reinterpret_cast<const __half*>(norm_w);
+  p.eps = (float)eps;
+  p.x_out = reinterpret_cast<__half*>(xn_out);
+  p.nseg = 2;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
+  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, slot_for(p, round_threshold_fp16(threshold_up)), 0, 0, 0};
+  return dispatch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y, int Z, int N,
+                                  int64_t ldw, double threshold, void* workspace, size_t workspace_bytes_,
+                                  void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, y, Z)) return rc;
+  if (!wt || !y || !resid || N <= 0 || ldw < N) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw");
+  p.mode = kModePlain;
+  p.out_mode = kOutAddResidual;
+  p.resid = reinterpret_cast<const __half*>(resid);
+  p.nseg = 1;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- the rest of the decode step -------------------------------------------------------------------
+int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, int dim, void* stream) {
+  return launch_embed(reinterpret_cast<const __half*>(tok_embeddings), token, reinterpret_cast<__half*>(x), dim,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+int teal_attn_decode_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos,
+                         void* out, int n_head, int n_kv_head, int head_dim, int max_seq, void* stream) {
+  return launch_attn_decode(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(freqs_cis),
+                            reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), pos,
+                            reinterpret_cast<__half*>(out), n_head, n_kv_head, head_dim, max_seq,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+int teal_dense_gemv_f16(const void* x, const void* norm_w, double eps, const void* w, void* y, void* argmax_packed,
+                        int Z, int V, int64_t ldw, void* stream) {
+  return launch_dense_rowmajor(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(norm_w), (float)eps,
+                               reinterpret_cast<const __half*>(w), reinterpret_cast<__half*>(y),
+                               reinterpret_cast<unsigned long long*>(argmax_packed), Z, V, ldw,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap, void* stream) {
+  return launch_advance(reinterpret_cast<unsigned long long*>(argmax_packed), token, pos, out_tokens, out_cap,
+                        reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out, int32_t* count_out, void* stream) {
@@ -154,7 +252,7 @@ int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out,
   slot_for(p, round_threshold_fp16(threshold));
   p.dbg_idx = idx_out;
   p.dbg_cnt = count_out;
-  return launch_gemv(p, nullptr, 0, 0, reinterpret_cast<cudaStream_t>(stream));
+  return dispatch_gemv(p, nullptr, 0, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_sparse_gemv_f16_simple(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, double threshold,

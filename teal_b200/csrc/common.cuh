@@ -18,6 +18,8 @@ constexpr int kMaxPieces = 8;
 constexpr int kMaxCounters = 4096;                // column tiles per call
 
 enum { kModePlain = 0, kModePairSilu = 1, kModeSurvivors = 2 };
+enum { kInPlain = 0, kInRmsNorm = 1 };        // how x is produced from the input vector
+enum { kOutPlain = 0, kOutAddResidual = 1 };  // what the finaliser adds before writing fp16
 
 struct GemvSeg {
   const __half* w;   // fp16 [Z][ldw], first column of the region
@@ -38,10 +40,54 @@ struct GemvParams {
   int* dbg_idx;
   int* dbg_cnt;
   long long* dbg_time;  // optional [grid][16] phase timestamps (profiling builds of the bench tools)
+  const __half* norm_w;  // RMSNorm weight (kInRmsNorm)
+  const __half* resid;   // residual stream added in the epilogue (kOutAddResidual)
+  __half* x_out;         // optional: the (normalised) x actually consumed
   int Z, nseg, nthr, mode;
   int nstages, list_cap, chunk, xs_elems;
+  int in_mode, out_mode;
+  float eps;
+  int tile_n, sub_n, cg, rg;  // gather_gemv tiling (filled by its launcher)
   float thr[kMaxThr];  // fp16-representable thresholds
   GemvSeg seg[kMaxSeg];
+};
+
+// ---- gather_gemv (cp.async per-warp rings) ------------------------------------------------------
+constexpr int kMaxTiles = 16;
+
+struct GatherTile {
+  const __half* w;   // fp16 [Z][ldw], first column of the tile
+  long long ldw;
+  int width;         // columns (multiple of 8)
+  int acc_col0;      // first column in the fp32 accumulator
+  int y_col0;        // first column in y / resid
+  int gate_acc0;     // pair mode: accumulator columns of the gate / up halves of this tile
+  int up_acc0;
+  int thr_slot;
+  int cta0, nctas;   // CTAs [cta0, cta0 + nctas) split this tile's survivor list evenly
+  unsigned magic;    // ceil(2^32 / nctas), 0 when nctas == 1
+  int cidx, target;  // completion counter and the arrival count that completes it
+  int pad;
+};
+
+struct GatherParams {
+  const __half* x;
+  __half* y;
+  float* acc;
+  unsigned* counters;
+  const __half* norm_w;
+  const __half* resid;
+  __half* x_out;
+  int* dbg_idx;
+  int* dbg_cnt;
+  long long* dbg_time;
+  unsigned long long* probe;  // optional [2]: gathered / dense weight bytes, accumulated
+  int Z, mode, in_mode, out_mode;
+  int ntiles, tile_n, sub_n, cg, rg;
+  int chunk, list_cap, region_bytes;
+  float eps;
+  float thr[kMaxThr];
+  GatherTile tile[kMaxTiles];
 };
 
 // ---------------------------------------------------------------------------------- host
@@ -58,9 +104,27 @@ float round_threshold_fp16(double t);
 size_t workspace_bytes(int max_out_cols);
 int set_config(int id);
 void set_debug_timestamps(long long* buf);
+long long* debug_timestamps();
+int forced_config();
+void set_pdl(bool on);
+bool pdl_enabled();
+int sub_cols_override();
+void set_bytes_probe(unsigned long long* p);
+unsigned long long* bytes_probe();
+int launch_gather_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream,
+                       int tiles_per_matrix);
+int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream);
 int launch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream);
 int launch_simple(const __half* x, const __half* wt, __half* y, int Z, int N, long long ldw, float thr,
                   cudaStream_t stream);
+
+int launch_embed(const __half* emb, const int* token, __half* x, int dim, cudaStream_t stream);
+int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,
+                       __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream);
+int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,
+                          unsigned long long* argmax_packed, int Z, int V, long long ldw, cudaStream_t stream);
+int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap,
+                   cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------- device
 #ifdef __CUDACC__

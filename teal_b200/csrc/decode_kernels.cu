@@ -1,0 +1,349 @@
+// The rest of one batch-1 decode step around the sparse GEMVs:
+// token embedding, RoPE + KV-append + decode attention, dense lm_head GEMV with the final RMSNorm
+// fused in and a fused arg-max, and the step bookkeeping.  Reference: gpt-fast/model.py:133-190,
+// 286-318 and generate.py:49-77.  All kernels read the position / token from device memory so
+// that one captured CUDA graph can be replayed for every token.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace teal {
+
+// --------------------------------------------------------------------------------------------
+// x[dim] = tok_embeddings[token]            (gpt-fast/model.py:137)
+// --------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const __half* __restrict__ emb, const int* __restrict__ token, __half* __restrict__ x,
+                             int dim) {
+  griddep_wait();
+  const int t = token[0];
+  const uint4* src = reinterpret_cast<const uint4*>(emb + (size_t)t * dim);
+  uint4* dst = reinterpret_cast<uint4*>(x);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim / 8; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  griddep_launch_dependents();
+}
+
+// --------------------------------------------------------------------------------------------
+// RoPE(q, k) + KV-cache append + attention of one query token over positions [0, pos].
+// gpt-fast/model.py:170-186: adjacent-pair rotation with the fp16 (cos, sin) table, KVCache.update,
+// GQA (kv head = q head / rep), scaled dot product attention, heads concatenated.
+// grid = n_head CTAs (one per query head), block = kAttnThreads.
+// --------------------------------------------------------------------------------------------
+constexpr int kAttnThreads = 256;
+constexpr int kAttnWarps = kAttnThreads / 32;
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
+    const __half* __restrict__ qkv,    // [n_head*HD | n_kv*HD | n_kv*HD]
+    const __half* __restrict__ freqs,  // [max_seq][HD/2][2] fp16 (cos, sin)
+    __half* __restrict__ k_cache,      // [n_kv][max_seq][HD]
+    __half* __restrict__ v_cache, const int* __restrict__ pos_ptr, __half* __restrict__ out,  // [n_head*HD]
+    int n_head, int n_kv, int max_seq, float scale) {
+  static_assert(HD % 64 == 0 && HD <= 256, "head_dim");
+  constexpr int EPL = HD / 32;  // elements per lane (4 for HD = 128)
+  __shared__ float s_q[HD];
+  __shared__ float s_knew[HD];
+  __shared__ float s_vnew[HD];
+  __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
+  __shared__ float s_acc[kAttnWarps][HD];
+
+  const int h = blockIdx.x;
+  const int kvh = h / (n_head / n_kv);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  griddep_wait();
+  const int pos = pos_ptr[0];
+
+  // ---- RoPE on q (this head) and on the new k (its kv head); v passes through ---------------------
+  const __half* qh = qkv + (size_t)h * HD;
+  const __half* kh = qkv + (size_t)n_head * HD + (size_t)kvh * HD;
+  const __half* vh = qkv + (size_t)(n_head + n_kv) * HD + (size_t)kvh * HD;
+  const __half* fr = freqs + (size_t)pos * HD;  // HD/2 pairs * 2
+  if (tid < HD / 2) {
+    const float c = __half2float(fr[2 * tid]), s = __half2float(fr[2 * tid + 1]);
+    const float q0 = __half2float(qh[2 * tid]), q1 = __half2float(qh[2 * tid + 1]);
+    const float k0 = __half2float(kh[2 * tid]), k1 = __half2float(kh[2 * tid + 1]);
+    // model.py:309-315, result cast back to fp16 (type_as)
+    const __half qa = __float2half_rn(q0 * c - q1 * s), qb = __float2half_rn(q1 * c + q0 * s);
+    const __half ka = __float2half_rn(k0 * c - k1 * s), kb = __float2half_rn(k1 * c + k0 * s);
+    s_q[2 * tid] = __half2float(qa);
+    s_q[2 * tid + 1] = __half2float(qb);
+    s_knew[2 * tid] = __half2float(ka);
+    s_knew[2 * tid + 1] = __half2float(kb);
+    if (h % (n_head / n_kv) == 0) {  // one CTA per kv head appends to the cache (model.py:93-94)
+      k_cache[((size_t)kvh * max_seq + pos) * HD + 2 * tid] = ka;
+      k_cache[((size_t)kvh * max_seq + pos) * HD + 2 * tid + 1] = kb;
+    }
+  } else if (tid < HD / 2 + HD / 2) {
+    const int i = tid - HD / 2;
+    const __half v0 = vh[2 * i], v1 = vh[2 * i + 1];
+    s_vnew[2 * i] = __half2float(v0);
+    s_vnew[2 * i + 1] = __half2float(v1);
+    if (h % (n_head / n_kv) == 0) {
+      v_cache[((size_t)kvh * max_seq + pos) * HD + 2 * i] = v0;
+      v_cache[((size_t)kvh * max_seq + pos) * HD + 2 * i + 1] = v1;
+    }
+  }
+  __syncthreads();
+
+  // ---- online-softmax attention: warp w takes positions w, w + kAttnWarps, ... ---------------------
+  float qreg[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) qreg[e] = s_q[lane * EPL + e];
+  float m = -CUDART_INF_F, l = 0.f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  const __half* kbase = k_cache + (size_t)kvh * max_seq * HD;
+  const __half* vbase = v_cache + (size_t)kvh * max_seq * HD;
+  for (int p = warp; p <= pos; p += kAttnWarps) {
+    float kk[EPL], vv[EPL];
+    if (p == pos) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) { kk[e] = s_knew[lane * EPL + e]; vv[e] = s_vnew[lane * EPL + e]; }
+    } else {
+      const __half2* kp = reinterpret_cast<const __half2*>(kbase + (size_t)p * HD + lane * EPL);
+      const __half2* vp = reinterpret_cast<const __half2*>(vbase + (size_t)p * HD + lane * EPL);
+#pragma unroll
+      for (int e = 0; e < EPL / 2; ++e) {
+        const float2 kf = __half22float2(kp[e]), vf = __half22float2(vp[e]);
+        kk[2 * e] = kf.x; kk[2 * e + 1] = kf.y;
+        vv[2 * e] = vf.x; vv[2 * e + 1] = vf.y;
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) s = fmaf(qreg[e], kk[e], s);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    s *= scale;
+    const float mn = fmaxf(m, s);
+    const float corr = __expf(m - mn), pe = __expf(s - mn);
+    l = l * corr + pe;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pe, vv[e], acc[e] * corr);
+    m = mn;
+  }
+  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) s_acc[warp][lane * EPL + e] = acc[e];
+  __syncthreads();
+  // ---- merge the warps' partial softmaxes ---------------------------------------------------------
+  if (tid < HD) {
+    float M = -CUDART_INF_F;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, s_m[w]);
+    float L = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float f = (s_m[w] == -CUDART_INF_F) ? 0.f : __expf(s_m[w] - M);
+      L = fmaf(s_l[w], f, L);
+      o = fmaf(s_acc[w][tid], f, o);
+    }
+    out[(size_t)h * HD + tid] = __float2half_rn(o / L);
+  }
+  griddep_launch_dependents();
+}
+
+// --------------------------------------------------------------------------------------------
+// Dense row-major GEMV for the (never sparsified) lm_head, gpt-fast/model.py:141-142:
+//   logits[v] = sum_z W[v][z] * rmsnorm(x)[z]
+// with the final RMSNorm in the prologue and a fused arg-max (packed 64-bit atomicMax).
+// One warp per output row, 16 B per lane per load, warp-shuffle reduction.
+// --------------------------------------------------------------------------------------------
+constexpr int kHeadThreads = 512;
+
+__device__ __forceinline__ unsigned long long pack_argmax(float v, int idx) {
+  unsigned b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // monotonic map float -> unsigned
+  return ((unsigned long long)b << 32) | (unsigned long long)(0xffffffffu - (unsigned)idx);  // ties -> smallest index
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(kHeadThreads, 2) dense_rowmajor_gemv_kernel(
+    const __half* __restrict__ x, const __half* __restrict__ norm_w, float eps, const __half* __restrict__ W,
+    __half* __restrict__ y, unsigned long long* __restrict__ argmax_packed, int Z, int V, long long ldw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* xs = reinterpret_cast<__half*>(smem_raw);  // normalised x, Z halves
+  __shared__ float s_part[kHeadThreads / 32];
+  __shared__ unsigned long long s_best[kHeadThreads / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarps = kHeadThreads / 32;
+  griddep_wait();
+  // ---- prologue: RMSNorm (model.py:286-291) or plain copy ------------------------------------------
+  float ss = 0.f;
+  for (int m = tid * 8; m < Z; m += kHeadThreads * 8) {
+    uint4 v = ld_nc_u4(reinterpret_cast<const uint4*>(x + m));
+    *reinterpret_cast<uint4*>(xs + m) = v;
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(h2[j]);
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+    }
+  }
+  if (norm_w) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    if (lane == 0) s_part[warp] = ss;
+    __syncthreads();
+    float tot = (lane < kWarps) ? s_part[lane] : 0.f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+    const float rs = rsqrtf(tot / (float)Z + eps);
+    for (int m = tid * 8; m < Z; m += kHeadThreads * 8) {
+      uint4 v = *reinterpret_cast<uint4*>(xs + m);
+      uint4 g = ld_nc_u4(reinterpret_cast<const uint4*>(norm_w + m));
+      __half2* h2 = reinterpret_cast<__half2*>(&v);
+      const __half2* g2 = reinterpret_cast<const __half2*>(&g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(h2[j]);
+        h2[j] = __hmul2(__floats2half2_rn(f.x * rs, f.y * rs), g2[j]);
+      }
+      *reinterpret_cast<uint4*>(xs + m) = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- rows: warp gw takes rows gw, gw + total_warps, ... ------------------------------------------
+  const int total_warps = gridDim.x * kWarps;
+  unsigned long long best = 0ull;
+  const int nvec = Z >> 3;  // 16-byte vectors per row
+  for (int v = blockIdx.x * kWarps + warp; v < V; v += total_warps) {
+    const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)v * ldw);
+    float acc = 0.f;
+    for (int c0 = lane; c0 < nvec; c0 += 32 * UNROLL) {
+      uint4 wv[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int c = c0 + 32 * u;
+        wv[u] = (c < nvec) ? ld_nc_u4(wr + c) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < nvec) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(xs + c * 8);
+          const __half2* w2 = reinterpret_cast<const __half2*>(&wv[u]);
+          const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 wf = __half22float2(w2[j]), xf = __half22float2(x2[j]);
+            acc = fmaf(wf.x, xf.x, acc);
+            acc = fmaf(wf.y, xf.y, acc);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) {
+      const __half r = __float2half_rn(acc);
+      y[v] = r;
+      const unsigned long long pk = pack_argmax(__half2float(r), v);
+      best = pk > best ? pk : best;
+    }
+  }
+  if (argmax_packed) {
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long b = 0ull;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) b = s_best[w] > b ? s_best[w] : b;
+      if (b) atomicMax(argmax_packed, b);
+    }
+  }
+  griddep_launch_dependents();
+}
+
+// --------------------------------------------------------------------------------------------
+// Step bookkeeping: next token = arg-max (greedy; reference sample() with temperature -> 0,
+// generate.py:49-66), append to the output, advance the position, reset the arg-max cell.
+// --------------------------------------------------------------------------------------------
+__global__ void advance_kernel(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap) {
+  griddep_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long pk = *argmax_packed;
+    const int t = (int)(0xffffffffu - (unsigned)(pk & 0xffffffffull));
+    const int p = pos[0];
+    token[0] = t;
+    if (p < out_cap) out_tokens[p] = t;
+    pos[0] = p + 1;
+    *argmax_packed = 0ull;
+  }
+  griddep_launch_dependents();
+}
+
+// ---------------------------------------------------------------------------------- launchers
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const char* what,
+                      Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) return set_cuda_error(e, what);
+  return TEAL_OK;
+}
+
+int launch_embed(const __half* emb, const int* token, __half* x, int dim, cudaStream_t stream) {
+  if (!emb || !token || !x || dim <= 0 || (dim & 7)) return set_error(TEAL_ERR_BAD_ARG, "embed: bad argument");
+  return launch_pdl(embed_kernel, dim3(1), dim3(256), 0, stream, "embed launch", emb, token, x, dim);
+}
+
+int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,
+                       __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream) {
+  if (!qkv || !freqs || !k_cache || !v_cache || !pos || !out || n_head <= 0 || n_kv <= 0 || n_head % n_kv)
+    return set_error(TEAL_ERR_BAD_ARG, "attn_decode: bad argument");
+  const float scale = 1.0f / sqrtf((float)head_dim);
+  if (head_dim == 128)
+    return launch_pdl(attn_decode_kernel<128>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, freqs,
+                      k_cache, v_cache, pos, out, n_head, n_kv, max_seq, scale);
+  if (head_dim == 64)
+    return launch_pdl(attn_decode_kernel<64>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, freqs,
+                      k_cache, v_cache, pos, out, n_head, n_kv, max_seq, scale);
+  return set_error(TEAL_ERR_UNSUPPORTED, "attn_decode: head_dim must be 64 or 128");
+}
+
+int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,
+                          unsigned long long* argmax_packed, int Z, int V, long long ldw, cudaStream_t stream) {
+  if (!x || !W || !y || Z <= 0 || V <= 0 || (Z & 7) || (ldw & 7) || ldw < Z)
+    return set_error(TEAL_ERR_BAD_ARG, "dense gemv: bad argument");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return set_error(TEAL_ERR_ALIGNMENT, "dense gemv: x / W must be 16-byte aligned");
+  const DeviceInfo& di = device_info();
+  if (di.err != cudaSuccess) return set_cuda_error(di.err, "device query");
+  const size_t smem = (size_t)Z * 2;
+  auto kern = dense_rowmajor_gemv_kernel<8>;
+  static bool attr_set = false;
+  if (!attr_set && smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  if (smem > 100 * 1024) return set_error(TEAL_ERR_UNSUPPORTED, "dense gemv: Z too large");
+  int grid = di.sm_count * 2;
+  const int rows_per_cta = kHeadThreads / 32;
+  if ((long long)grid * rows_per_cta > V) grid = (V + rows_per_cta - 1) / rows_per_cta;
+  return launch_pdl(kern, dim3(grid), dim3(kHeadThreads), smem, stream, "dense gemv launch", x, norm_w, eps, W, y,
+                    argmax_packed, Z, V, ldw);
+}
+
+int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap,
+                   cudaStream_t stream) {
+  if (!argmax_packed || !token || !pos || !out_tokens) return set_error(TEAL_ERR_BAD_ARG, "advance: bad argument");
+  return launch_pdl(advance_kernel, dim3(1), dim3(32), 0, stream, "advance launch", argmax_packed, token, pos,
+                    out_tokens, out_cap);
+}
+
+}  // namespace teal

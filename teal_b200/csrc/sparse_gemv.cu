@@ -510,10 +510,23 @@ static constexpr int kNumConfigs = sizeof(kConfigs) / sizeof(kConfigs[0]);
 static int g_forced_config = 0;
 static long long* g_dbg_time = nullptr;
 
+static bool g_pdl = false;
 void set_debug_timestamps(long long* buf) { g_dbg_time = buf; }
+long long* debug_timestamps() { return g_dbg_time; }
+int forced_config() { return g_forced_config; }
+void set_pdl(bool on) { g_pdl = on; }
+bool pdl_enabled() { return g_pdl; }
+// config ids 100 + k*256 (k = 1..4) additionally cap the per-warp sub-tile of gather_gemv at k*256 columns
+static unsigned long long* g_probe = nullptr;
+void set_bytes_probe(unsigned long long* q) { g_probe = q; }
+unsigned long long* bytes_probe() { return g_probe; }
+static int g_sub_cols = 0;
+int sub_cols_override() { return g_sub_cols; }
 
 int set_config(int id) {
-  if (id < 0 || id > kNumConfigs) return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
+  g_sub_cols = 0;
+  if (id >= 1000) { g_sub_cols = (id / 1000) * 256; id %= 1000; }  // e.g. 2014: sub-tile 512, 4 tiles
+  if (id < 0 || (id > kNumConfigs && (id < 11 || id > 26)) || g_sub_cols > 1024) return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
   g_forced_config = id;
   return TEAL_OK;
 }
@@ -521,6 +534,20 @@ int set_config(int id) {
 static int pick_config(const GemvParams& p) {
   if (g_forced_config) return g_forced_config - 1;
   return 0;
+}
+
+// Config ids: 0 = default (gather_gemv, 4 tiles per matrix, 2 for the fused gate/up pair);
+// 1..6 = the TMA-bulk-ring kernel of this file; 10+T = gather_gemv with T tiles per matrix.
+int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream) {
+  const int id = g_forced_config;
+  if (id >= 1 && id <= kNumConfigs) {
+    if (p.in_mode != kInPlain || p.out_mode != kOutPlain || p.x_out)
+      return set_error(TEAL_ERR_UNSUPPORTED, "fused norm/residual modes need the gather_gemv kernel");
+    return launch_gemv(p, workspace, ws_bytes, out_cols_total, stream);
+  }
+  int tiles = (p.mode == kModePairSilu) ? 2 : 4;
+  if (id > 10) tiles = id - 10;
+  return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, tiles);
 }
 
 size_t workspace_bytes(int max_out_cols) {

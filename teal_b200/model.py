@@ -1,0 +1,364 @@
+"""Batch-1 decode engine around the fused sparse GEMV kernels.
+
+Mirrors the pieces of the reference's gpt-fast fork that sit on the north-star path:
+
+* ``ModelArgs`` / ``transformer_configs`` -- gpt-fast/model.py:25-79 (shapes verbatim).
+* ``SparseDecoder`` -- what ``_load_model`` + ``monkeypatch_layer`` + ``decode_one_token`` build
+  (gpt-fast/generate.py:73-77,225-334; model.py:133-190,258-259), but as ONE captured CUDA graph of
+  hand-written kernels per token: 5 launches per layer
+  (RMSNorm+QKV-GEMV | RoPE+KV+attention | o-GEMV+residual | RMSNorm+gate/up-GEMV+SiLU*mul |
+  down-GEMV+residual) + embedding, lm_head(+final norm, +argmax) and the step bookkeeping.
+* weights live in the reference's "column major" layout ([Z][N] storage, generate.py:296-317).
+* tensor parallelism follows gpt-fast/tp.py: wqkv/w1/w3 column-sharded (per-rank [q_r; k_r; v_r]),
+  wo/w2 row-sharded, one NCCL all-reduce after the attention block and one after the MLP block.
+
+PyTorch here is plumbing: device memory, the CUDA-graph capture and torch.distributed.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .distribution import Distribution, PROJS, threshold_for
+
+
+def find_multiple(n: int, k: int) -> int:
+    return n if n % k == 0 else n + k - (n % k)
+
+
+@dataclass
+class ModelArgs:
+    block_size: int = 2048
+    vocab_size: int = 32000
+    n_layer: int = 32
+    n_head: int = 32
+    dim: int = 4096
+    intermediate_size: Optional[int] = None
+    n_local_heads: int = -1
+    head_dim: int = 64
+    rope_base: float = 10000
+    norm_eps: float = 1e-5
+
+    def __post_init__(self):
+        if self.n_local_heads == -1:
+            self.n_local_heads = self.n_head
+        if self.intermediate_size is None:
+            self.intermediate_size = find_multiple(int(2 * 4 * self.dim / 3), 256)
+        self.head_dim = self.dim // self.n_head
+
+    @classmethod
+    def from_name(cls, name: str) -> "ModelArgs":
+        if name in transformer_configs:
+            return cls(**transformer_configs[name])
+        cands = [c for c in transformer_configs if c.lower() in str(name).lower()]
+        cands.sort(key=len, reverse=True)
+        return cls(**transformer_configs[cands[0]])
+
+
+# gpt-fast/model.py:66-79 (the shapes BASELINE.json's configs name)
+transformer_configs = {
+    "7B": dict(n_layer=32, n_head=32, dim=4096),
+    "13B": dict(n_layer=40, n_head=40, dim=5120),
+    "70B": dict(n_layer=80, n_head=64, dim=8192, n_local_heads=8, intermediate_size=28672),
+    "Mistral-7B": dict(n_layer=32, n_head=32, n_local_heads=8, dim=4096, intermediate_size=14336, vocab_size=32000),
+    "llama-3-8b": dict(block_size=8192, n_layer=32, n_head=32, n_local_heads=8, dim=4096, intermediate_size=14336,
+                       vocab_size=128256, rope_base=500000),
+    "llama-3-70b": dict(block_size=8192, n_layer=80, n_head=64, n_local_heads=8, dim=8192, intermediate_size=28672,
+                        vocab_size=128256, rope_base=500000),
+    # small shapes for tests / smoke
+    "tiny": dict(block_size=256, n_layer=2, n_head=4, n_local_heads=2, dim=256, intermediate_size=704, vocab_size=512),
+}
+
+
+def precompute_freqs_cis(seq_len: int, n_elem: int, base: float, dtype=torch.float16) -> torch.Tensor:
+    """Same table as gpt-fast/model.py:294-303 ((cos, sin) rounded to the model dtype)."""
+    freqs = 1.0 / (base ** (torch.arange(0, n_elem, 2)[: (n_elem // 2)].float() / n_elem))
+    t = torch.arange(seq_len)
+    freqs = torch.outer(t, freqs)
+    fc = torch.polar(torch.ones_like(freqs), freqs)
+    return torch.stack([fc.real, fc.imag], dim=-1).to(dtype)
+
+
+def build_histogram(values: torch.Tensor, num_bins: int = 10000, outlier: float = 0.01):
+    """Histogram in the reference's format (utils/utils.py:145-173: fp32 counts + bin centres,
+    1% / 99% outliers clipped into the two edge bins)."""
+    v = values.flatten().float().cpu().sort().values
+    n = v.numel()
+    lo, hi = v[int(n * outlier)], v[min(n - 1, int(n * (1 - outlier)))]
+    inner = v[(v >= lo) & (v <= hi)]
+    counts = torch.histc(inner, bins=num_bins - 2, min=float(lo), max=float(hi))
+    width = (hi - lo) / (num_bins - 2)
+    centers = lo + width * (torch.arange(num_bins - 2) + 0.5)
+    counts = torch.cat([torch.tensor([float((v < lo).sum())]), counts, torch.tensor([float((v > hi).sum())])])
+    centers = torch.cat([torch.tensor([float(v[0])]), centers, torch.tensor([float(v[-1])])])
+    return centers.float().numpy(), counts.float().numpy()
+
+
+class SparseDecoder:
+    """Random-init (or state-dict) gpt-fast-shaped model decoding one token per CUDA-graph replay."""
+
+    def __init__(self, args: ModelArgs, device="cuda", max_seq: int = 512, seed: int = 1234, rank: int = 0,
+                 world: int = 1, process_group=None, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 out_cap: int = 4096):
+        if not torch.cuda.is_available():
+            raise _lib.TealLibraryError("SparseDecoder needs a CUDA device: the decode path has no CPU fallback")
+        self.lib = _lib.load()
+        self.args, self.dev, self.rank, self.world, self.pg = args, torch.device(device), rank, world, process_group
+        a = args
+        assert a.n_head % world == 0 and a.n_local_heads % world == 0 and a.intermediate_size % world == 0
+        self.n_head_l, self.n_kv_l = a.n_head // world, a.n_local_heads // world   # tp.py:134-137
+        self.hd = a.head_dim
+        self.dim_l = self.n_head_l * self.hd                                      # local attention width
+        self.kv_l = self.n_kv_l * self.hd
+        self.nqkv_l = self.dim_l + 2 * self.kv_l
+        self.inter_l = a.intermediate_size // world
+        self.max_seq = find_multiple(max_seq, 8)                                  # model.py:118
+        self.sparse = False
+        self.thresholds: List[Optional[Dict[str, float]]] = [None] * a.n_layer
+        self._build_weights(seed, state_dict)
+        f16, dev = torch.float16, self.dev
+        self.freqs = precompute_freqs_cis(min(a.block_size, self.max_seq), self.hd, a.rope_base).to(dev).contiguous()
+        self.k_cache = [torch.zeros(self.n_kv_l, self.max_seq, self.hd, dtype=f16, device=dev) for _ in range(a.n_layer)]
+        self.v_cache = [torch.zeros(self.n_kv_l, self.max_seq, self.hd, dtype=f16, device=dev) for _ in range(a.n_layer)]
+        # step state (device resident so the graph replays unchanged)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.out_tokens = torch.zeros(out_cap, dtype=torch.int32, device=dev)
+        self.argmax = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.x = torch.zeros(1, 1, a.dim, dtype=f16, device=dev)
+        self.qkv = torch.zeros(1, 1, self.nqkv_l, dtype=f16, device=dev)
+        self.att = torch.zeros(1, 1, self.dim_l, dtype=f16, device=dev)
+        self.h = torch.zeros(1, 1, self.inter_l, dtype=f16, device=dev)
+        self.part = torch.zeros(1, 1, a.dim, dtype=f16, device=dev)
+        self.logits = torch.zeros(1, 1, a.vocab_size, dtype=f16, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_mode = None
+        self.taps = None  # calibration taps
+        self.kernels_per_step = 0
+
+    # ------------------------------------------------------------------ weights
+    def _colmajor_rand(self, g, n, z, std=0.02):
+        """fp16 [Z][N] storage viewed as the logical [N, Z] weight (stride (1, N))."""
+        w = torch.empty(z, n, dtype=torch.float16, device=self.dev)
+        w.normal_(0.0, std, generator=g)
+        return w.T
+
+    def _build_weights(self, seed, sd):
+        a, dev = self.args, self.dev
+        g = torch.Generator(device=dev).manual_seed(seed)
+        f16 = torch.float16
+        r, w = self.rank, self.world
+
+        def shard(t, dim):
+            return torch.tensor_split(t, w, dim=dim)[r] if w > 1 else t
+
+        def shard_qkv(t):                                                        # tp.py:73-78
+            q, k, v = t.split([a.dim, a.n_local_heads * self.hd, a.n_local_heads * self.hd], dim=0)
+            return torch.cat((shard(q, 0), shard(k, 0), shard(v, 0)), dim=0)
+
+        self.layers = []
+        if sd is None:
+            self.tok_emb = torch.empty(a.vocab_size, a.dim, dtype=f16, device=dev).normal_(0, 1.0, generator=g)
+            self.lm_head = torch.empty(a.vocab_size, a.dim, dtype=f16, device=dev).normal_(0, 0.02, generator=g)
+            self.final_norm = torch.ones(a.dim, dtype=f16, device=dev)
+            for _ in range(a.n_layer):
+                # random init is generated per rank at the sharded shape (same seed => TP ranks differ only in
+                # which slice they would hold; for synthetic weights the values themselves are irrelevant)
+                L = dict(wqkv=self._colmajor_rand(g, self.nqkv_l, a.dim), wo=self._colmajor_rand(g, a.dim, self.dim_l),
+                         w1=self._colmajor_rand(g, self.inter_l, a.dim), w3=self._colmajor_rand(g, self.inter_l, a.dim),
+                         w2=self._colmajor_rand(g, a.dim, self.inter_l),
+                         attn_norm=torch.ones(a.dim, dtype=f16, device=dev), ffn_norm=torch.ones(a.dim, dtype=f16, device=dev))
+                self.layers.append(L)
+        else:
+            cm = ops.to_column_major
+            self.tok_emb = sd["tok_embeddings.weight"].to(dev, f16).contiguous()
+            self.lm_head = sd["output.weight"].to(dev, f16).contiguous()
+            self.final_norm = sd["norm.weight"].to(dev, f16).contiguous()
+            for i in range(a.n_layer):
+                p = f"layers.{i}."
+                L = dict(wqkv=cm(shard_qkv(sd[p + "attention.wqkv.weight"]).to(dev, f16)),
+                         wo=cm(shard(sd[p + "attention.wo.weight"], 1).to(dev, f16)),
+                         w1=cm(shard(sd[p + "feed_forward.w1.weight"], 0).to(dev, f16)),
+                         w3=cm(shard(sd[p + "feed_forward.w3.weight"], 0).to(dev, f16)),
+                         w2=cm(shard(sd[p + "feed_forward.w2.weight"], 1).to(dev, f16)),
+                         attn_norm=sd[p + "attention_norm.weight"].to(dev, f16).contiguous(),
+                         ffn_norm=sd[p + "ffn_norm.weight"].to(dev, f16).contiguous())
+                self.layers.append(L)
+
+    def weight_bytes(self):
+        """(sparsifiable layer bytes, dense lm_head bytes) read per token on this rank."""
+        a = self.args
+        per_layer = 2 * (a.dim * self.nqkv_l + self.dim_l * a.dim + 2 * a.dim * self.inter_l + self.inter_l * a.dim)
+        return per_layer * a.n_layer, 2 * a.vocab_size * a.dim
+
+    # ------------------------------------------------------------------ thresholds
+    def set_thresholds(self, thresholds: List[Optional[Dict[str, float]]]):
+        """Per layer {q,k,v,o,gate,up,down} -> threshold (None = dense layer).  Invalidates the graph."""
+        self.thresholds = list(thresholds)
+        self.sparse = any(t is not None for t in thresholds)
+        self.graph = None
+
+    def calibrate(self, sparsities, n_tokens: int = 16, seed: int = 7):
+        """Synthetic-model calibration through the reference's own path: run dense
+        decode steps, histogram the four activation sites per layer (grab_acts -> histograms.pt),
+        then threshold = Distribution.icdf(0.5 + s/2) per projection (generate.py:278-287).
+        `sparsities`: float, or {proj: float}, or list (per layer) of {proj: float}."""
+        a = self.args
+        saved = self.thresholds
+        self.set_thresholds([None] * a.n_layer)
+        acts = [dict(attn_h1=[], attn_h2=[], mlp_h1=[], mlp_h2=[]) for _ in range(a.n_layer)]
+        self.taps = acts
+        rng = np.random.RandomState(seed)
+        self.reset(int(rng.randint(0, a.vocab_size)))
+        for _ in range(n_tokens):
+            self._enqueue_step(mode="dense_own")
+            torch.cuda.synchronize()
+            self.token.fill_(int(rng.randint(0, a.vocab_size)))  # random token stream
+        self.taps = None
+        site = {"q": "attn_h1", "k": "attn_h1", "v": "attn_h1", "o": "attn_h2", "gate": "mlp_h1", "up": "mlp_h1",
+                "down": "mlp_h2"}
+        thr = []
+        for li in range(a.n_layer):
+            sp = sparsities[li] if isinstance(sparsities, (list, tuple)) else sparsities
+            if not isinstance(sp, dict):
+                sp = {p: float(sp) for p in PROJS}
+            dists = {k: Distribution(None, None, **dict(zip(("centers", "counts"), build_histogram(torch.cat(v)))))
+                     for k, v in acts[li].items()}
+            thr.append({p: threshold_for(dists[site[p]], sp[p]) for p in PROJS})
+        self.set_thresholds(thr)
+        return thr
+
+    # ------------------------------------------------------------------ one decode step (enqueue only)
+    def reset(self, first_token: int = 1):
+        self.token.fill_(int(first_token))
+        self.pos.zero_()
+        self.argmax.zero_()
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+
+    def _enqueue_step(self, mode: str):
+        """mode: 'sparse' (fused kernels with thresholds), 'dense_own' (same kernels, nothing dropped),
+        'dense_cublas' (projections through torch.matmul like the reference's dense nn.Linear)."""
+        a, lib, L = self.args, self.lib, self.layers
+        sp = torch.cuda.current_stream().cuda_stream
+        ws = ops.workspace(self.dev, sp)
+        wsp, wsn = ws.data_ptr(), ws.numel()
+        chk = _lib.check
+        n_launch = 0
+        chk(lib.teal_embed_f16(self.tok_emb.data_ptr(), self.token.data_ptr(), self.x.data_ptr(), a.dim, sp), "embed")
+        n_launch += 1
+        dense_t = {p: -1.0 for p in PROJS}
+        for li in range(a.n_layer):
+            W = L[li]
+            t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else dense_t
+            tap = self.taps[li] if self.taps is not None else None
+            if mode == "dense_cublas":
+                xn = _rms_norm(self.x, W["attn_norm"], a.norm_eps)
+                torch.matmul(xn, W["wqkv"].T, out=self.qkv)
+            else:
+                xn_out = torch.empty_like(self.x) if tap is not None else None
+                chk(lib.teal_norm_sparse_qkv_gemv_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps,
+                                                      W["wqkv"].data_ptr(), self.qkv.data_ptr(),
+                                                      xn_out.data_ptr() if tap is not None else None, a.dim, self.nqkv_l,
+                                                      W["wqkv"].stride(1), self.kv_l, t["q"], t["k"], t["v"], wsp, wsn, sp),
+                    "norm_qkv")
+                if tap is not None:
+                    tap["attn_h1"].append(xn_out.flatten().float().cpu())
+            chk(lib.teal_attn_decode_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
+                                         self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
+                                         self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
+            if tap is not None:
+                tap["attn_h2"].append(self.att.flatten().float().cpu())
+            n_launch += 2
+            if mode == "dense_cublas":
+                torch.matmul(self.att, W["wo"].T, out=self.part)
+                self._allreduce(self.part)
+                self.x.add_(self.part)
+                xn = _rms_norm(self.x, W["ffn_norm"], a.norm_eps)
+                g1 = torch.matmul(xn, W["w1"].T)
+                u1 = torch.matmul(xn, W["w3"].T)
+                torch.mul(torch.nn.functional.silu(g1), u1, out=self.h)
+                torch.matmul(self.h, W["w2"].T, out=self.part)
+                self._allreduce(self.part)
+                self.x.add_(self.part)
+                continue
+            if self.world == 1:
+                chk(lib.teal_sparse_gemv_residual_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(),
+                                                      self.x.data_ptr(), self.dim_l, a.dim, W["wo"].stride(1), t["o"],
+                                                      wsp, wsn, sp), "o_proj")
+            else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
+                chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.part.data_ptr(), self.dim_l,
+                                             a.dim, W["wo"].stride(1), t["o"], wsp, wsn, sp), "o_proj")
+                self._allreduce(self.part)
+                self.x.add_(self.part)
+            xn_out = torch.empty_like(self.x) if tap is not None else None
+            chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps,
+                                                 W["w1"].data_ptr(), W["w3"].data_ptr(), self.h.data_ptr(),
+                                                 xn_out.data_ptr() if tap is not None else None, a.dim, self.inter_l,
+                                                 W["w1"].stride(1), W["w3"].stride(1), t["gate"], t["up"], wsp, wsn, sp),
+                "gate_up")
+            if tap is not None:
+                tap["mlp_h1"].append(xn_out.flatten().float().cpu())
+                tap["mlp_h2"].append(self.h.flatten().float().cpu())
+            if self.world == 1:
+                chk(lib.teal_sparse_gemv_residual_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(),
+                                                      self.x.data_ptr(), self.inter_l, a.dim, W["w2"].stride(1),
+                                                      t["down"], wsp, wsn, sp), "down_proj")
+            else:
+                chk(lib.teal_sparse_gemv_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.part.data_ptr(), self.inter_l,
+                                             a.dim, W["w2"].stride(1), t["down"], wsp, wsn, sp), "down_proj")
+                self._allreduce(self.part)
+                self.x.add_(self.part)
+            n_launch += 3
+        chk(lib.teal_dense_gemv_f16(self.x.data_ptr(), self.final_norm.data_ptr(), a.norm_eps, self.lm_head.data_ptr(),
+                                    self.logits.data_ptr(), self.argmax.data_ptr(), a.dim, a.vocab_size, a.dim, sp),
+            "lm_head")
+        chk(lib.teal_advance(self.argmax.data_ptr(), self.token.data_ptr(), self.pos.data_ptr(),
+                             self.out_tokens.data_ptr(), self.out_tokens.numel(), sp), "advance")
+        self.kernels_per_step = n_launch + 2
+
+    # ------------------------------------------------------------------ public API
+    def capture(self, mode: str = "sparse", pdl: bool = True):
+        """Capture one decode step into a CUDA graph (generate.py:420's reduce-overhead equivalent)."""
+        if mode == "sparse" and not self.sparse:
+            raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
+        self.lib.teal_set_pdl(1 if (pdl and mode != "dense_cublas") else 0)
+        with torch.cuda.stream(self.stream):
+            ops.workspace(self.dev, self.stream.cuda_stream)
+            saved = (self.token.clone(), self.pos.clone())
+            self._enqueue_step(mode)  # warm-up outside capture (allocations, lazy init)
+            self.stream.synchronize()
+            self.token.copy_(saved[0]); self.pos.copy_(saved[1]); self.argmax.zero_()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                self._enqueue_step(mode)
+        self.lib.teal_set_pdl(0)
+        torch.cuda.synchronize()
+        self.graph, self.graph_mode = g, mode
+        return g
+
+    def decode_one_token(self):
+        """Replay the captured step (device-side token/position; no host sync)."""
+        self.graph.replay()
+
+    def generate(self, first_token: int, n_new: int, mode: str = "sparse") -> torch.Tensor:
+        if self.graph is None or self.graph_mode != mode:
+            self.capture(mode)
+        self.reset(first_token)
+        for _ in range(n_new):
+            self.graph.replay()
+        torch.cuda.synchronize()
+        return self.out_tokens[:n_new].clone()
+
+
+def _rms_norm(x, w, eps):
+    xf = x.float()
+    return (xf * torch.rsqrt(torch.mean(xf * xf, dim=-1, keepdim=True) + eps)).to(x.dtype) * w

@@ -122,6 +122,54 @@ def sparse_gate_up(x: torch.Tensor, w1: torch.Tensor, w3: torch.Tensor, threshol
     return out
 
 
+def norm_qkv_gemv(x, norm_w, eps, weight, tq, tk, tv, kv_size, want_xn=False):
+    """attention_norm + fused QKV GEMV in one launch (decode pipeline building block)."""
+    N, Z = weight.shape
+    x = _check_x(x, Z)
+    ldw = _check_w(weight)
+    out = torch.empty(1, 1, N, device=x.device, dtype=torch.float16)
+    xn = torch.empty(1, 1, Z, device=x.device, dtype=torch.float16) if want_xn else None
+    sp = _stream_ptr()
+    ws = workspace(x.device, sp)
+    rc = _lib.load().teal_norm_sparse_qkv_gemv_f16(x.data_ptr(), norm_w.data_ptr(), float(eps), weight.data_ptr(),
+                                                   out.data_ptr(), xn.data_ptr() if want_xn else None, Z, N, ldw,
+                                                   int(kv_size), float(tq), float(tk), float(tv), ws.data_ptr(),
+                                                   ws.numel(), sp)
+    _lib.check(rc, "teal_norm_sparse_qkv_gemv_f16")
+    return (out, xn) if want_xn else out
+
+
+def norm_gate_up(x, norm_w, eps, w1, w3, t_gate, t_up, want_xn=False):
+    """ffn_norm + gate/up GEMVs + SiLU*mul in one launch."""
+    I, Z = w1.shape
+    x = _check_x(x, Z)
+    ld1, ld3 = _check_w(w1), _check_w(w3)
+    out = torch.empty(1, 1, I, device=x.device, dtype=torch.float16)
+    xn = torch.empty(1, 1, Z, device=x.device, dtype=torch.float16) if want_xn else None
+    sp = _stream_ptr()
+    ws = workspace(x.device, sp)
+    rc = _lib.load().teal_norm_sparse_gate_up_f16(x.data_ptr(), norm_w.data_ptr(), float(eps), w1.data_ptr(),
+                                                  w3.data_ptr(), out.data_ptr(), xn.data_ptr() if want_xn else None,
+                                                  Z, I, ld1, ld3, float(t_gate), float(t_up), ws.data_ptr(),
+                                                  ws.numel(), sp)
+    _lib.check(rc, "teal_norm_sparse_gate_up_f16")
+    return (out, xn) if want_xn else out
+
+
+def gemv_residual(x, weight, resid, threshold):
+    """resid + sparse_gemv(x, weight) with the add fused into the kernel's finaliser."""
+    N, Z = weight.shape
+    x = _check_x(x, Z)
+    ldw = _check_w(weight)
+    out = torch.empty(1, 1, N, device=x.device, dtype=torch.float16)
+    sp = _stream_ptr()
+    ws = workspace(x.device, sp)
+    rc = _lib.load().teal_sparse_gemv_residual_f16(x.data_ptr(), weight.data_ptr(), resid.data_ptr(), out.data_ptr(),
+                                                   Z, N, ldw, float(threshold), ws.data_ptr(), ws.numel(), sp)
+    _lib.check(rc, "teal_sparse_gemv_residual_f16")
+    return out
+
+
 def survivors(x: torch.Tensor, threshold: float) -> torch.Tensor:
     """Sorted surviving lane indices, computed by the device compaction code (parity hook)."""
     xf = x.reshape(-1).contiguous()

@@ -10,12 +10,12 @@ NAMES = ["start", "x_staged", "scan", "pieces", "lists", "first_full", "consumed
          "epilogue", "end", "prod_first", "prod_done"]
 ap = argparse.ArgumentParser()
 ap.add_argument("--shapes", default="4096x4096,4096x14336")
-ap.add_argument("--configs", default="2")
+ap.add_argument("--configs", default="0")
 ap.add_argument("--sparsity", type=float, default=0.5)
 a = ap.parse_args()
 lib = _lib.load()
 nsm = lib.teal_device_sm_count()
-buf = torch.zeros(nsm * 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(nsm * 16 + nsm * 64, dtype=torch.int64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for shp in a.shapes.split(","):
     Z, N = (int(v) for v in shp.split("x"))
@@ -32,7 +32,14 @@ for shp in a.shapes.split(","):
             ops.splitk_sparse_gemv(x, W, thr, 0)
             torch.cuda.synchronize()
             lib.teal_set_debug_timestamps(None)
-        t = buf.cpu().numpy().reshape(nsm, 16)
+        allb = buf.cpu().numpy()
+        t = allb[: nsm * 16].reshape(nsm, 16)
+        rowt = allb[nsm * 16:].reshape(nsm, 2, 32)
+        for cta in (0, 73, 147):
+            for wi, wn in ((0, "w0"), (1, "w15")):
+                r = rowt[cta, wi]
+                r = r[r > 0] - t[cta, 0]
+                print(f"   cta {cta} {wn} row-done cycles: " + " ".join(str(int(v)) for v in r))
         rel = t[:, :13] - t[:, 0:1]
         g0 = t[:, 13].min()
         print(f"== {shp} cfg {cfg}: kernel span {(t[:,14].max()-g0)} ns; CTA start skew max {(t[:,13]-g0).max()} ns; "
