@@ -42,7 +42,8 @@ typedef enum teal_status {
   TEAL_ERR_CUDA = -5         /* CUDA runtime error (message has the cudaError string) */
 } teal_status;
 
-#define TEAL_B200_ABI_VERSION 1
+#define TEAL_B200_ABI_VERSION 2
+#define TEAL_SSQ_PARTS 64 /* floats in a sum-of-squares partials buffer */
 
 int teal_abi_version(void);
 const char* teal_last_error(void);
@@ -84,27 +85,35 @@ int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, voi
 /* ---- fused variants used by the decode pipeline (one launch per projection group) ---------------
  * RMSNorm (gpt-fast/model.py:286-291: fp32 norm, fp16 cast, fp16 multiply by norm_w) of the fp16
  * residual stream x is computed in the kernel prologue, then thresholded; `xn_out` (nullable)
- * receives the normalised vector.  Replaces attention_norm + gemv1 (model.py:159,168) ... */
-int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps, const void* wt,
-                                  void* y, void* xn_out, int Z, int N, int64_t ldw, int kv_size,
+ * receives the normalised vector.  Replaces attention_norm + gemv1 (model.py:159,168) ...
+ * Sum-of-squares hand-off: no CTA reads the whole vector for the norm.  The producer of x leaves
+ * TEAL_SSQ_PARTS fp32 partial sums of squares (`ssq_out` of teal_embed_f16 /
+ * teal_sparse_gemv_residual_f16: it writes its tiles' partials, the unused tail of the buffer must
+ * be zero) and the consumer takes them as `ssq_in`; with ssq_in == NULL the library computes them
+ * with one extra tiny launch. */
+int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps, const float* ssq_in,
+                                  const void* wt, void* y, void* xn_out, int Z, int N, int64_t ldw,
+                                  int kv_size,
                                   double threshold_q, double threshold_k, double threshold_v,
                                   void* workspace, size_t workspace_bytes, void* stream);
 /* ... ffn_norm + gemv1(gate) + gemv1(up) + SiLU*mul (model.py:161,259) ... */
-int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, const void* w1t,
-                                 const void* w3t, void* h, void* xn_out, int Z, int I, int64_t ldw1,
+int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, const float* ssq_in,
+                                 const void* w1t, const void* w3t, void* h, void* xn_out, int Z, int I,
+                                 int64_t ldw1,
                                  int64_t ldw3, double threshold_gate, double threshold_up,
                                  void* workspace, size_t workspace_bytes, void* stream);
 /* ... and gemv2 + residual add: y = resid + fp16(sparse_gemv(x, wt)) in fp16
  * (model.py:160-161,188,259).  y may alias resid. */
-int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y, int Z,
-                                  int N, int64_t ldw, double threshold, void* workspace,
-                                  size_t workspace_bytes, void* stream);
+int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y,
+                                  float* ssq_out, int Z, int N, int64_t ldw, double threshold,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- the rest of one batch-1 decode step -----------------------------
  * All of them read the token / position from device memory so a captured CUDA graph replays for
  * every token.
  * x[dim] = tok_embeddings[*token]  (gpt-fast/model.py:137). */
-int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, int dim, void* stream);
+int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, float* ssq_out, int dim,
+                   void* stream);
 /* RoPE(q, k) with the fp16 (cos, sin) table freqs_cis[max_seq][head_dim/2][2], KV-cache append at
  * *pos, attention of the one query token over positions [0, *pos], heads concatenated
  * (gpt-fast/model.py:170-186).  qkv: fp16 [n_head*hd | n_kv*hd | n_kv*hd]; caches fp16
@@ -123,7 +132,8 @@ int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out
 
 /* Survivor set of one threshold, produced by the same device code the GEMV kernels use
  * (parity hook: "surviving-index set bit-exact").  idx_out: int32[Z] (sorted ascending, first
- * *count_out entries valid), count_out: int32[1].  Both device pointers. */
+ * *count_out entries valid; its upper quarter is used as scratch for the keep mask),
+ * count_out: int32[1].  Both device pointers. */
 int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out,
                        int32_t* count_out, void* stream);
 

@@ -30,16 +30,16 @@ _SIGS = {
     "teal_sparse_gate_up_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                            _c.c_int64, _c.c_int64, _c.c_double, _c.c_double, _c.c_void_p,
                                            _c.c_size_t, _c.c_void_p]),
-    "teal_norm_sparse_qkv_gemv_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p,
+    "teal_norm_sparse_qkv_gemv_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                  _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_double,
                                                  _c.c_double, _c.c_double, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
-    "teal_norm_sparse_gate_up_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p,
+    "teal_norm_sparse_gate_up_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                 _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64,
                                                 _c.c_double, _c.c_double, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
-    "teal_sparse_gemv_residual_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
+    "teal_sparse_gemv_residual_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                                  _c.c_int, _c.c_int64, _c.c_double, _c.c_void_p, _c.c_size_t,
                                                  _c.c_void_p]),
-    "teal_embed_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
+    "teal_embed_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "teal_attn_decode_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                         _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "teal_dense_gemv_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
@@ -94,7 +94,7 @@ def load():
     except OSError as e:  # fail loudly: there is no fallback path
         raise TealLibraryError(f"cannot load {LIB_PATH}: {e}") from e
     _bind(lib)
-    if lib.teal_abi_version() != 1:
+    if lib.teal_abi_version() != 2:
         raise TealLibraryError("libteal_b200 ABI version mismatch")
     _lib = lib
     return lib

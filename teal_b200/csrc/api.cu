@@ -153,9 +153,24 @@ int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, voi
 }
 
 // ---- fused variants used by the decode pipeline --------------------------------------------------
-int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps, const void* wt, void* y, void* xn_out,
-                                  int Z, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
-                                  double threshold_v, void* workspace, size_t workspace_bytes_, void* stream) {
+// RMSNorm input: use the producer's sum-of-squares partials when given, else compute them here (one tiny launch)
+static int norm_input(GemvParams& p, const void* norm_w, double eps, const float* ssq_in, void* workspace,
+                      size_t ws_bytes, cudaStream_t stream) {
+  p.in_mode = kInRmsNorm;
+  p.norm_w = reinterpret_cast<const __half*>(norm_w);
+  p.eps = (float)eps;
+  p.n_ssq_in = kSsqParts;
+  if (ssq_in) { p.ssq_in = ssq_in; return TEAL_OK; }
+  if (!workspace || ws_bytes < workspace_bytes(8)) return set_error(TEAL_ERR_WORKSPACE, "workspace too small");
+  float* scratch = workspace_ssq_scratch(workspace, ws_bytes);
+  p.ssq_in = scratch;
+  return launch_ssq(p.x, p.Z, scratch, kSsqParts, stream);
+}
+
+int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt,
+                                  void* y, void* xn_out, int Z, int N, int64_t ldw, int kv_size, double threshold_q,
+                                  double threshold_k, double threshold_v, void* workspace, size_t workspace_bytes_,
+                                  void* stream) {
   GemvParams p;
   if (int rc = fill_common(p, x, y, Z)) return rc;
   if (!wt || !y || !norm_w || N <= 0 || ldw < N || kv_size < 0 || 2 * (int64_t)kv_size > N)
@@ -164,9 +179,7 @@ int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps,
   const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k),
               tv = round_threshold_fp16(threshold_v);
   p.mode = kModePlain;
-  p.in_mode = kInRmsNorm;
-  p.norm_w = reinterpret_cast<const __half*>(norm_w);
-  p.eps = (float)eps;
+  if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
   p.x_out = reinterpret_cast<__half*>(xn_out);
   const __half* w = reinterpret_cast<const __half*>(wt);
   if (tq == tk && tk == tv) {
@@ -185,8 +198,8 @@ int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps,
   return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, const void* w1t, const void* w3t,
-                                 void* h, void* xn_out, int Z, int I, int64_t ldw1, int64_t ldw3,
+int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
+                                 const void* w3t, void* h, void* xn_out, int Z, int I, int64_t ldw1, int64_t ldw3,
                                  double threshold_gate, double threshold_up, void* workspace,
                                  size_t workspace_bytes_, void* stream) {
   GemvParams p;
@@ -194,9 +207,7 @@ int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, 
   if (!w1t || !w3t || !h || !norm_w || I <= 0 || ldw1 < I || ldw3 < I)
     return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / h / norm_w / I / ldw");
   p.mode = kModePairSilu;
-  p.in_mode = kInRmsNorm;
-  p.norm_w = reinterpret_cast<const __half*>(norm_w);
-  p.eps = (float)eps;
+  if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
   p.x_out = reinterpret_cast<__half*>(xn_out);
   p.nseg = 2;
   p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
@@ -204,8 +215,8 @@ int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, 
   return dispatch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y, int Z, int N,
-                                  int64_t ldw, double threshold, void* workspace, size_t workspace_bytes_,
+int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y, float* ssq_out, int Z,
+                                  int N, int64_t ldw, double threshold, void* workspace, size_t workspace_bytes_,
                                   void* stream) {
   GemvParams p;
   if (int rc = fill_common(p, x, y, Z)) return rc;
@@ -213,14 +224,15 @@ int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* res
   p.mode = kModePlain;
   p.out_mode = kOutAddResidual;
   p.resid = reinterpret_cast<const __half*>(resid);
+  p.ssq_out = ssq_out;
   p.nseg = 1;
   p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
   return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- the rest of the decode step -------------------------------------------------------------------
-int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, int dim, void* stream) {
-  return launch_embed(reinterpret_cast<const __half*>(tok_embeddings), token, reinterpret_cast<__half*>(x), dim,
+int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, float* ssq_out, int dim, void* stream) {
+  return launch_embed(reinterpret_cast<const __half*>(tok_embeddings), token, reinterpret_cast<__half*>(x), ssq_out, dim,
                       reinterpret_cast<cudaStream_t>(stream));
 }
 int teal_attn_decode_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos,
@@ -250,9 +262,12 @@ int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out,
   p.nseg = 0;
   p.nthr = 0;
   slot_for(p, round_threshold_fp16(threshold));
-  p.dbg_idx = idx_out;
-  p.dbg_cnt = count_out;
-  return dispatch_gemv(p, nullptr, 0, 0, reinterpret_cast<cudaStream_t>(stream));
+  // the production kernel writes its keep mask into the upper quarter of idx_out (Z bytes of scratch); a
+  // single-CTA pass then turns it into the sorted index list (it never overtakes the mask bytes it still needs)
+  p.keep_out = reinterpret_cast<unsigned char*>(idx_out) + (size_t)3 * Z;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = dispatch_gemv(p, nullptr, 0, 0, s)) return rc;
+  return launch_mask_to_indices(p.keep_out, Z, idx_out, count_out, s);
 }
 
 int teal_sparse_gemv_f16_simple(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, double threshold,

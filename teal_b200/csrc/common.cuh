@@ -43,6 +43,10 @@ struct GemvParams {
   const __half* norm_w;  // RMSNorm weight (kInRmsNorm)
   const __half* resid;   // residual stream added in the epilogue (kOutAddResidual)
   __half* x_out;         // optional: the (normalised) x actually consumed
+  const float* ssq_in;   // RMSNorm: per-tile sums of squares of x left by its producer
+  int n_ssq_in;
+  float* ssq_out;        // optional: per-tile sums of squares of y (for the next RMSNorm)
+  unsigned char* keep_out;  // optional: keep mask (parity hook)
   int Z, nseg, nthr, mode;
   int nstages, list_cap, chunk, xs_elems;
   int in_mode, out_mode;
@@ -90,6 +94,35 @@ struct GatherParams {
   GatherTile tile[kMaxTiles];
 };
 
+// ---- rowchunk_gemv (many small CTAs) --------------------------------------------------------------
+constexpr int kSsqParts = 64;  // fixed length of a sum-of-squares partials buffer (unused tail stays zero)
+
+struct RcSeg {
+  const __half* w;
+  long long ldw;
+  int ncols, acc_col0, y_col0;
+  float thr;
+  int ctile0, nctiles;
+};
+
+struct RcParams {
+  const __half* x;
+  const __half* norm_w;
+  const float* ssq_in;
+  __half* y;
+  const __half* resid;
+  float* ssq_out;
+  __half* x_out;
+  unsigned char* keep_out;
+  float* acc;
+  unsigned* counters;
+  unsigned long long* probe;
+  int Z, mode, in_mode, out_mode, nseg;
+  int n_ssq_in, rows_per_cta, nkchunks, total_ctiles, target;
+  float eps;
+  RcSeg seg[kMaxSeg];
+};
+
 // ---------------------------------------------------------------------------------- host
 struct DeviceInfo {
   cudaError_t err;
@@ -102,6 +135,7 @@ int set_cuda_error(cudaError_t e, const char* where);
 float round_threshold_fp16(double t);
 
 size_t workspace_bytes(int max_out_cols);
+float* workspace_ssq_scratch(void* workspace, size_t ws_bytes);
 int set_config(int id);
 void set_debug_timestamps(long long* buf);
 long long* debug_timestamps();
@@ -113,12 +147,15 @@ void set_bytes_probe(unsigned long long* p);
 unsigned long long* bytes_probe();
 int launch_gather_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream,
                        int tiles_per_matrix);
+int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream, int variant);
+int launch_ssq(const __half* x, int Z, float* ssq_out, int nparts, cudaStream_t stream);
+int launch_mask_to_indices(const unsigned char* keep, int Z, int* idx, int* cnt, cudaStream_t stream);
 int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream);
 int launch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream);
 int launch_simple(const __half* x, const __half* wt, __half* y, int Z, int N, long long ldw, float thr,
                   cudaStream_t stream);
 
-int launch_embed(const __half* emb, const int* token, __half* x, int dim, cudaStream_t stream);
+int launch_embed(const __half* emb, const int* token, __half* x, float* ssq_out, int dim, cudaStream_t stream);
 int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,
                        __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream);
 int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,

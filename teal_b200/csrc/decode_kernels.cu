@@ -15,13 +15,38 @@ namespace teal {
 // --------------------------------------------------------------------------------------------
 // x[dim] = tok_embeddings[token]            (gpt-fast/model.py:137)
 // --------------------------------------------------------------------------------------------
+// Also leaves the row's sum of squares in ssq_out[0] (and zeroes ssq_out[1..kSsqParts)) for the first RMSNorm.
 __global__ void embed_kernel(const __half* __restrict__ emb, const int* __restrict__ token, __half* __restrict__ x,
-                             int dim) {
+                             float* __restrict__ ssq_out, int dim) {
+  __shared__ float sp[32];
   griddep_wait();
   const int t = token[0];
   const uint4* src = reinterpret_cast<const uint4*>(emb + (size_t)t * dim);
   uint4* dst = reinterpret_cast<uint4*>(x);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim / 8; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < dim / 8; i += blockDim.x) {
+    const uint4 v = src[i];
+    dst[i] = v;
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+    }
+  }
+  if (ssq_out) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sp[w];
+      ssq_out[0] = a;
+    } else if (threadIdx.x < kSsqParts) {
+      ssq_out[threadIdx.x] = 0.f;
+    }
+  }
   griddep_launch_dependents();
 }
 
@@ -296,9 +321,9 @@ static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
   return TEAL_OK;
 }
 
-int launch_embed(const __half* emb, const int* token, __half* x, int dim, cudaStream_t stream) {
+int launch_embed(const __half* emb, const int* token, __half* x, float* ssq_out, int dim, cudaStream_t stream) {
   if (!emb || !token || !x || dim <= 0 || (dim & 7)) return set_error(TEAL_ERR_BAD_ARG, "embed: bad argument");
-  return launch_pdl(embed_kernel, dim3(1), dim3(256), 0, stream, "embed launch", emb, token, x, dim);
+  return launch_pdl(embed_kernel, dim3(1), dim3(256), 0, stream, "embed launch", emb, token, x, ssq_out, dim);
 }
 
 int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,

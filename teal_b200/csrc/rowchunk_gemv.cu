@@ -1,0 +1,411 @@
+// rowchunk_gemv: fused [RMSNorm ->] threshold -> warp-level survivor compaction -> gather-GEMV
+// [-> +residual | SiLU(gate)*up] for sm_100a, built from MANY SMALL CTAs.
+//
+// Why this shape (measured on B200): a batch-1 projection moves 17-117 MB, i.e.
+// it lasts 3-18 us at HBM speed, so every serialised latency inside the kernel (x load, compaction,
+// first DRAM access, cross-CTA reduction, completion protocol) is worth 5-15 % of its runtime.  One
+// fat CTA per SM runs those phases in lock-step on all 148 SMs and leaves HBM idle during each of
+// them.  Here a CTA is 4 warps and owns (one 256/512-column tile) x (one K-chunk of 128-256 input
+// lanes): ~3600 CTAs per projection, 6-8 resident per SM, all at different phases, so HBM always has
+// somebody streaming; the hardware CTA scheduler doubles as the load balancer for the random
+// survivor counts.
+//
+//   per warp: 32 lanes of x -> (optional RMSNorm scale) -> |x| > thr -> ballot = survivor set
+//             -> for each surviving lane m (warp-uniform): LDG.128 of W[m][tile] (512 B coalesced per
+//                instruction, up to 8 rows in flight per lane), FFMA2 in fp32 against x[m] (shuffle)
+//   per CTA : 4 warp partials -> shared memory -> fp32 vector RED into the L2-resident accumulator
+//   per tile: arrival counter; the last CTA converts the tile to fp16, applies the epilogue
+//             (+residual / SiLU(gate)*up), writes the tile's sum of squares for the next RMSNorm and
+//             re-zeroes accumulator + counter (no memset launch, nothing to clean up afterwards).
+//
+// The RMSNorm of the consumer is fused without any CTA reading the whole vector: the producer of the
+// residual stream (embedding, o-proj, down-proj finalisers) leaves per-tile sums of squares, the
+// consumer adds <= 64 floats.
+//
+// Replaces kernels/sparse_gemv.py:45-83 (splitk_sparse_gemv_kernel + its Y.zero_() pre-hook) and
+// :147-194 (qkv_kernel) of the reference; thresholds are selected per column region exactly.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace teal {
+
+namespace {
+
+
+__device__ __forceinline__ void rc_ffma2(float2& acc, const float2 w, const float2 x) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(*reinterpret_cast<unsigned long long*>(&acc))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&w)), "l"(*reinterpret_cast<const unsigned long long*>(&x)));
+}
+// streaming 16-byte load: read-only path, no L1 allocation, L2 evict-first (weights are read once per token)
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p, uint64_t policy) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
+
+}  // namespace
+
+// VEC: 16-byte vectors per lane per row (column tile = 256 * VEC); U: rows in flight per lane;
+// WARPS: warps per CTA (each owns 32-lane groups of the CTA's K chunk).
+template <int VEC, int U, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
+  constexpr int COLS = 256 * VEC;
+  constexpr int kRcWarps = WARPS;
+  constexpr int kRcThreads = WARPS * 32;
+  __shared__ __align__(16) float s_red[kRcWarps][COLS];
+  __shared__ float s_ssq[kRcWarps];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // ---- which (column tile, K chunk) is mine: column tile varies fastest so that concurrently running
+  // CTAs read neighbouring pieces of the same weight rows ---------------------------------------------
+  const int ct = (int)(blockIdx.x % (unsigned)p.total_ctiles);
+  const int kc = (int)(blockIdx.x / (unsigned)p.total_ctiles);
+  int s = 0;
+#pragma unroll
+  for (int j = 1; j < kMaxSeg; ++j) s += (j < p.nseg && ct >= p.seg[j].ctile0) ? 1 : 0;
+  const RcSeg& sg = p.seg[s];
+  const int col0 = (ct - sg.ctile0) * COLS;
+  const int wcols = min(COLS, sg.ncols - col0);
+  const float thr = sg.thr;
+  bool vact[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) vact[v] = lane * 8 + 256 * v < wcols;
+  const __half* wbase = sg.w + col0 + lane * 8;
+  const long long ldw = sg.ldw;
+  const uint64_t policy = make_evict_first_policy();
+
+  griddep_wait();                 // PDL: everything above overlapped the previous kernel's tail
+  griddep_launch_dependents();    // the next kernel may start launching once all our CTAs are running
+
+  // ---- RMSNorm scale from the producer's per-tile sums of squares (gpt-fast/model.py:286-291) --------
+  float rs = 1.f;
+  if (p.in_mode == kInRmsNorm) {
+    float t = 0.f;
+    for (int i = lane; i < p.n_ssq_in; i += 32) t += __ldcg(p.ssq_in + i);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    rs = rsqrtf(t / (float)p.Z + p.eps);
+  }
+
+  float2 acc[VEC][4];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[v][c] = make_float2(0.f, 0.f);
+
+  const int kbeg = kc * p.rows_per_cta;
+  const int kend = min(p.Z, kbeg + p.rows_per_cta);
+  int my_nnz = 0;
+  for (int k0 = kbeg + warp * 32; k0 < kend; k0 += kRcWarps * 32) {
+    const int k = k0 + lane;
+    float xf = 0.f;
+    if (k < kend) {
+      const __half xh = p.x[k];
+      if (p.in_mode == kInRmsNorm) {
+        // fp32 norm, cast to fp16, multiply by the fp16 weight in fp16
+        xf = __half2float(__hmul(__float2half_rn(__half2float(xh) * rs), p.norm_w[k]));
+        if (p.x_out && ct == 0) p.x_out[k] = __float2half_rn(xf);
+      } else {
+        xf = __half2float(xh);
+      }
+    }
+    const bool keep = (k < kend) && !(fabsf(xf) <= thr);  // strict >, NaN kept (it must poison y like mask*x)
+    unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (p.keep_out && ct == 0 && k < kend) p.keep_out[k] = keep ? 1 : 0;
+    my_nnz += __popc(mask);
+    if (p.mode == kModeSurvivors) mask = 0u;  // parity hook: thresholds only, no weights
+    while (mask) {
+      int bit[U];
+      uint4 wv[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bit[u] = mask ? (__ffs(mask) - 1) : -1;
+        mask &= mask - 1;  // no-op when mask == 0
+        if (bit[u] >= 0) {
+          const __half* src = wbase + (long long)(k0 + bit[u]) * ldw;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            if (vact[v]) wv[u][v] = ld_stream_u4(src + 256 * v, policy);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (bit[u] >= 0) {
+          const float xs = __shfl_sync(0xffffffffu, xf, bit[u]);
+          const float2 x2 = make_float2(xs, xs);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if (vact[v]) {
+              rc_ffma2(acc[v][0], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].x)), x2);
+              rc_ffma2(acc[v][1], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].y)), x2);
+              rc_ffma2(acc[v][2], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].z)), x2);
+              rc_ffma2(acc[v][3], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].w)), x2);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (p.probe && lane == 0) {  // measurement probe: gathered vs dense weight bytes
+    atomicAdd(p.probe, (unsigned long long)my_nnz * (unsigned long long)wcols * 2ull);
+    const int rows = max(0, min(kend, kbeg + p.rows_per_cta) - kbeg);
+    if (warp == 0) atomicAdd(p.probe + 1, (unsigned long long)rows * (unsigned long long)wcols * 2ull);
+  }
+  if (p.mode == kModeSurvivors) return;
+
+  // ---- CTA partial: 4 warps -> smem -> fp32 vector RED into the L2 accumulator ------------------------
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float* d = &s_red[warp][lane * 8 + 256 * v];
+    *reinterpret_cast<float4*>(d) = make_float4(acc[v][0].x, acc[v][0].y, acc[v][1].x, acc[v][1].y);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(acc[v][2].x, acc[v][2].y, acc[v][3].x, acc[v][3].y);
+  }
+  __syncthreads();
+  const int acc0 = sg.acc_col0 + col0;
+  for (int c = tid * 4; c < wcols; c += kRcThreads * 4) {
+    float4 a = *reinterpret_cast<const float4*>(&s_red[0][c]);
+#pragma unroll
+    for (int w = 1; w < kRcWarps; ++w) {
+      const float4 b = *reinterpret_cast<const float4*>(&s_red[w][c]);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) red_add_v4(p.acc + acc0 + c, a);
+  }
+  // ---- arrival counter: REDs of all threads happen-before the barrier, thread 0's release fence is
+  // cumulative over them; the last arrival acquires and finalises the tile ------------------------------
+  __syncthreads();
+  const int pair = p.mode == kModePairSilu;
+  const int cidx = pair ? (ct - sg.ctile0) : ct;
+  if (tid == 0) {
+    fence_acq_rel_gpu();
+    const unsigned old = atomicAdd(&p.counters[cidx], 1u);
+    const int last = ((int)old + 1 == p.target) ? 1 : 0;
+    if (last) fence_acq_rel_gpu();
+    s_last = last;
+  }
+  __syncthreads();
+  if (!s_last) return;
+
+  float ssq = 0.f;
+  if (pair) {
+    const int g0 = p.seg[0].acc_col0 + col0, u0 = p.seg[1].acc_col0 + col0;
+    for (int c = tid * 4; c < wcols; c += kRcThreads * 4) {
+      const float4 g = ld_cg_f4(p.acc + g0 + c), u = ld_cg_f4(p.acc + u0 + c);
+      st_cg_f4(p.acc + g0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      st_cg_f4(p.acc + u0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      const __half2 h0 = __halves2half2(silu_mul_f16(g.x, u.x), silu_mul_f16(g.y, u.y));
+      const __half2 h1 = __halves2half2(silu_mul_f16(g.z, u.z), silu_mul_f16(g.w, u.w));
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.y + col0 + c) = o;
+    }
+  } else {
+    const int y0 = sg.y_col0 + col0;
+    for (int c = tid * 4; c < wcols; c += kRcThreads * 4) {
+      const float4 a = ld_cg_f4(p.acc + acc0 + c);
+      st_cg_f4(p.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      if (p.out_mode == kOutAddResidual) {  // h = x + y in fp16 (gpt-fast/model.py:160-161)
+        const uint2 r = *reinterpret_cast<const uint2*>(p.resid + y0 + c);
+        h0 = __hadd2(*reinterpret_cast<const __half2*>(&r.x), h0);
+        h1 = __hadd2(*reinterpret_cast<const __half2*>(&r.y), h1);
+      }
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.y + y0 + c) = o;
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      ssq = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, ssq))));
+    }
+  }
+  if (p.ssq_out) {  // this tile's contribution to the next RMSNorm (fixed reduction order: deterministic)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+    if (lane == 0) s_ssq[warp] = ssq;
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRcWarps; ++w) a += s_ssq[w];
+      p.ssq_out[cidx] = a;
+    }
+  }
+  if (tid == 0) p.counters[cidx] = 0;
+}
+
+// Sum-of-squares partials of a vector that did not come out of a GEMV finaliser (embedding row, tests).
+__global__ void ssq_kernel(const __half* __restrict__ x, int Z, float* __restrict__ ssq_out, int nparts) {
+  griddep_wait();
+  // part i covers [i*len, (i+1)*len)
+  const int len = (Z + nparts - 1) / nparts;
+  const int i = blockIdx.x;
+  float t = 0.f;
+  for (int k = i * len + threadIdx.x; k < min(Z, (i + 1) * len); k += blockDim.x) {
+    const float f = __half2float(x[k]);
+    t = fmaf(f, f, t);
+  }
+  __shared__ float sp[32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sp[w];
+    ssq_out[i] = a;
+  }
+  griddep_launch_dependents();
+}
+
+// keep-mask -> sorted index list (single CTA; parity hook only)
+__global__ void mask_to_indices_kernel(const unsigned char* __restrict__ keep, int Z, int* __restrict__ idx, int* __restrict__ cnt) {
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < Z; k0 += blockDim.x) {
+    const int k = k0 + threadIdx.x;
+    const bool kp = k < Z && keep[k];
+    const unsigned m = __ballot_sync(0xffffffffu, kp);
+    __shared__ int s_w[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    if (kp) idx[off + __popc(m & ((1u << lane) - 1u))] = k;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_w[w];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cnt[0] = s_base;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream,
+                    int variant) {
+  if (gp.Z <= 0 || gp.Z > (1 << 20)) return set_error(TEAL_ERR_BAD_ARG, "Z out of range");
+  RcParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = gp.x; p.y = gp.y; p.norm_w = gp.norm_w; p.resid = gp.resid; p.x_out = gp.x_out;
+  p.ssq_in = gp.ssq_in; p.n_ssq_in = gp.n_ssq_in; p.ssq_out = gp.ssq_out; p.keep_out = gp.keep_out;
+  p.probe = bytes_probe();
+  p.Z = gp.Z; p.mode = gp.mode; p.in_mode = gp.in_mode; p.out_mode = gp.out_mode; p.eps = gp.eps;
+  p.nseg = gp.nseg;
+  if (gp.mode != kModeSurvivors) {
+    if (!workspace || ws_bytes < workspace_bytes(out_cols_total)) return set_error(TEAL_ERR_WORKSPACE, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(gp.y) & 7)) return set_error(TEAL_ERR_ALIGNMENT, "y must be 8-byte aligned");
+    p.counters = reinterpret_cast<unsigned*>(workspace);
+    p.acc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)kMaxCounters * 4);
+  }
+  if (gp.in_mode == kInRmsNorm && (!gp.norm_w || !gp.ssq_in || gp.n_ssq_in <= 0))
+    return set_error(TEAL_ERR_BAD_ARG, "RMSNorm mode needs norm_w and the producer's sum-of-squares partials");
+  if (gp.out_mode == kOutAddResidual && (!gp.resid || (reinterpret_cast<uintptr_t>(gp.resid) & 7)))
+    return set_error(TEAL_ERR_ALIGNMENT, "residual must be non-null and 8-byte aligned");
+  struct Variant { int vec, u, warps, rows; void (*kern)(const RcParams); };
+#define TEAL_RC(V, UU, W, R) {V, UU, W, R, rowchunk_gemv_kernel<V, UU, W>}
+  static const Variant kVariants[] = {
+      TEAL_RC(1, 8, 4, 128),   // 0
+      TEAL_RC(2, 4, 4, 128),   // 1
+      TEAL_RC(1, 8, 2, 64),    // 2
+      TEAL_RC(2, 4, 2, 64),    // 3
+      TEAL_RC(1, 16, 4, 128),  // 4
+      TEAL_RC(2, 8, 4, 128),   // 5
+      TEAL_RC(1, 16, 2, 64),   // 6
+      TEAL_RC(2, 8, 2, 64),    // 7
+      TEAL_RC(1, 8, 1, 32),    // 8
+      TEAL_RC(2, 8, 1, 32),    // 9
+      TEAL_RC(1, 8, 4, 256),   // 10
+      TEAL_RC(1, 16, 1, 32),   // 11
+  };
+#undef TEAL_RC
+  constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+  if (variant < 0 || variant >= kNumVariants) variant = 0;
+  const Variant& var = kVariants[variant];
+  const int vec = var.vec;
+  const int cols = 256 * vec;
+  int rows = var.rows;
+  int ctile0 = 0;
+  for (int s = 0; s < gp.nseg; ++s) {
+    const GemvSeg& g = gp.seg[s];
+    if (g.ncols <= 0 || (g.ncols & 7) || (g.ldw & 7) || (g.out_col0 & 7) || (reinterpret_cast<uintptr_t>(g.w) & 15))
+      return set_error(TEAL_ERR_ALIGNMENT, "weights: N, ldw, region offsets must be multiples of 8 and 16-byte aligned");
+    RcSeg& r = p.seg[s];
+    r.w = g.w; r.ldw = g.ldw; r.ncols = g.ncols; r.acc_col0 = g.out_col0;
+    r.y_col0 = g.out_col0; r.thr = gp.thr[g.thr_slot];
+    r.ctile0 = ctile0; r.nctiles = (g.ncols + cols - 1) / cols;
+    ctile0 += r.nctiles;
+  }
+  if (gp.mode == kModeSurvivors) {  // threshold + keep-mask only: one pseudo column tile
+    p.nseg = 1;
+    p.seg[0] = RcSeg{};
+    p.seg[0].thr = gp.thr[0];
+    p.seg[0].ncols = 8;
+    p.seg[0].nctiles = 1;
+    ctile0 = 1;
+  }
+  p.total_ctiles = ctile0;
+  const bool pair = gp.mode == kModePairSilu;
+  if (pair && (gp.nseg != 2 || p.seg[0].nctiles != p.seg[1].nctiles)) return set_error(TEAL_ERR_BAD_ARG, "pair mode needs two equal segments");
+  const int ncounters = pair ? p.seg[0].nctiles : ctile0;
+  if (ncounters > kMaxCounters) return set_error(TEAL_ERR_UNSUPPORTED, "too many column tiles");
+  p.rows_per_cta = rows;
+  p.nkchunks = (gp.Z + rows - 1) / rows;
+  p.target = pair ? 2 * p.nkchunks : p.nkchunks;
+  const long long grid = (long long)p.total_ctiles * p.nkchunks;
+  if (grid > 0x7fffffffll) return set_error(TEAL_ERR_UNSUPPORTED, "grid too large");
+
+  void (*kern)(const RcParams) = var.kern;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(var.warps * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return set_cuda_error(e, "rowchunk_gemv launch");
+  return TEAL_OK;
+}
+
+int launch_ssq(const __half* x, int Z, float* ssq_out, int nparts, cudaStream_t stream) {
+  if (!x || !ssq_out || Z <= 0 || nparts <= 0 || nparts > 64) return set_error(TEAL_ERR_BAD_ARG, "ssq: bad argument");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nparts);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, ssq_kernel, x, Z, ssq_out, nparts);
+  if (e != cudaSuccess) return set_cuda_error(e, "ssq launch");
+  return TEAL_OK;
+}
+
+int launch_mask_to_indices(const unsigned char* keep, int Z, int* idx, int* cnt, cudaStream_t stream) {
+  mask_to_indices_kernel<<<1, 1024, 0, stream>>>(keep, Z, idx, cnt);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "mask_to_indices launch");
+  return TEAL_OK;
+}
+
+}  // namespace teal

@@ -526,7 +526,8 @@ int sub_cols_override() { return g_sub_cols; }
 int set_config(int id) {
   g_sub_cols = 0;
   if (id >= 1000) { g_sub_cols = (id / 1000) * 256; id %= 1000; }  // e.g. 2014: sub-tile 512, 4 tiles
-  if (id < 0 || (id > kNumConfigs && (id < 11 || id > 26)) || g_sub_cols > 1024) return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
+  if (id < 0 || (id > kNumConfigs && (id < 11 || id > 26) && (id < 30 || id > 49)) || g_sub_cols > 1024)
+    return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
   g_forced_config = id;
   return TEAL_OK;
 }
@@ -536,23 +537,35 @@ static int pick_config(const GemvParams& p) {
   return 0;
 }
 
-// Config ids: 0 = default (gather_gemv, 4 tiles per matrix, 2 for the fused gate/up pair);
-// 1..6 = the TMA-bulk-ring kernel of this file; 10+T = gather_gemv with T tiles per matrix.
+// Config ids: 0 = default = rowchunk_gemv (many small CTAs), 30 + v = rowchunk variant v
+// (bit 0: 512-column tiles, bits 1-2: rows per CTA = 128 << n);
+// 1..6 = the TMA-bulk-ring kernel of this file; 10 + T = gather_gemv (cp.async rings) with T tiles per matrix.
+// The two alternative kernels are kept as measured design points; they do not
+// implement the sum-of-squares hand-off, so the fused-RMSNorm entry points always use rowchunk_gemv.
 int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream) {
   const int id = g_forced_config;
-  if (id >= 1 && id <= kNumConfigs) {
-    if (p.in_mode != kInPlain || p.out_mode != kOutPlain || p.x_out)
-      return set_error(TEAL_ERR_UNSUPPORTED, "fused norm/residual modes need the gather_gemv kernel");
+  const bool needs_rc = p.in_mode != kInPlain || p.ssq_out || p.keep_out || p.mode == kModeSurvivors;
+  if (id >= 1 && id <= kNumConfigs && !needs_rc && p.out_mode == kOutPlain && !p.x_out)
     return launch_gemv(p, workspace, ws_bytes, out_cols_total, stream);
+  if (id >= 11 && id <= 26 && !needs_rc)
+    return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, id - 10);
+  int variant;
+  if (id >= 30 && id <= 49) {
+    variant = id - 30;
+  } else {  // measured on B200 (profiles/r01_bench_gemv_history.jsonl): wide tiles pay off once a launch moves >= ~40 MB
+    long long elems = 0;
+    for (int s = 0; s < p.nseg; ++s) elems += (long long)p.Z * p.seg[s].ncols;
+    variant = (elems >= 40ll * 1000 * 1000) ? 1 : 2;
   }
-  int tiles = (p.mode == kModePairSilu) ? 2 : 4;
-  if (id > 10) tiles = id - 10;
-  return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, tiles);
+  return launch_rowchunk(p, workspace, ws_bytes, out_cols_total, stream, variant);
 }
 
 size_t workspace_bytes(int max_out_cols) {
   size_t acc = ((size_t)max_out_cols * 4 + 255) & ~(size_t)255;
-  return (size_t)kMaxCounters * 4 + acc;
+  return (size_t)kMaxCounters * 4 + acc + (size_t)kSsqParts * 4;  // [counters][acc][ssq scratch]
+}
+float* workspace_ssq_scratch(void* workspace, size_t ws_bytes) {
+  return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + ws_bytes - (size_t)kSsqParts * 4);
 }
 
 int launch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream) {

@@ -136,6 +136,7 @@ class SparseDecoder:
         self.h = torch.zeros(1, 1, self.inter_l, dtype=f16, device=dev)
         self.part = torch.zeros(1, 1, a.dim, dtype=f16, device=dev)
         self.logits = torch.zeros(1, 1, a.vocab_size, dtype=f16, device=dev)
+        self.ssq = torch.zeros(64, dtype=torch.float32, device=dev)  # sum-of-squares partials of the residual stream
         self.stream = torch.cuda.Stream(device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_mode = None
@@ -253,7 +254,8 @@ class SparseDecoder:
         wsp, wsn = ws.data_ptr(), ws.numel()
         chk = _lib.check
         n_launch = 0
-        chk(lib.teal_embed_f16(self.tok_emb.data_ptr(), self.token.data_ptr(), self.x.data_ptr(), a.dim, sp), "embed")
+        ssq = self.ssq.data_ptr() if self.world == 1 else None  # TP: x is updated by torch ops, no hand-off
+        chk(lib.teal_embed_f16(self.tok_emb.data_ptr(), self.token.data_ptr(), self.x.data_ptr(), ssq, a.dim, sp), "embed")
         n_launch += 1
         dense_t = {p: -1.0 for p in PROJS}
         for li in range(a.n_layer):
@@ -265,7 +267,7 @@ class SparseDecoder:
                 torch.matmul(xn, W["wqkv"].T, out=self.qkv)
             else:
                 xn_out = torch.empty_like(self.x) if tap is not None else None
-                chk(lib.teal_norm_sparse_qkv_gemv_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps,
+                chk(lib.teal_norm_sparse_qkv_gemv_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps, ssq,
                                                       W["wqkv"].data_ptr(), self.qkv.data_ptr(),
                                                       xn_out.data_ptr() if tap is not None else None, a.dim, self.nqkv_l,
                                                       W["wqkv"].stride(1), self.kv_l, t["q"], t["k"], t["v"], wsp, wsn, sp),
@@ -292,7 +294,7 @@ class SparseDecoder:
                 continue
             if self.world == 1:
                 chk(lib.teal_sparse_gemv_residual_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(),
-                                                      self.x.data_ptr(), self.dim_l, a.dim, W["wo"].stride(1), t["o"],
+                                                      self.x.data_ptr(), ssq, self.dim_l, a.dim, W["wo"].stride(1), t["o"],
                                                       wsp, wsn, sp), "o_proj")
             else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
                 chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.part.data_ptr(), self.dim_l,
@@ -300,7 +302,7 @@ class SparseDecoder:
                 self._allreduce(self.part)
                 self.x.add_(self.part)
             xn_out = torch.empty_like(self.x) if tap is not None else None
-            chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps,
+            chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq,
                                                  W["w1"].data_ptr(), W["w3"].data_ptr(), self.h.data_ptr(),
                                                  xn_out.data_ptr() if tap is not None else None, a.dim, self.inter_l,
                                                  W["w1"].stride(1), W["w3"].stride(1), t["gate"], t["up"], wsp, wsn, sp),
@@ -310,7 +312,7 @@ class SparseDecoder:
                 tap["mlp_h2"].append(self.h.flatten().float().cpu())
             if self.world == 1:
                 chk(lib.teal_sparse_gemv_residual_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(),
-                                                      self.x.data_ptr(), self.inter_l, a.dim, W["w2"].stride(1),
+                                                      self.x.data_ptr(), ssq, self.inter_l, a.dim, W["w2"].stride(1),
                                                       t["down"], wsp, wsn, sp), "down_proj")
             else:
                 chk(lib.teal_sparse_gemv_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.part.data_ptr(), self.inter_l,

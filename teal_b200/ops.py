@@ -131,7 +131,7 @@ def norm_qkv_gemv(x, norm_w, eps, weight, tq, tk, tv, kv_size, want_xn=False):
     xn = torch.empty(1, 1, Z, device=x.device, dtype=torch.float16) if want_xn else None
     sp = _stream_ptr()
     ws = workspace(x.device, sp)
-    rc = _lib.load().teal_norm_sparse_qkv_gemv_f16(x.data_ptr(), norm_w.data_ptr(), float(eps), weight.data_ptr(),
+    rc = _lib.load().teal_norm_sparse_qkv_gemv_f16(x.data_ptr(), norm_w.data_ptr(), float(eps), None, weight.data_ptr(),
                                                    out.data_ptr(), xn.data_ptr() if want_xn else None, Z, N, ldw,
                                                    int(kv_size), float(tq), float(tk), float(tv), ws.data_ptr(),
                                                    ws.numel(), sp)
@@ -148,7 +148,7 @@ def norm_gate_up(x, norm_w, eps, w1, w3, t_gate, t_up, want_xn=False):
     xn = torch.empty(1, 1, Z, device=x.device, dtype=torch.float16) if want_xn else None
     sp = _stream_ptr()
     ws = workspace(x.device, sp)
-    rc = _lib.load().teal_norm_sparse_gate_up_f16(x.data_ptr(), norm_w.data_ptr(), float(eps), w1.data_ptr(),
+    rc = _lib.load().teal_norm_sparse_gate_up_f16(x.data_ptr(), norm_w.data_ptr(), float(eps), None, w1.data_ptr(),
                                                   w3.data_ptr(), out.data_ptr(), xn.data_ptr() if want_xn else None,
                                                   Z, I, ld1, ld3, float(t_gate), float(t_up), ws.data_ptr(),
                                                   ws.numel(), sp)
@@ -165,7 +165,7 @@ def gemv_residual(x, weight, resid, threshold):
     sp = _stream_ptr()
     ws = workspace(x.device, sp)
     rc = _lib.load().teal_sparse_gemv_residual_f16(x.data_ptr(), weight.data_ptr(), resid.data_ptr(), out.data_ptr(),
-                                                   Z, N, ldw, float(threshold), ws.data_ptr(), ws.numel(), sp)
+                                                   None, Z, N, ldw, float(threshold), ws.data_ptr(), ws.numel(), sp)
     _lib.check(rc, "teal_sparse_gemv_residual_f16")
     return out
 

@@ -99,7 +99,8 @@ def test_attention_kernel_vs_sdpa():
     for p in range(20):
         qkv = torch.randn((n_head + 2 * n_kv) * hd).half()
         pos.fill_(p)
-        rc = lib.teal_attn_decode_f16(qkv.cuda().data_ptr(), freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), pos.data_ptr(),
+        qg = qkv.cuda()
+        rc = lib.teal_attn_decode_f16(qg.data_ptr(), freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), pos.data_ptr(),
                                       out.data_ptr(), n_head, n_kv, hd, S, torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         q, k, v = qkv.split([n_head * hd, n_kv * hd, n_kv * hd])
@@ -125,8 +126,10 @@ def test_dense_rowmajor_gemv_and_argmax():
         W = (torch.randn(V, Z) * 0.02).half()
         y = torch.zeros(V, dtype=torch.float16, device="cuda")
         am = torch.zeros(1, dtype=torch.int64, device="cuda")
-        rc = lib.teal_dense_gemv_f16(x.cuda().data_ptr(), nw.cuda().data_ptr(), 1e-5, W.cuda().data_ptr(), y.data_ptr(),
+        xg, ng, Wg = x.cuda(), nw.cuda(), W.cuda()  # keep the device copies alive across the async launch
+        rc = lib.teal_dense_gemv_f16(xg.data_ptr(), ng.data_ptr(), 1e-5, Wg.data_ptr(), y.data_ptr(),
                                      am.data_ptr(), Z, V, Z, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
         assert rc == 0
         xn = O.rms_norm(x.view(1, 1, Z), nw, 1e-5).view(Z)
         want = W.float() @ xn.float()

@@ -78,7 +78,7 @@ def test_survivor_tie_rule(golden_dir):
     assert 0 not in got and 1 not in got and 2 in got
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 11, 12, 14, 18, 26])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 11, 12, 14, 18, 26, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41])
 def test_golden_cases_all_configs(golden_dir, cfg):
     ops = _ops()
     ops.set_config(cfg)
@@ -120,7 +120,7 @@ def test_full_size_vs_oracle(Z, N, sparsity):
 
 
 @pytest.mark.parametrize("sparsity", [0.0, 0.1, 0.4, 0.9, 0.99, 1.0])
-@pytest.mark.parametrize("cfg", [0, 2, 5, 12, 18])
+@pytest.mark.parametrize("cfg", [0, 2, 5, 12, 18, 31, 33, 36, 38, 41])
 def test_sparsity_sweep_config1(sparsity, cfg):
     """BASELINE config 1: Llama-2-7B gate_proj 4096 -> 11008."""
     ops = _ops()
