@@ -156,13 +156,7 @@ class SparseDecoder:
         f16 = torch.float16
         r, w = self.rank, self.world
 
-        def shard(t, dim):
-            return torch.tensor_split(t, w, dim=dim)[r] if w > 1 else t
-
-        def shard_qkv(t):                                                        # tp.py:73-78
-            q, k, v = t.split([a.dim, a.n_local_heads * self.hd, a.n_local_heads * self.hd], dim=0)
-            return torch.cat((shard(q, 0), shard(k, 0), shard(v, 0)), dim=0)
-
+        from . import tp as _tp
         self.layers = []
         if sd is None:
             self.tok_emb = torch.empty(a.vocab_size, a.dim, dtype=f16, device=dev).normal_(0, 1.0, generator=g)
@@ -178,16 +172,17 @@ class SparseDecoder:
                 self.layers.append(L)
         else:
             cm = ops.to_column_major
+            sd = _tp.shard_state_dict(sd, a.dim, a.n_head, a.n_local_heads, a.n_layer, r, w)
             self.tok_emb = sd["tok_embeddings.weight"].to(dev, f16).contiguous()
             self.lm_head = sd["output.weight"].to(dev, f16).contiguous()
             self.final_norm = sd["norm.weight"].to(dev, f16).contiguous()
             for i in range(a.n_layer):
                 p = f"layers.{i}."
-                L = dict(wqkv=cm(shard_qkv(sd[p + "attention.wqkv.weight"]).to(dev, f16)),
-                         wo=cm(shard(sd[p + "attention.wo.weight"], 1).to(dev, f16)),
-                         w1=cm(shard(sd[p + "feed_forward.w1.weight"], 0).to(dev, f16)),
-                         w3=cm(shard(sd[p + "feed_forward.w3.weight"], 0).to(dev, f16)),
-                         w2=cm(shard(sd[p + "feed_forward.w2.weight"], 1).to(dev, f16)),
+                L = dict(wqkv=cm(sd[p + "attention.wqkv.weight"].to(dev, f16)),
+                         wo=cm(sd[p + "attention.wo.weight"].to(dev, f16)),
+                         w1=cm(sd[p + "feed_forward.w1.weight"].to(dev, f16)),
+                         w3=cm(sd[p + "feed_forward.w3.weight"].to(dev, f16)),
+                         w2=cm(sd[p + "feed_forward.w2.weight"].to(dev, f16)),
                          attn_norm=sd[p + "attention_norm.weight"].to(dev, f16).contiguous(),
                          ffn_norm=sd[p + "ffn_norm.weight"].to(dev, f16).contiguous())
                 self.layers.append(L)
@@ -243,7 +238,8 @@ class SparseDecoder:
 
     def _allreduce(self, t):
         if self.world > 1:
-            torch.distributed.all_reduce(t, group=self.pg)
+            from . import tp as _tp
+            _tp.all_reduce_sum(t, self.pg)
 
     def _enqueue_step(self, mode: str):
         """mode: 'sparse' (fused kernels with thresholds), 'dense_own' (same kernels, nothing dropped),
