@@ -126,6 +126,9 @@ int teal_attn_decode_f16(const void* qkv, const void* freqs_cis, void* k_cache, 
  * argmax_packed (nullable, uint64[1], zero before the call) receives the packed arg-max. */
 int teal_dense_gemv_f16(const void* x, const void* norm_w, double eps, const void* w, void* y,
                         void* argmax_packed, int Z, int V, int64_t ldw, void* stream);
+/* Tensor-parallel path: x += part (the all-reduced o/down partial, fp16 add of gpt-fast/model.py:160-161
+ * after the all-reduce of tp.py:120-121,139-140) and the sum-of-squares partials of the new x. */
+int teal_residual_add_f16(void* x, const void* part, float* ssq_out, int dim, void* stream);
 /* Greedy step bookkeeping: *token = arg-max index, out_tokens[*pos] = *token, ++*pos, reset cell. */
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap,
                  void* stream);

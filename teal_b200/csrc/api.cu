@@ -249,6 +249,10 @@ int teal_dense_gemv_f16(const void* x, const void* norm_w, double eps, const voi
                                reinterpret_cast<unsigned long long*>(argmax_packed), Z, V, ldw,
                                reinterpret_cast<cudaStream_t>(stream));
 }
+int teal_residual_add_f16(void* x, const void* part, float* ssq_out, int dim, void* stream) {
+  return launch_residual_add(reinterpret_cast<__half*>(x), reinterpret_cast<const __half*>(part), ssq_out, dim,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap, void* stream) {
   return launch_advance(reinterpret_cast<unsigned long long*>(argmax_packed), token, pos, out_tokens, out_cap,
                         reinterpret_cast<cudaStream_t>(stream));

@@ -143,6 +143,7 @@ int forced_config();
 void set_pdl(bool on);
 bool pdl_enabled();
 int sub_cols_override();
+bool wave_balance_enabled();
 void set_bytes_probe(unsigned long long* p);
 unsigned long long* bytes_probe();
 int launch_gather_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream,
@@ -160,6 +161,7 @@ int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, 
                        __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream);
 int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,
                           unsigned long long* argmax_packed, int Z, int V, long long ldw, cudaStream_t stream);
+int launch_residual_add(__half* x, const __half* part, float* ssq_out, int dim, cudaStream_t stream);
 int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap,
                    cudaStream_t stream);
 

@@ -121,33 +121,45 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
   const __half* kbase = k_cache + (size_t)kvh * max_seq * HD;
   const __half* vbase = v_cache + (size_t)kvh * max_seq * HD;
-  for (int p = warp; p <= pos; p += kAttnWarps) {
-    float kk[EPL], vv[EPL];
-    if (p == pos) {
+  // 4 positions per iteration so that the 8 global loads of a lane are independent (latency-bound at short context)
+  constexpr int PB = 4;
+  for (int p0 = warp; p0 <= pos; p0 += kAttnWarps * PB) {
+    float kk[PB][EPL], vv[PB][EPL];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) { kk[e] = s_knew[lane * EPL + e]; vv[e] = s_vnew[lane * EPL + e]; }
-    } else {
-      const __half2* kp = reinterpret_cast<const __half2*>(kbase + (size_t)p * HD + lane * EPL);
-      const __half2* vp = reinterpret_cast<const __half2*>(vbase + (size_t)p * HD + lane * EPL);
+    for (int b = 0; b < PB; ++b) {
+      const int p = p0 + b * kAttnWarps;
+      if (p < pos) {
+        const __half2* kp = reinterpret_cast<const __half2*>(kbase + (size_t)p * HD + lane * EPL);
+        const __half2* vp = reinterpret_cast<const __half2*>(vbase + (size_t)p * HD + lane * EPL);
 #pragma unroll
-      for (int e = 0; e < EPL / 2; ++e) {
-        const float2 kf = __half22float2(kp[e]), vf = __half22float2(vp[e]);
-        kk[2 * e] = kf.x; kk[2 * e + 1] = kf.y;
-        vv[2 * e] = vf.x; vv[2 * e + 1] = vf.y;
+        for (int e = 0; e < EPL / 2; ++e) {
+          const float2 kf = __half22float2(kp[e]), vf = __half22float2(vp[e]);
+          kk[b][2 * e] = kf.x; kk[b][2 * e + 1] = kf.y;
+          vv[b][2 * e] = vf.x; vv[b][2 * e + 1] = vf.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { kk[b][e] = s_knew[lane * EPL + e]; vv[b][e] = s_vnew[lane * EPL + e]; }
       }
     }
-    float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) s = fmaf(qreg[e], kk[e], s);
+    for (int b = 0; b < PB; ++b) {
+      const int p = p0 + b * kAttnWarps;
+      if (p <= pos) {
+        float s = 0.f;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    s *= scale;
-    const float mn = fmaxf(m, s);
-    const float corr = __expf(m - mn), pe = __expf(s - mn);
-    l = l * corr + pe;
+        for (int e = 0; e < EPL; ++e) s = fmaf(qreg[e], kk[b][e], s);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pe, vv[e], acc[e] * corr);
-    m = mn;
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        s *= scale;
+        const float mn = fmaxf(m, s);
+        const float corr = __expf(m - mn), pe = __expf(s - mn);
+        l = l * corr + pe;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pe, vv[b][e], acc[e] * corr);
+        m = mn;
+      }
+    }
   }
   if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
 #pragma unroll
@@ -302,6 +314,38 @@ __global__ void advance_kernel(unsigned long long* argmax_packed, int* token, in
   griddep_launch_dependents();
 }
 
+// --------------------------------------------------------------------------------------------
+// TP path: x += all-reduced partial (fp16 add, gpt-fast/model.py:160-161 after tp.py:120-121,139-140) and the
+// sum of squares of the new residual stream for the next RMSNorm, in one tiny launch.
+// --------------------------------------------------------------------------------------------
+__global__ void residual_add_kernel(__half* __restrict__ x, const __half* __restrict__ part, float* __restrict__ ssq_out,
+                                    int dim) {
+  __shared__ float sp[32];
+  griddep_wait();
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < dim / 2; i += blockDim.x) {
+    const __half2 a = reinterpret_cast<const __half2*>(x)[i], b = reinterpret_cast<const __half2*>(part)[i];
+    const __half2 r = __hadd2(a, b);
+    reinterpret_cast<__half2*>(x)[i] = r;
+    const float2 f = __half22float2(r);
+    ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+  }
+  if (ssq_out) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sp[w];
+      ssq_out[0] = a;
+    } else if (threadIdx.x < kSsqParts) {
+      ssq_out[threadIdx.x] = 0.f;
+    }
+  }
+  griddep_launch_dependents();
+}
+
 // ---------------------------------------------------------------------------------- launchers
 template <typename... KArgs, typename... Args>
 static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const char* what,
@@ -362,6 +406,11 @@ int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, cons
   if ((long long)grid * rows_per_cta > V) grid = (V + rows_per_cta - 1) / rows_per_cta;
   return launch_pdl(kern, dim3(grid), dim3(kHeadThreads), smem, stream, "dense gemv launch", x, norm_w, eps, W, y,
                     argmax_packed, Z, V, ldw);
+}
+
+int launch_residual_add(__half* x, const __half* part, float* ssq_out, int dim, cudaStream_t stream) {
+  if (!x || !part || dim <= 0 || (dim & 1)) return set_error(TEAL_ERR_BAD_ARG, "residual_add: bad argument");
+  return launch_pdl(residual_add_kernel, dim3(1), dim3(1024), 0, stream, "residual_add launch", x, part, ssq_out, dim);
 }
 
 int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap,

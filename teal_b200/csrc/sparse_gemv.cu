@@ -520,10 +520,14 @@ bool pdl_enabled() { return g_pdl; }
 static unsigned long long* g_probe = nullptr;
 void set_bytes_probe(unsigned long long* q) { g_probe = q; }
 unsigned long long* bytes_probe() { return g_probe; }
+static bool g_wave_balance = true;
+bool wave_balance_enabled() { return g_wave_balance; }
 static int g_sub_cols = 0;
 int sub_cols_override() { return g_sub_cols; }
 
 int set_config(int id) {
+  g_wave_balance = true;
+  if (id >= 100 && id < 200) { g_wave_balance = false; id -= 70; }  // 100 + v: rowchunk variant v without wave balancing
   g_sub_cols = 0;
   if (id >= 1000) { g_sub_cols = (id / 1000) * 256; id %= 1000; }  // e.g. 2014: sub-tile 512, 4 tiles
   if (id < 0 || (id > kNumConfigs && (id < 11 || id > 26) && (id < 30 || id > 49)) || g_sub_cols > 1024)

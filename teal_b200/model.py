@@ -141,6 +141,7 @@ class SparseDecoder:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_mode = None
         self.taps = None  # calibration taps
+        self.ffn_inputs = None  # when a list: per-layer copies of (x, ssq) entering the MLP block (bench roofline)
         self.kernels_per_step = 0
 
     # ------------------------------------------------------------------ weights
@@ -250,7 +251,7 @@ class SparseDecoder:
         wsp, wsn = ws.data_ptr(), ws.numel()
         chk = _lib.check
         n_launch = 0
-        ssq = self.ssq.data_ptr() if self.world == 1 else None  # TP: x is updated by torch ops, no hand-off
+        ssq = self.ssq.data_ptr()
         chk(lib.teal_embed_f16(self.tok_emb.data_ptr(), self.token.data_ptr(), self.x.data_ptr(), ssq, a.dim, sp), "embed")
         n_launch += 1
         dense_t = {p: -1.0 for p in PROJS}
@@ -296,7 +297,10 @@ class SparseDecoder:
                 chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.part.data_ptr(), self.dim_l,
                                              a.dim, W["wo"].stride(1), t["o"], wsp, wsn, sp), "o_proj")
                 self._allreduce(self.part)
-                self.x.add_(self.part)
+                chk(lib.teal_residual_add_f16(self.x.data_ptr(), self.part.data_ptr(), ssq, a.dim, sp), "residual_add")
+                n_launch += 1
+            if self.ffn_inputs is not None:
+                self.ffn_inputs.append((self.x.clone(), self.ssq.clone()))
             xn_out = torch.empty_like(self.x) if tap is not None else None
             chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq,
                                                  W["w1"].data_ptr(), W["w3"].data_ptr(), self.h.data_ptr(),
@@ -314,7 +318,8 @@ class SparseDecoder:
                 chk(lib.teal_sparse_gemv_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.part.data_ptr(), self.inter_l,
                                              a.dim, W["w2"].stride(1), t["down"], wsp, wsn, sp), "down_proj")
                 self._allreduce(self.part)
-                self.x.add_(self.part)
+                chk(lib.teal_residual_add_f16(self.x.data_ptr(), self.part.data_ptr(), ssq, a.dim, sp), "residual_add")
+                n_launch += 1
             n_launch += 3
         chk(lib.teal_dense_gemv_f16(self.x.data_ptr(), self.final_norm.data_ptr(), a.norm_eps, self.lm_head.data_ptr(),
                                     self.logits.data_ptr(), self.argmax.data_ptr(), a.dim, a.vocab_size, a.dim, sp),
@@ -336,7 +341,9 @@ class SparseDecoder:
             self.stream.synchronize()
             self.token.copy_(saved[0]); self.pos.copy_(saved[1]); self.argmax.zero_()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.stream):
+            # TP: the NCCL watchdog thread polls events while we capture -> capture errors must be thread-local
+            cap_mode = "thread_local" if self.world > 1 else "global"
+            with torch.cuda.graph(g, stream=self.stream, capture_error_mode=cap_mode):
                 self._enqueue_step(mode)
         self.lib.teal_set_pdl(0)
         torch.cuda.synchronize()

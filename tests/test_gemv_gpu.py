@@ -78,7 +78,7 @@ def test_survivor_tie_rule(golden_dir):
     assert 0 not in got and 1 not in got and 2 in got
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 11, 12, 14, 18, 26, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 11, 12, 14, 18, 26, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 100, 101, 102])
 def test_golden_cases_all_configs(golden_dir, cfg):
     ops = _ops()
     ops.set_config(cfg)
