@@ -259,18 +259,20 @@ def main():
     peak, peak_kind = measured_peak()
     a = margs
     rf = None
+    # every rank replays 4 sparse steps (they contain the TP all-reduces) to capture each layer's real MLP input
+    dec.set_thresholds(thr)
+    dec.reset(1)
+    with torch.cuda.stream(dec.stream):
+        for _ in range(3):
+            dec._enqueue_step("sparse")
+        dec.ffn_inputs = []
+        dec._enqueue_step("sparse")
+    dec.stream.synchronize()
+    ffn_in, dec.ffn_inputs = dec.ffn_inputs, None
+    barrier()
     if rank == 0:
         ws = ops.workspace(dec.dev, dec.stream.cuda_stream)
         probe.zero_()
-        dec.set_thresholds(thr)
-        dec.reset(1)
-        with torch.cuda.stream(dec.stream):  # every layer's real MLP input (x, sum-of-squares partials) at token 3
-            for _ in range(3):
-                dec._enqueue_step("sparse")
-            dec.ffn_inputs = []
-            dec._enqueue_step("sparse")
-        dec.stream.synchronize()
-        ffn_in, dec.ffn_inputs = dec.ffn_inputs, None
         t_l = [t for t in thr]
         reps = max(1, 96 // a.n_layer)
         with torch.cuda.stream(dec.stream):

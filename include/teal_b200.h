@@ -129,6 +129,15 @@ int teal_dense_gemv_f16(const void* x, const void* norm_w, double eps, const voi
 /* Tensor-parallel path: x += part (the all-reduced o/down partial, fp16 add of gpt-fast/model.py:160-161
  * after the all-reduce of tp.py:120-121,139-140) and the sum-of-squares partials of the new x. */
 int teal_residual_add_f16(void* x, const void* part, float* ssq_out, int dim, void* stream);
+/* Fused exchange step of the tensor-parallel path: one-shot all-reduce of the row-parallel partials over
+ * NVLink peer memory + fp16 residual add + sum of squares, one kernel (replaces the ncclAllReduce of
+ * gpt-fast/tp.py:120-121,139-140 and the add of model.py:160-161).  peer_partials[r] / peer_flags[r] (HOST arrays of
+ * `world` device pointers, peer-mapped, e.g. from torch symmetric memory) are rank r's fp16 partial buffer [dim]
+ * and uint32 flag array [world] (zero-initialised); epoch_cell is a local device uint32 (zero-initialised) the
+ * kernel increments.  Consecutive calls must alternate between two partial buffers. */
+int teal_tp_allreduce_residual_f16(const void* const* peer_partials, void* const* peer_flags, int rank,
+                                   int world, void* x, float* ssq_out, void* epoch_cell, int dim,
+                                   void* stream);
 /* Greedy step bookkeeping: *token = arg-max index, out_tokens[*pos] = *token, ++*pos, reset cell. */
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap,
                  void* stream);

@@ -253,6 +253,11 @@ int teal_residual_add_f16(void* x, const void* part, float* ssq_out, int dim, vo
   return launch_residual_add(reinterpret_cast<__half*>(x), reinterpret_cast<const __half*>(part), ssq_out, dim,
                              reinterpret_cast<cudaStream_t>(stream));
 }
+int teal_tp_allreduce_residual_f16(const void* const* peer_partials, void* const* peer_flags, int rank, int world,
+                                   void* x, float* ssq_out, void* epoch_cell, int dim, void* stream) {
+  return launch_tp_allreduce_residual(peer_partials, peer_flags, rank, world, reinterpret_cast<__half*>(x), ssq_out,
+                                      reinterpret_cast<unsigned*>(epoch_cell), dim, reinterpret_cast<cudaStream_t>(stream));
+}
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap, void* stream) {
   return launch_advance(reinterpret_cast<unsigned long long*>(argmax_packed), token, pos, out_tokens, out_cap,
                         reinterpret_cast<cudaStream_t>(stream));

@@ -162,6 +162,8 @@ int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, 
 int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,
                           unsigned long long* argmax_packed, int Z, int V, long long ldw, cudaStream_t stream);
 int launch_residual_add(__half* x, const __half* part, float* ssq_out, int dim, cudaStream_t stream);
+int launch_tp_allreduce_residual(const void* const* bufs, void* const* flags, int rank, int ws, __half* x, float* ssq_out,
+                                 unsigned* epoch_cell, int dim, cudaStream_t stream);
 int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap,
                    cudaStream_t stream);
 

@@ -346,6 +346,94 @@ __global__ void residual_add_kernel(__half* __restrict__ x, const __half* __rest
   griddep_launch_dependents();
 }
 
+// --------------------------------------------------------------------------------------------
+// Tensor-parallel exchange step, fused: one-shot all-reduce over NVLink peer memory + residual add + sum of
+// squares, in ONE single-CTA kernel (replaces ncclAllReduce + add, gpt-fast/tp.py:120-121,139-140 + model.py:160-161).
+//   * every rank's row-parallel GEMV writes its fp16 partial straight into its own symmetric buffer
+//   * this kernel publishes "epoch e ready" into every peer's flag array (st.release.sys over NVLink), spins until all
+//     peers have published e (ld.acquire.sys on local memory), then pulls the ws partials with volatile 16-byte P2P
+//     loads, sums them in rank order in fp32 (identical on every rank => replicas stay bit-identical), rounds once to
+//     fp16, adds the residual in fp16 and leaves the sum of squares for the next RMSNorm.
+// The two all-reduces of a layer use alternating buffers (o-proj: 0, down-proj: 1): a rank can only overwrite a
+// buffer two exchanges later, by which time every peer has entered the next exchange and is done reading it.
+// --------------------------------------------------------------------------------------------
+constexpr int kMaxTpWorld = 16;
+struct TpPeers {
+  const __half* buf[kMaxTpWorld];  // this parity's partial buffer of every rank (peer-mapped)
+  unsigned* flags[kMaxTpWorld];    // flag array of every rank: flags[r][s] = last epoch published by sender s
+};
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_volatile_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+__global__ void __launch_bounds__(1024, 1) tp_allreduce_residual_kernel(const __grid_constant__ TpPeers peers, int rank,
+                                                                        int ws, __half* __restrict__ x,
+                                                                        float* __restrict__ ssq_out, unsigned* epoch_cell,
+                                                                        int dim) {
+  __shared__ float sp[32];
+  griddep_wait();  // our own partial (previous kernel in the stream) is complete and visible
+  const unsigned e = *epoch_cell + 1u;
+  if (threadIdx.x < ws) {
+    __threadfence_system();
+    st_release_sys_u32(peers.flags[threadIdx.x] + rank, e);  // tell peer `threadIdx.x` that rank's partial e is ready
+    const unsigned* mine = peers.flags[rank] + threadIdx.x;  // ... and wait for its partial
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys_u32(mine) - e) < 0) {
+      if (clock64() - t0 > 4000000000ll) __trap();  // a missing peer traps instead of hanging the GPU
+    }
+  }
+  __syncthreads();
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < dim; i += blockDim.x * 8) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (int r = 0; r < ws; ++r) {  // fixed rank order on every rank
+      const uint4 v = ld_volatile_u4(peers.buf[r] + i);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        a[2 * j] += f.x;
+        a[2 * j + 1] += f.y;
+      }
+    }
+    uint4 xv = *reinterpret_cast<const uint4*>(x + i);
+    __half2* x2 = reinterpret_cast<__half2*>(&xv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x2[j] = __hadd2(x2[j], __floats2half2_rn(a[2 * j], a[2 * j + 1]));  // y rounds to fp16, then the fp16 residual add
+      const float2 f = __half22float2(x2[j]);
+      ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+    }
+    *reinterpret_cast<uint4*>(x + i) = xv;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+  if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sp[w];
+    if (ssq_out) ssq_out[0] = t;
+    *epoch_cell = e;
+  } else if (ssq_out && threadIdx.x < kSsqParts) {
+    ssq_out[threadIdx.x] = 0.f;
+  }
+  griddep_launch_dependents();
+}
+
 // ---------------------------------------------------------------------------------- launchers
 template <typename... KArgs, typename... Args>
 static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const char* what,
@@ -411,6 +499,21 @@ int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, cons
 int launch_residual_add(__half* x, const __half* part, float* ssq_out, int dim, cudaStream_t stream) {
   if (!x || !part || dim <= 0 || (dim & 1)) return set_error(TEAL_ERR_BAD_ARG, "residual_add: bad argument");
   return launch_pdl(residual_add_kernel, dim3(1), dim3(1024), 0, stream, "residual_add launch", x, part, ssq_out, dim);
+}
+
+int launch_tp_allreduce_residual(const void* const* bufs, void* const* flags, int rank, int ws, __half* x, float* ssq_out,
+                                 unsigned* epoch_cell, int dim, cudaStream_t stream) {
+  if (!bufs || !flags || !x || !epoch_cell || ws < 1 || ws > kMaxTpWorld || rank < 0 || rank >= ws || dim <= 0 || (dim & 7))
+    return set_error(TEAL_ERR_BAD_ARG, "tp_allreduce_residual: bad argument");
+  TpPeers p;
+  for (int r = 0; r < kMaxTpWorld; ++r) {
+    p.buf[r] = (r < ws) ? reinterpret_cast<const __half*>(bufs[r]) : nullptr;
+    p.flags[r] = (r < ws) ? reinterpret_cast<unsigned*>(flags[r]) : nullptr;
+    if (r < ws && (!p.buf[r] || !p.flags[r] || (reinterpret_cast<uintptr_t>(p.buf[r]) & 15)))
+      return set_error(TEAL_ERR_ALIGNMENT, "tp_allreduce_residual: null / unaligned peer pointer");
+  }
+  return launch_pdl(tp_allreduce_residual_kernel, dim3(1), dim3(1024), 0, stream, "tp_allreduce_residual launch", p, rank,
+                    ws, x, ssq_out, epoch_cell, dim);
 }
 
 int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap,

@@ -138,11 +138,68 @@ class SparseDecoder:
         self.logits = torch.zeros(1, 1, a.vocab_size, dtype=f16, device=dev)
         self.ssq = torch.zeros(64, dtype=torch.float32, device=dev)  # sum-of-squares partials of the residual stream
         self.stream = torch.cuda.Stream(device=dev)
+        self.tp_fused = False
+        if world > 1:
+            self._setup_peer_exchange()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_mode = None
         self.taps = None  # calibration taps
+        self.force_tp_path = False  # tests: take the (plain GEMV -> all-reduce -> residual_add) route at world == 1
         self.ffn_inputs = None  # when a list: per-layer copies of (x, ssq) entering the MLP block (bench roofline)
         self.kernels_per_step = 0
+
+    # ------------------------------------------------------------------ TP exchange buffers
+    def _setup_peer_exchange(self):
+        """Symmetric (peer-mapped) memory for the fused one-shot all-reduce: two fp16 partial buffers [dim] + a flag
+        array per rank.  Falls back to NCCL all-reduce (all ranks together) if symmetric memory is unavailable."""
+        import ctypes
+        import os
+        import torch.distributed as dist
+        ok = 1
+        try:
+            if os.environ.get("TEAL_TP_ALLREDUCE", "fused") != "fused":
+                raise RuntimeError("disabled by TEAL_TP_ALLREDUCE")
+            import torch.distributed._symmetric_memory as symm
+            dim, ws = self.args.dim, self.world
+            pg = self.pg if self.pg is not None else dist.group.WORLD
+            if hasattr(symm, "enable_symm_mem_for_group"):
+                try:
+                    symm.enable_symm_mem_for_group(pg.group_name)
+                except Exception:
+                    pass
+            t = symm.empty(4 * dim + 256, dtype=torch.uint8, device=self.dev)
+            t.zero_()
+            hdl = symm.rendezvous(t, pg)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            assert len(ptrs) == ws and all(ptrs)
+            self._symm = (t, hdl)
+            self.tp_bufs = [(ctypes.c_void_p * ws)(*[p + par * dim * 2 for p in ptrs]) for par in (0, 1)]
+            self.tp_flags = (ctypes.c_void_p * ws)(*[p + 4 * dim for p in ptrs])
+            self.tp_part = [t[par * dim * 2:(par + 1) * dim * 2].view(torch.float16).view(1, 1, dim) for par in (0, 1)]
+            self.tp_epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        except Exception as e:  # noqa: BLE001 - any failure means: use NCCL
+            ok = 0
+            self._symm_error = repr(e)
+        flag = torch.tensor([ok], device=self.dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+        torch.cuda.synchronize()
+        self.tp_fused = bool(int(flag.item()))
+        if not self.tp_fused and self.rank == 0:
+            print(f"[teal_b200] fused peer-memory all-reduce unavailable ({getattr(self, '_symm_error', 'peer failed')}); "
+                  "using NCCL all-reduce", flush=True)
+
+    def _exchange(self, parity: int, sp):
+        """The TP exchange step after a row-parallel GEMV whose partial is in tp_part[parity] / self.part."""
+        a, lib = self.args, self.lib
+        if self.tp_fused:
+            _lib.check(lib.teal_tp_allreduce_residual_f16(self.tp_bufs[parity], self.tp_flags, self.rank, self.world,
+                                                          self.x.data_ptr(), self.ssq.data_ptr(), self.tp_epoch.data_ptr(),
+                                                          a.dim, sp), "tp_allreduce_residual")
+            return 1
+        self._allreduce(self.part)
+        _lib.check(lib.teal_residual_add_f16(self.x.data_ptr(), self.part.data_ptr(), self.ssq.data_ptr(), a.dim, sp),
+                   "residual_add")
+        return 1
 
     # ------------------------------------------------------------------ weights
     def _colmajor_rand(self, g, n, z, std=0.02):
@@ -289,16 +346,15 @@ class SparseDecoder:
                 self._allreduce(self.part)
                 self.x.add_(self.part)
                 continue
-            if self.world == 1:
+            if self.world == 1 and not self.force_tp_path:
                 chk(lib.teal_sparse_gemv_residual_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(),
                                                       self.x.data_ptr(), ssq, self.dim_l, a.dim, W["wo"].stride(1), t["o"],
                                                       wsp, wsn, sp), "o_proj")
             else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
-                chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.part.data_ptr(), self.dim_l,
+                dst = self.tp_part[0] if self.tp_fused else self.part
+                chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), dst.data_ptr(), self.dim_l,
                                              a.dim, W["wo"].stride(1), t["o"], wsp, wsn, sp), "o_proj")
-                self._allreduce(self.part)
-                chk(lib.teal_residual_add_f16(self.x.data_ptr(), self.part.data_ptr(), ssq, a.dim, sp), "residual_add")
-                n_launch += 1
+                n_launch += self._exchange(0, sp)
             if self.ffn_inputs is not None:
                 self.ffn_inputs.append((self.x.clone(), self.ssq.clone()))
             xn_out = torch.empty_like(self.x) if tap is not None else None
@@ -310,16 +366,15 @@ class SparseDecoder:
             if tap is not None:
                 tap["mlp_h1"].append(xn_out.flatten().float().cpu())
                 tap["mlp_h2"].append(self.h.flatten().float().cpu())
-            if self.world == 1:
+            if self.world == 1 and not self.force_tp_path:
                 chk(lib.teal_sparse_gemv_residual_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(),
                                                       self.x.data_ptr(), ssq, self.inter_l, a.dim, W["w2"].stride(1),
                                                       t["down"], wsp, wsn, sp), "down_proj")
             else:
-                chk(lib.teal_sparse_gemv_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.part.data_ptr(), self.inter_l,
+                dst = self.tp_part[1] if self.tp_fused else self.part
+                chk(lib.teal_sparse_gemv_f16(self.h.data_ptr(), W["w2"].data_ptr(), dst.data_ptr(), self.inter_l,
                                              a.dim, W["w2"].stride(1), t["down"], wsp, wsn, sp), "down_proj")
-                self._allreduce(self.part)
-                chk(lib.teal_residual_add_f16(self.x.data_ptr(), self.part.data_ptr(), ssq, a.dim, sp), "residual_add")
-                n_launch += 1
+                n_launch += self._exchange(1, sp)
             n_launch += 3
         chk(lib.teal_dense_gemv_f16(self.x.data_ptr(), self.final_norm.data_ptr(), a.norm_eps, self.lm_head.data_ptr(),
                                     self.logits.data_ptr(), self.argmax.data_ptr(), a.dim, a.vocab_size, a.dim, sp),

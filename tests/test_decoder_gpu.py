@@ -151,3 +151,17 @@ def test_calibration_hits_target_sparsity():
     dec.lib.teal_set_bytes_probe(None)
     kept = float(probe[0]) / float(probe[1])
     assert 0.35 < kept < 0.65, kept
+
+
+def test_tp_route_equals_fused_route_on_one_gpu():
+    """The TP code path (plain GEMV -> all-reduce -> residual_add kernel) must be bit-identical to the fused
+    residual epilogue when there is a single rank (same fp16 rounding sequence)."""
+    a, _ = _mk(THR)
+    b, _ = _mk(THR)
+    b.force_tp_path = True
+    a.reset(7); b.reset(7)
+    for i in range(6):
+        a._enqueue_step("sparse"); b._enqueue_step("sparse")
+        torch.cuda.synchronize()
+        assert torch.equal(a.logits, b.logits), i
+        assert int(a.token.item()) == int(b.token.item())

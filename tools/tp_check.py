@@ -18,7 +18,7 @@ sd = _state_dict(CFG)
 args = ModelArgs(**CFG)
 tpd = SparseDecoder(args, device=f"cuda:{rank}", max_seq=64, rank=rank, world=world, process_group=dist.group.WORLD, state_dict=sd)
 tpd.set_thresholds(THR)
-print(f"[rank {rank}] tp decoder built", flush=True)
+print(f"[rank {rank}] tp decoder built, fused peer all-reduce = {tpd.tp_fused}", flush=True)
 ref = SparseDecoder(args, device=f"cuda:{rank}", max_seq=64, state_dict=sd)
 ref.set_thresholds(THR)
 ok = True
