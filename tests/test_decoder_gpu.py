@@ -165,3 +165,63 @@ def test_tp_route_equals_fused_route_on_one_gpu():
         torch.cuda.synchronize()
         assert torch.equal(a.logits, b.logits), i
         assert int(a.token.item()) == int(b.token.item())
+
+
+def test_hf_sparse_linear_decode_uses_kernel_and_matches_reference_semantics():
+    """HF surface (teal/mlp.py:50-56): SparseLinear at q_len == 1 on CUDA == mask-then-matmul of the reference."""
+    from teal_b200.hf import SparseLinear, SparsifyFn
+    torch.manual_seed(3)
+    Z, N = 512, 1024
+    lin = torch.nn.Linear(Z, N, bias=False, dtype=torch.float16)
+    lin.weight.data = (torch.randn(N, Z) * 0.05).half()
+    fn = SparsifyFn(init_threshold=0.6)
+    x = torch.randn(1, 1, Z).half()
+    want = O.sparse_linear_f32(x, lin.weight.data, 0.6).reshape(-1)
+    sl = SparseLinear(lin, fn).cuda()
+    y = sl(x.cuda())
+    err = (y.reshape(-1).float().cpu() - want).abs()
+    assert (err <= want.abs() * 2.0 ** -10 + 1e-3).all()
+    xp = torch.randn(1, 6, Z).half()  # prefill: half-sequence rule, dense matmul
+    yp = sl(xp.cuda()).float().cpu()
+    wp = torch.nn.functional.linear(O.sparsify_forward(xp, 0.6).float(), lin.weight.data.float().cpu())
+    assert torch.allclose(yp, wp, rtol=1e-2, atol=1e-2)
+
+
+def test_gptfast_call_sites_drop_in():
+    """The reference's call sites (gemv1/gemv2/thresh_*/sparsity_bin attrs, apply_monkeypatch, torch.ops.teal.*)
+    on a gpt-fast-shaped nn.Module: prefill (dense branch of the ops) + decode steps vs the oracle, then the same
+    decode steps replayed from a captured CUDA graph."""
+    from teal_b200.gptfast_compat import Transformer, install_sparsity
+    from teal_b200.model import ModelArgs
+    sd = _state_dict(CFG)
+    m = Transformer(ModelArgs(**CFG))
+    m.load_state_dict(sd)
+    m = m.half().cuda()
+    install_sparsity(m, THR)
+    m.setup_caches(1, 32)
+    orc = O.OracleDecoder(CFG, sd, THR, max_seq=32)
+    assert m.layers[0].attention.gemv1 is torch.ops.teal.sparse_qkv_gemv
+    assert m.layers[0].feed_forward.w1.weight.stride() == (1, CFG["intermediate_size"])
+    with torch.no_grad():
+        prompt = torch.tensor([[3, 17, 42, 8]])
+        got = m(prompt.cuda(), torch.arange(4, device="cuda"))
+        want = orc.forward(prompt, torch.arange(4))
+        assert torch.allclose(got.float().cpu(), want.float(), rtol=3e-2, atol=3e-2)
+        for i, t in enumerate([77, 300, 5]):
+            got = m(torch.tensor([[t]], device="cuda"), torch.tensor([4 + i], device="cuda"))
+            want = orc.forward(torch.tensor([[t]]), torch.tensor([4 + i]))
+            scale = float(want.abs().max())
+            assert float((got.float().cpu() - want.float()).abs().max()) <= 6e-2 * scale + 2e-2
+        # capture one decode step of the nn.Module (the ops are graph-safe: no sync, no host allocation)
+        tok = torch.tensor([[9]], device="cuda")
+        pos = torch.tensor([7], device="cuda")
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            m(tok, pos)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                out = m(tok, pos)
+            g.replay()
+        torch.cuda.synchronize()
+        want = orc.forward(torch.tensor([[9]]), torch.tensor([7]))
+        assert float((out.float().cpu() - want.float()).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2

@@ -60,3 +60,46 @@ def test_histogram_round_trip_gives_target_sparsity():
     for s in (0.3, 0.5, 0.7):
         t = threshold_for(d, s)
         assert abs(float((v.abs() <= t).float().mean()) - s) < 0.01
+
+
+def test_hf_sparsify_fn_matches_reference_golden(golden_dir):
+    """teal_b200.hf.SparsifyFn (CPU path = the reference's mask semantics) against the reference's own outputs."""
+    from teal_b200.hf import SparsifyFn
+    g = np.load(os.path.join(golden_dir, "sparsify_linear.npz"))
+    fn = SparsifyFn(init_threshold=float(g["tie__thr"]))
+    assert np.array_equal(fn(torch.from_numpy(g["tie__x"])).numpy().view(np.uint16), g["tie__xm"].view(np.uint16))
+    fn = SparsifyFn(init_threshold=float(g["prefill__thr"]))
+    xp = torch.from_numpy(g["prefill__x"])
+    assert np.array_equal(fn(xp).numpy(), g["prefill__xm"])
+    fn.apply_prefill = False
+    assert np.array_equal(fn(xp).numpy(), g["prefill_off__xm"])
+    k = np.load(os.path.join(golden_dir, "icdf_kat.npz"))
+    d = Distribution(centers=k["Llama_2_7B_L0_mlp__h1_centers"], counts=k["Llama_2_7B_L0_mlp__h1_counts"])
+    fn = SparsifyFn(d)
+    for s, want in zip(k["Llama_2_7B_L0_mlp__h1_hf_s"], k["Llama_2_7B_L0_mlp__h1_hf_thr"]):
+        fn.set_threshold(float(s))
+        assert fn.threshold == float(want)
+
+
+def test_hf_mlp_patch_cpu_path_matches_reference(golden_dir):
+    from teal_b200.hf import patch_mlp
+    g = np.load(os.path.join(golden_dir, "hf_mlp.npz"))
+
+    class MLP(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            Z, I = g["w_gate"].shape[1], g["w_gate"].shape[0]
+            self.gate_proj = torch.nn.Linear(Z, I, bias=False, dtype=torch.float16)
+            self.up_proj = torch.nn.Linear(Z, I, bias=False, dtype=torch.float16)
+            self.down_proj = torch.nn.Linear(I, Z, bias=False, dtype=torch.float16)
+            self.act_fn = torch.nn.SiLU()
+    m = MLP()
+    m.gate_proj.weight.data = torch.from_numpy(g["w_gate"])
+    m.up_proj.weight.data = torch.from_numpy(g["w_up"])
+    m.down_proj.weight.data = torch.from_numpy(g["w_down"])
+    patch_mlp(m, {"h1": None, "h2": None})
+    for k, t in zip(("gate", "up", "down"), g["thr"]):
+        m.sparse_fns[k].threshold = float(t)
+    with torch.no_grad():
+        y = m(torch.from_numpy(g["x"]))
+    assert np.allclose(y.float().numpy(), g["y"].astype(np.float32), rtol=2e-3, atol=2e-3)
