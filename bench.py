@@ -227,7 +227,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    ncu_window = os.environ.get("TEAL_NCU_WINDOW") == "1"  # ncu --profile-from-start off: profile only this region
+    if ncu_window:
+        torch.cuda.profiler.start()
     ms_step = timed("sparse", K, Wm)
+    if ncu_window:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed("sparse", K, Wm, e2e=True)
     kernels_per_step = dec.kernels_per_step
