@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libteal_b200.so")
 SOURCES = ["api.cu", "sparse_gemv.cu", "gather_gemv.cu", "rowchunk_gemv.cu", "decode_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC"]  # no --use_fast_math: denormals and exact division matter for parity
 
 
 def _nvcc() -> str:
@@ -40,8 +40,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc(), *flags, "-shared", "-o", LIB, *sources()]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

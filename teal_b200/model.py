@@ -16,7 +16,6 @@ PyTorch here is plumbing: device memory, the CUDA-graph capture and torch.distri
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -264,7 +263,6 @@ class SparseDecoder:
         then threshold = Distribution.icdf(0.5 + s/2) per projection (generate.py:278-287).
         `sparsities`: float, or {proj: float}, or list (per layer) of {proj: float}."""
         a = self.args
-        saved = self.thresholds
         self.set_thresholds([None] * a.n_layer)
         acts = [dict(attn_h1=[], attn_h2=[], mlp_h1=[], mlp_h2=[]) for _ in range(a.n_layer)]
         self.taps = acts

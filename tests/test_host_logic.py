@@ -103,3 +103,15 @@ def test_hf_mlp_patch_cpu_path_matches_reference(golden_dir):
     with torch.no_grad():
         y = m(torch.from_numpy(g["x"]))
     assert np.allclose(y.float().numpy(), g["y"].astype(np.float32), rtol=2e-3, atol=2e-3)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under teal_b200/ may import or execute it."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "teal_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "teal_oracle" not in src, f
