@@ -237,6 +237,9 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
 #pragma unroll
       for (int w = 0; w < kRcWarps; ++w) a += s_ssq[w];
       p.ssq_out[cidx] = a;
+      // every slot of the kSsqParts-long buffer is (re)defined by exactly one tile on every call: slot i by tile i,
+      // the unused tail i + T, i + 2T, ... is zeroed -- a previous producer with more tiles leaves nothing stale
+      for (int sidx = cidx + p.total_ctiles; sidx < kSsqParts; sidx += p.total_ctiles) p.ssq_out[sidx] = 0.f;
     }
   }
   if (tid == 0) p.counters[cidx] = 0;
@@ -314,6 +317,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   }
   if (gp.in_mode == kInRmsNorm && (!gp.norm_w || !gp.ssq_in || gp.n_ssq_in <= 0))
     return set_error(TEAL_ERR_BAD_ARG, "RMSNorm mode needs norm_w and the producer's sum-of-squares partials");
+  if (gp.ssq_out && gp.mode == kModePairSilu) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out is not defined for the gate/up pair");
   if (gp.out_mode == kOutAddResidual && (!gp.resid || (reinterpret_cast<uintptr_t>(gp.resid) & 7)))
     return set_error(TEAL_ERR_ALIGNMENT, "residual must be non-null and 8-byte aligned");
   struct Variant { int vec, u, warps, rows; void (*kern)(const RcParams); };
@@ -363,6 +367,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (pair && (gp.nseg != 2 || p.seg[0].nctiles != p.seg[1].nctiles)) return set_error(TEAL_ERR_BAD_ARG, "pair mode needs two equal segments");
   const int ncounters = pair ? p.seg[0].nctiles : ctile0;
   if (ncounters > kMaxCounters) return set_error(TEAL_ERR_UNSUPPORTED, "too many column tiles");
+  if (gp.ssq_out && ctile0 > kSsqParts) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out: more column tiles than TEAL_SSQ_PARTS");
   // Wave quantisation: pick the K-chunk so that the grid is (just under) a whole number of full waves of
   // resident CTAs -- 1792 CTAs on 1036 slots ran 1.73 waves, i.e. the second wave left 27 % of the chip idle.
   if (gp.mode != kModeSurvivors && wave_balance_enabled()) {

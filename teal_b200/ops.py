@@ -122,8 +122,9 @@ def sparse_gate_up(x: torch.Tensor, w1: torch.Tensor, w3: torch.Tensor, threshol
     return out
 
 
-def norm_qkv_gemv(x, norm_w, eps, weight, tq, tk, tv, kv_size, want_xn=False):
-    """attention_norm + fused QKV GEMV in one launch (decode pipeline building block)."""
+def norm_qkv_gemv(x, norm_w, eps, weight, tq, tk, tv, kv_size, want_xn=False, ssq_in=None):
+    """attention_norm + fused QKV GEMV in one launch (decode pipeline building block); ``ssq_in``: the producer's
+    sum-of-squares partials of x (else computed by one extra tiny launch)."""
     N, Z = weight.shape
     x = _check_x(x, Z)
     ldw = _check_w(weight)
@@ -131,7 +132,8 @@ def norm_qkv_gemv(x, norm_w, eps, weight, tq, tk, tv, kv_size, want_xn=False):
     xn = torch.empty(1, 1, Z, device=x.device, dtype=torch.float16) if want_xn else None
     sp = _stream_ptr()
     ws = workspace(x.device, sp)
-    rc = _lib.load().teal_norm_sparse_qkv_gemv_f16(x.data_ptr(), norm_w.data_ptr(), float(eps), None, weight.data_ptr(),
+    rc = _lib.load().teal_norm_sparse_qkv_gemv_f16(x.data_ptr(), norm_w.data_ptr(), float(eps),
+                                                   ssq_in.data_ptr() if ssq_in is not None else None, weight.data_ptr(),
                                                    out.data_ptr(), xn.data_ptr() if want_xn else None, Z, N, ldw,
                                                    int(kv_size), float(tq), float(tk), float(tv), ws.data_ptr(),
                                                    ws.numel(), sp)
@@ -156,8 +158,9 @@ def norm_gate_up(x, norm_w, eps, w1, w3, t_gate, t_up, want_xn=False):
     return (out, xn) if want_xn else out
 
 
-def gemv_residual(x, weight, resid, threshold):
-    """resid + sparse_gemv(x, weight) with the add fused into the kernel's finaliser."""
+def gemv_residual(x, weight, resid, threshold, ssq_out=None):
+    """resid + sparse_gemv(x, weight) with the add fused into the kernel's finaliser; ``ssq_out`` (fp32[64], optional)
+    receives the per-tile sums of squares of the result for the next fused RMSNorm."""
     N, Z = weight.shape
     x = _check_x(x, Z)
     ldw = _check_w(weight)
@@ -165,7 +168,7 @@ def gemv_residual(x, weight, resid, threshold):
     sp = _stream_ptr()
     ws = workspace(x.device, sp)
     rc = _lib.load().teal_sparse_gemv_residual_f16(x.data_ptr(), weight.data_ptr(), resid.data_ptr(), out.data_ptr(),
-                                                   None, Z, N, ldw, float(threshold), ws.data_ptr(), ws.numel(), sp)
+                                                   ssq_out.data_ptr() if ssq_out is not None else None, Z, N, ldw, float(threshold), ws.data_ptr(), ws.numel(), sp)
     _lib.check(rc, "teal_sparse_gemv_residual_f16")
     return out
 

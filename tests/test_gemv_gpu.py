@@ -300,3 +300,33 @@ def test_fused_rmsnorm_gate_up_and_residual_down(Z, I):
     want2 = (x + y16).float()                               # ... then the fp16 residual add (model.py:161)
     err2 = (out.reshape(-1).float().cpu() - want2.reshape(-1)).abs()
     assert (err2 <= want2.reshape(-1).abs() * 2.0 ** -9 + 2e-3).all()
+
+
+def test_ssq_handoff_across_different_tilings():
+    """Sum-of-squares hand-off (fused RMSNorm without reading the whole vector): two producers with DIFFERENT tile
+    counts write the same 64-float buffer one after the other (o-proj then down-proj in a layer); the buffer must
+    always describe exactly the last result, and the consumer's RMSNorm must equal the oracle's."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    N = 4096
+    ssq = torch.zeros(64, dtype=torch.float32, device="cuda")
+    resid = torch.randn(1, 1, N, generator=g).half()
+    nw = (1 + 0.1 * torch.randn(N, generator=g)).half()
+    try:
+        for cfg, Z in ((32, 256), (31, 512), (30, 256), (33, 384)):  # 16, 8, 16, 8 column tiles
+            ops.set_config(cfg)
+            x, W = _mk(Z, N, 100 + cfg)
+            y = ops.gemv_residual(x.cuda(), _colmajor_cuda(W), resid.cuda(), 0.5, ssq_out=ssq)
+            yk = y.cpu().float().reshape(-1)
+            want = float((yk * yk).sum())
+            got = float(ssq.sum())
+            assert abs(got - want) <= 1e-4 * want, (cfg, got, want)
+            # consumer: RMSNorm from the partials == oracle rms_norm of the same vector
+            ops.set_config(0)
+            _, Wq = _mk(N, 256, 7)
+            out, xn = ops.norm_qkv_gemv(y, nw.cuda(), 1e-5, _colmajor_cuda(Wq), 0.5, 0.5, 0.5, 64, want_xn=True, ssq_in=ssq)
+            xn_ref = O.rms_norm(y.cpu(), nw, 1e-5)
+            d = (xn.cpu().float() - xn_ref.float()).abs()
+            assert (d <= xn_ref.float().abs() * 2.0 ** -10 + 1e-6).all(), cfg
+    finally:
+        ops.set_config(0)
