@@ -89,3 +89,14 @@ def get_layer_greedy_sparsities(layer_sparsities: Sequence[float], results_dir: 
         for p in PROJS:
             out[p][layer] = sel[p]
     return out
+
+
+def resolve_histogram_dir(model_dir: str) -> str:
+    """Directory that holds ``layer-i/{mlp,self_attn}/histograms.pt`` for a model of the reference's ``models/`` tree.
+    Fixture quirk: ``models/Llama-3-8B/histograms/layer-*`` are byte-identical copies of the
+    Llama-2-7B files; the genuine Llama-3-8B histograms sit in ``histograms/Untitled/``."""
+    base = os.path.join(model_dir, "histograms")
+    untitled = os.path.join(base, "Untitled")
+    if os.path.isdir(os.path.join(untitled, "layer-0")):
+        return untitled
+    return base

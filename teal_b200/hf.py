@@ -95,3 +95,27 @@ def patch_mlp(mlp: nn.Module, distrs: Dict[str, object]) -> nn.Module:
                                         "down": SparseLinear(mlp.down_proj, mlp.sparse_fns["down"])})
     mlp.forward = types.MethodType(mlp_forward, mlp)
     return mlp
+
+
+def patch_self_attn(attn: nn.Module, distrs: Dict[str, object]) -> nn.Module:
+    """teal/self_attn.py:21-43: sparse_fns {'q','k','v' <- h1; 'o' <- h2}.  Instead of re-implementing the HF
+    attention forward (the reference copies the flash-attn forward, :46-156), the four projection modules are
+    swapped for ``SparseLinear`` wrappers, so whatever attention forward the installed transformers version uses
+    computes ``proj(sparse_fns[p](x))`` -- and at decode the gather kernel."""
+    attn.distrs = distrs
+    attn.sparse_fns = nn.ModuleDict({"q": SparsifyFn(distrs["h1"]), "k": SparsifyFn(distrs["h1"]),
+                                     "v": SparsifyFn(distrs["h1"]), "o": SparsifyFn(distrs["h2"])})
+    for p in ("q", "k", "v", "o"):
+        name = f"{p}_proj"
+        setattr(attn, name, SparseLinear(getattr(attn, name), attn.sparse_fns[p]))
+    return attn
+
+
+def set_sparsities(layers, sparsities: Dict[str, list]) -> None:
+    """teal/model.py:142-147 (set_sparsities): per-layer, per-projection sparsity -> thresholds; the dict is what
+    ``teal_b200.distribution.get_layer_greedy_sparsities`` returns (utils/utils.py:243-258) or a uniform fill."""
+    for i, layer in enumerate(layers):
+        for p in ("q", "k", "v", "o"):
+            layer.self_attn.sparse_fns[p].set_threshold(sparsities[p][i])
+        for p in ("gate", "up", "down"):
+            layer.mlp.sparse_fns[p].set_threshold(sparsities[p][i])

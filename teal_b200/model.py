@@ -83,6 +83,24 @@ def precompute_freqs_cis(seq_len: int, n_elem: int, base: float, dtype=torch.flo
     return torch.stack([fc.real, fc.imag], dim=-1).to(dtype)
 
 
+def fuse_qkv_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """``Attention.load_hook`` (gpt-fast/model.py:209-214): checkpoints that still carry wq / wk / wv get the fused
+    ``wqkv = cat([wq, wk, wv])`` the model (and the QKV kernel's region layout) expects."""
+    out = dict(sd)
+    for k in [k for k in sd if k.endswith("attention.wq.weight")]:
+        p = k[: -len("wq.weight")]
+        out[p + "wqkv.weight"] = torch.cat([out.pop(p + "wq.weight"), out.pop(p + "wk.weight"), out.pop(p + "wv.weight")])
+    return out
+
+
+def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+    """gpt-fast ``model.pth`` state dict (generate.py:244-247: mmap, weights only), QKV-fused."""
+    sd = torch.load(path, mmap=True, weights_only=True)
+    if "model" in sd and isinstance(sd["model"], dict):
+        sd = sd["model"]
+    return fuse_qkv_state_dict(sd)
+
+
 def build_histogram(values: torch.Tensor, num_bins: int = 10000, outlier: float = 0.01):
     """Histogram in the reference's format (utils/utils.py:145-173: fp32 counts + bin centres,
     1% / 99% outliers clipped into the two edge bins)."""

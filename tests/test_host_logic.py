@@ -115,3 +115,61 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "teal_oracle" not in src, f
+
+
+def test_hf_self_attn_patch_and_setters():
+    from teal_b200.hf import SparseLinear, patch_mlp, patch_self_attn, set_sparsities
+
+    class D:  # stand-in Distribution: icdf(q) = q
+        def icdf(self, q):
+            return q
+
+    class Attn(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            for p in "qkvo":
+                setattr(self, f"{p}_proj", torch.nn.Linear(16, 16, bias=False, dtype=torch.float16))
+
+    class MLP(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj = torch.nn.Linear(16, 32, bias=False, dtype=torch.float16)
+            self.up_proj = torch.nn.Linear(16, 32, bias=False, dtype=torch.float16)
+            self.down_proj = torch.nn.Linear(32, 16, bias=False, dtype=torch.float16)
+            self.act_fn = torch.nn.SiLU()
+
+    class Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_attn, self.mlp = Attn(), MLP()
+
+    layers = [Layer(), Layer()]
+    for l in layers:
+        patch_self_attn(l.self_attn, {"h1": D(), "h2": D()})
+        patch_mlp(l.mlp, {"h1": D(), "h2": D()})
+    assert isinstance(layers[0].self_attn.q_proj, SparseLinear) and set(layers[0].self_attn.sparse_fns) == {"q", "k", "v", "o"}
+    sp = {p: [0.0, 0.5] for p in O.PROJS}
+    set_sparsities(layers, sp)
+    assert layers[0].mlp.sparse_fns["down"].threshold == 0.0          # utils/utils.py:29
+    assert layers[1].self_attn.sparse_fns["o"].threshold == 0.75       # icdf(0.5 + 0.5/2)
+    x = torch.randn(1, 3, 16).half()
+    y = layers[1].self_attn.q_proj(x)                                   # CPU: reference mask-then-matmul semantics
+    want = torch.nn.functional.linear(O.sparsify_forward(x, 0.75), layers[1].self_attn.q_proj.linear.weight)
+    assert torch.equal(y, want)
+
+
+def test_checkpoint_helpers(tmp_path):
+    from teal_b200.model import fuse_qkv_state_dict, load_checkpoint
+    from teal_b200.distribution import resolve_histogram_dir
+    sd = {"layers.0.attention.wq.weight": torch.ones(8, 4), "layers.0.attention.wk.weight": 2 * torch.ones(2, 4),
+          "layers.0.attention.wv.weight": 3 * torch.ones(2, 4), "norm.weight": torch.ones(4)}
+    f = fuse_qkv_state_dict(sd)
+    assert "layers.0.attention.wq.weight" not in f and f["layers.0.attention.wqkv.weight"].shape == (12, 4)
+    assert f["layers.0.attention.wqkv.weight"][8:10].eq(2).all() and f["layers.0.attention.wqkv.weight"][10:].eq(3).all()
+    p = tmp_path / "model.pth"
+    torch.save(sd, p)
+    assert set(load_checkpoint(str(p))) == {"layers.0.attention.wqkv.weight", "norm.weight"}
+    (tmp_path / "m" / "histograms" / "Untitled" / "layer-0").mkdir(parents=True)
+    (tmp_path / "m2" / "histograms" / "layer-0").mkdir(parents=True)
+    assert resolve_histogram_dir(str(tmp_path / "m")).endswith("Untitled")
+    assert resolve_histogram_dir(str(tmp_path / "m2")).endswith("histograms")
