@@ -127,6 +127,9 @@ def main():
     ap.add_argument("--impl", default="teal_b200", choices=["teal_b200", "reference"])
     ap.add_argument("--workload", default="llama-3-8b", choices=sorted(WORKLOADS))
     ap.add_argument("--sparsity", type=float, default=0.5)
+    ap.add_argument("--profile", default="uniform", choices=["uniform", "greedy-means"],
+                    help="greedy-means: per-projection sparsities = the means of models/Mistral-7B/lookup at 0.5 "
+                         "(SURVEY.md section 8d, config 5): non-uniform thresholds, 3-threshold QKV, gate != up")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense baselines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--config", type=int, default=0, help="teal_set_config id (tuning)")
@@ -178,7 +181,12 @@ def main():
     max_seq = max(256, K + Wm + 16)
     dec = SparseDecoder(margs, device=f"cuda:{local_rank}", max_seq=max_seq, rank=rank, world=world, process_group=pg,
                         out_cap=max_seq)
-    thr = dec.calibrate(args.sparsity, n_tokens=8)
+    if args.profile == "greedy-means":
+        sp = {"q": 0.589, "k": 0.469, "v": 0.300, "o": 0.566, "gate": 0.474, "up": 0.417, "down": 0.582}
+        config["sparsity_profile"] = sp
+        thr = dec.calibrate(sp, n_tokens=8)
+    else:
+        thr = dec.calibrate(args.sparsity, n_tokens=8)
     lib = dec.lib
 
     def barrier():
