@@ -314,8 +314,14 @@ def main():
         n_l = reps * a.n_layer
         us = e0.elapsed_time(e1) * 1e3 / n_l
         alg = int(probe[0]) / a.n_layer + a.dim * 2 + dec.inter_l * 2  # gathered rows + x + h per launch
+        traffic = None
+        try:  # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu --set full capture (per launch)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get("traffic_bytes") if world == 1 else None
+        except Exception:
+            traffic = None
         rf = {"bound": "hbm", "kernel": "rowchunk_gemv_kernel<2,4,4> (fused RMSNorm + gate/up gather-GEMV + SiLU*mul)", "achieved": alg / us / 1e3,
-              "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": None, "peak_kind": f"of {peak_kind}",
+              "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
               "us_per_launch": us, "alg_bytes_per_launch": alg, "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),
               "timing": "CUDA events on the launching stream, graph of n_layer launches, each layer on its own weights and its own real decode input (L2 defeated)"}
 

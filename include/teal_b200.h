@@ -19,6 +19,8 @@
  *     `x.abs().gt(threshold)` on an fp16 tensor (utils/utils.py:51-52).  A lane survives iff
  *     |x| > fp16(threshold); NaN lanes are also gathered so that NaN poisons the output exactly
  *     as `mask * x` does in the reference.
+ *   - the teal_set_* knobs (config, PDL, probes) are process-global and not thread-safe: they exist for
+ *     benchmarks and profiling; the compute entry points themselves keep no state besides the workspace.
  *   - workspace: teal_workspace_bytes() bytes of device memory, zeroed ONCE with
  *     teal_workspace_init(); kernels leave it zeroed again on exit.  One workspace must not be
  *     used by two streams at the same time.
