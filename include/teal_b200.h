@@ -144,6 +144,85 @@ int teal_tp_allreduce_residual_f16(const void* const* peer_partials, void* const
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap,
                  void* stream);
 
+/* ---- step program: the whole decode step as ONE persistent data-flow kernel ------------------------
+ * The same step the calls above perform launch by launch (decode_one_token, gpt-fast/generate.py:73-77
+ * over model.py:133-190,258-259), planned once into a table of phases and run by one kernel per token:
+ * CTAs take (column tile, K chunk) items from a global ticket counter in dependency order and wait only
+ * on the completion flags of the producer tiles they read -- the down projection starts on the first
+ * finished tiles of gate/up, attention heads on their q/k/v tiles, the o projection on finished heads.
+ * Only the two RMSNorm points of a layer remain full barriers.
+ *
+ *   teal_step_program_sizes  bytes of the program blob and of the device scratch buffer
+ *   teal_step_program_plan   fills a HOST blob (device pointers embedded; no CUDA call, runs without a GPU);
+ *                            the caller uploads it verbatim to device memory
+ *   teal_step_program_run    one launch = one token; scratch must have been zeroed once before the first
+ *                            run and whenever a program is re-planned into it
+ *   teal_step_program_item   CPU-side introspection of one ticket (schedule verifier / tests)
+ * Layout and thresholds as in the calls above; a negative threshold keeps every lane. */
+typedef struct teal_layer_desc {
+  const void* wqkv;      /* fp16 [dim][ld_qkv], columns [q | k | v]; NULL = no attention block */
+  const void* wo;        /* fp16 [n_head*head_dim][ld_o] */
+  const void* w1;        /* gate, fp16 [dim][ld_1]; NULL = no MLP block */
+  const void* w3;        /* up,   fp16 [dim][ld_3] */
+  const void* w2;        /* down, fp16 [inter][ld_2] */
+  const void* attn_norm; /* fp16 [dim] */
+  const void* ffn_norm;  /* fp16 [dim] */
+  void* k_cache;         /* fp16 [n_kv_head][max_seq][head_dim] */
+  void* v_cache;
+  int64_t ld_qkv, ld_o, ld_1, ld_3, ld_2;
+  double thr[7];         /* q, k, v, o, gate, up, down */
+} teal_layer_desc;
+
+typedef struct teal_step_desc {
+  int32_t dim, n_head, n_kv_head, head_dim, inter, vocab, n_layer, max_seq;
+  double eps;
+  const void* tok_emb;     /* fp16 [vocab][dim]; NULL = x is preset by the caller and *ssq_init = sum(x^2) */
+  const int32_t* token;    /* device int32[1] */
+  const float* ssq_init;   /* device float[1], only read when tok_emb == NULL */
+  const void* lm_head;     /* fp16 [vocab][ld_head] row-major; NULL = stop after the last layer */
+  const void* final_norm;  /* fp16 [dim] */
+  int64_t ld_head;
+  const void* freqs_cis;   /* fp16 [max_seq][head_dim/2][2] */
+  int32_t* pos;            /* device int32[1] */
+  int32_t* out_tokens;     /* device int32[out_cap] */
+  void* argmax_packed;     /* device uint64[1], zero */
+  void* x;                 /* fp16 [dim] residual stream */
+  void* qkv;               /* fp16 [(n_head + 2 n_kv_head) * head_dim] */
+  void* att;               /* fp16 [n_head * head_dim] */
+  void* h;                 /* fp16 [inter] */
+  void* logits;            /* fp16 [vocab] */
+  void* scratch;           /* device, teal_step_program_sizes() bytes, zeroed once */
+  const teal_layer_desc* layers; /* HOST array [n_layer] */
+  int32_t out_cap;
+  /* tuning knobs, 0 = library default */
+  int32_t rows_small;      /* K chunk of the 256-column-tile GEMVs (default 64) */
+  int32_t rows_large;      /* K chunk of the 512-column-tile GEMVs (default 128) */
+  int32_t group_qkv;       /* column tiles per order group of the QKV phase (default 4) */
+  int32_t group_gate_up;   /* column tiles per order group of the gate/up phase (even; default 8) */
+  int32_t head_rows;       /* vocabulary rows per lm_head item (default 32) */
+  int32_t wide_melems;     /* projections with >= this many million weights use 512-column tiles (default 40) */
+  int32_t reserved;
+} teal_step_desc;
+
+typedef struct teal_item_info {
+  int32_t phase, kind, layer, item;       /* kind: 0 embed, 1 gemv, 2 attention, 3 lm_head, 4 advance */
+  int32_t ctile, kchunk, k_begin, k_end;  /* gemv items */
+  int32_t pub_index;                      /* publication (tile / head / item) this item contributes to */
+  int32_t pub_flag;                       /* absolute completion-flag index of that publication, -1 = none */
+  int32_t pub_cell;                       /* done cell it increments */
+  int32_t arrivals;                       /* items that must arrive before the publication completes */
+  int32_t dep_kind, dep_cell, dep_per_epoch; /* 0 none, 1 all publications of a phase, 2/3 flag list */
+  int32_t n_deps;
+  int32_t deps[32];
+} teal_item_info;
+
+int teal_step_program_sizes(const teal_step_desc* desc, size_t* program_bytes, size_t* scratch_bytes);
+int teal_step_program_plan(const teal_step_desc* desc, void* host_program, size_t program_bytes);
+int teal_step_program_run(const void* host_program, const void* device_program, void* stream);
+int teal_step_program_item(const void* host_program, int ticket, teal_item_info* out);
+/* number of tickets (items) of one step, or a negative teal_status */
+int teal_step_program_items(const void* host_program);
+
 /* Survivor set of one threshold, produced by the same device code the GEMV kernels use
  * (parity hook: "surviving-index set bit-exact").  idx_out: int32[Z] (sorted ascending, first
  * *count_out entries valid; its upper quarter is used as scratch for the keep mask),

@@ -57,6 +57,46 @@ _SIGS = {
     "teal_set_debug_timestamps": (_c.c_int, [_c.c_void_p]),
 }
 
+
+
+class LayerDesc(_c.Structure):
+    """``teal_layer_desc`` of include/teal_b200.h."""
+    _fields_ = [("wqkv", _c.c_void_p), ("wo", _c.c_void_p), ("w1", _c.c_void_p), ("w3", _c.c_void_p), ("w2", _c.c_void_p),
+                ("attn_norm", _c.c_void_p), ("ffn_norm", _c.c_void_p), ("k_cache", _c.c_void_p), ("v_cache", _c.c_void_p),
+                ("ld_qkv", _c.c_int64), ("ld_o", _c.c_int64), ("ld_1", _c.c_int64), ("ld_3", _c.c_int64),
+                ("ld_2", _c.c_int64), ("thr", _c.c_double * 7)]
+
+
+class StepDesc(_c.Structure):
+    """``teal_step_desc`` of include/teal_b200.h."""
+    _fields_ = [("dim", _c.c_int32), ("n_head", _c.c_int32), ("n_kv_head", _c.c_int32), ("head_dim", _c.c_int32),
+                ("inter", _c.c_int32), ("vocab", _c.c_int32), ("n_layer", _c.c_int32), ("max_seq", _c.c_int32),
+                ("eps", _c.c_double),
+                ("tok_emb", _c.c_void_p), ("token", _c.c_void_p), ("ssq_init", _c.c_void_p), ("lm_head", _c.c_void_p),
+                ("final_norm", _c.c_void_p), ("ld_head", _c.c_int64), ("freqs_cis", _c.c_void_p), ("pos", _c.c_void_p),
+                ("out_tokens", _c.c_void_p), ("argmax_packed", _c.c_void_p), ("x", _c.c_void_p), ("qkv", _c.c_void_p),
+                ("att", _c.c_void_p), ("h", _c.c_void_p), ("logits", _c.c_void_p), ("scratch", _c.c_void_p),
+                ("layers", _c.POINTER(LayerDesc)),
+                ("out_cap", _c.c_int32), ("rows_small", _c.c_int32), ("rows_large", _c.c_int32),
+                ("group_qkv", _c.c_int32), ("group_gate_up", _c.c_int32), ("head_rows", _c.c_int32),
+                ("wide_melems", _c.c_int32), ("reserved", _c.c_int32)]
+
+
+class ItemInfo(_c.Structure):
+    """``teal_item_info`` of include/teal_b200.h."""
+    _fields_ = [(n, _c.c_int32) for n in ("phase", "kind", "layer", "item", "ctile", "kchunk", "k_begin", "k_end",
+                                           "pub_index", "pub_flag", "pub_cell", "arrivals", "dep_kind", "dep_cell",
+                                           "dep_per_epoch", "n_deps")] + [("deps", _c.c_int32 * 32)]
+
+
+_SIGS.update({
+    "teal_step_program_sizes": (_c.c_int, [_c.POINTER(StepDesc), _c.POINTER(_c.c_size_t), _c.POINTER(_c.c_size_t)]),
+    "teal_step_program_plan": (_c.c_int, [_c.POINTER(StepDesc), _c.c_void_p, _c.c_size_t]),
+    "teal_step_program_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "teal_step_program_item": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(ItemInfo)]),
+    "teal_step_program_items": (_c.c_int, [_c.c_void_p]),
+})
+
 _lib = None
 
 

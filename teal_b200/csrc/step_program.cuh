@@ -1,0 +1,217 @@
+// Step program: the whole batch-1 decode step as ONE persistent kernel that walks a table of phases
+// (embedding, RMSNorm+QKV GEMV, RoPE+KV+attention, o GEMV+residual, RMSNorm+gate/up GEMV+SiLU*mul,
+// down GEMV+residual, lm_head+arg-max, bookkeeping) item by item.  Items are handed out by one global
+// ticket counter in dependency order; an item waits on the completion flags of exactly the producer
+// tiles it reads (data-flow), not on a kernel boundary.
+//
+// This header holds the phase table layout and the item -> (tile, chunk, dependency) arithmetic.  The
+// arithmetic is __host__ __device__: the planner, the CPU-side verifier (teal_step_program_item, used by
+// tests/test_step_program.py) and the kernel all run the same code.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace teal {
+
+constexpr int kSpWarps = 4;
+constexpr int kSpThreads = kSpWarps * 32;
+constexpr int kSpMaxDeps = 32;          // completion flags one item may wait on (one polling lane each)
+constexpr unsigned kSpMagic = 0x54454131u;  // "TEA1"
+
+enum { kPhEmbed = 0, kPhGemv = 1, kPhAttn = 2, kPhHead = 3, kPhAdvance = 4 };
+enum { kDepNone = 0, kDepAll = 1, kDepLanes = 2, kDepQkvHead = 3 };
+
+// What an item waits for before it reads its input.
+struct SpDep {
+  int kind;
+  int cell;        // kDepAll: done[cell] must reach epoch * per_epoch (every publication of the producer phase)
+  int per_epoch;
+  int flag0;       // kDepLanes / kDepQkvHead: first completion flag of the producer phase
+  int div;         // kDepLanes: input lanes per producer flag (producer column-tile width, or head_dim)
+  int pad[3];
+};
+
+// What a finished tile / head / item publishes.
+struct SpPub {
+  int flag0;       // flags[flag0 + i] = epoch when publication i of this phase is complete (-1: no flags)
+  int cell;        // done[cell] += 1 per publication
+  int count;       // publications per epoch
+  int pad;
+};
+
+struct SpSeg {
+  const __half* w;  // fp16 [Z][ldw], first column of the region
+  long long ldw;
+  int ncols, out_col0;
+  float thr;        // fp16-representable
+  int ctile0, nctiles;
+  int pad;
+};
+
+struct SpGemv {
+  const __half* x;
+  const __half* norm_w;
+  const float* ssq_in;
+  __half* y;
+  const __half* resid;
+  float* ssq_out;
+  float* acc;          // fp32 accumulator region of this projection kind (zero on entry, re-zeroed by the finaliser)
+  unsigned* counters;  // per-tile arrival counters of this projection kind
+  int Z, mode, in_mode, out_mode, nseg, n_ssq_in;
+  int variant;         // 0: 256-column tiles, 8 rows in flight; 1: 512-column tiles, 4 rows in flight
+  int rows_per_item;   // K chunk
+  int lpw;             // input lanes per warp per pass (<= 32): rows_per_item = kSpWarps * lpw * passes
+  int nkchunks, total_ctiles, target;
+  int group;           // order positions per group: items run K-chunk-major inside a group, groups in sequence
+  int rot;             // plain mode: order position p -> column tile (p + rot) % total_ctiles (k, v tiles before q)
+  float eps;
+  int pad;
+  SpSeg seg[3];
+};
+
+struct SpAttn {
+  const __half* qkv;
+  const __half* freqs;
+  __half* k_cache;
+  __half* v_cache;
+  const int* pos;
+  __half* out;
+  int n_head, n_kv, hd, max_seq;
+  float scale;
+  int prod_cols;       // column-tile width of the producing QKV phase
+  int prod_nseg;
+  int prod_col0[3], prod_ncols[3], prod_ctile0[3];
+};
+
+struct SpHead {
+  const __half* x;
+  const __half* norm_w;
+  const __half* W;     // [V][ldw] row-major (never sparsified, gpt-fast/model.py:141-142)
+  __half* y;
+  unsigned long long* argmax;
+  long long ldw;
+  int Z, V, rows_per_item;
+  float eps;
+};
+
+struct SpEmbed {
+  const __half* emb;
+  const int* token;
+  __half* x;
+  float* ssq_out;
+  int dim, pad;
+};
+
+struct SpAdvance {
+  unsigned long long* argmax;
+  int* token;
+  int* pos;
+  int* out_tokens;
+  int out_cap, pad;
+};
+
+struct alignas(16) SpPhase {
+  int kind, item0, nitems, layer;
+  SpDep dep;
+  SpPub pub;
+  union {
+    SpGemv g;
+    SpAttn a;
+    SpHead h;
+    SpEmbed e;
+    SpAdvance v;
+  } u;
+};
+static_assert(sizeof(SpPhase) % 16 == 0, "SpPhase is copied to shared memory in 16-byte words");
+
+struct alignas(16) SpHeader {
+  unsigned magic;
+  int nphases, total_items, smem_bytes;
+  unsigned* ticket;   // control block in the scratch buffer: [ticket][exited][epoch]
+  unsigned* exited;
+  unsigned* epoch;
+  unsigned* flags;
+  unsigned* done;
+  int nflags, ndone;
+  unsigned long long scratch_bytes;
+  int pad[2];
+};
+static_assert(sizeof(SpHeader) % 16 == 0, "phase table must stay 16-byte aligned");
+
+// ------------------------------------------------------------------------------------------------
+// item -> (column tile, K chunk).  Order position p runs over the column tiles in "publication order":
+//   pair mode : gate tile j and up tile j are neighbours (p = 2j, 2j+1), so tile pair j completes early;
+//   plain mode: rotated by `rot` (QKV: the k and v tiles first, every attention head needs them).
+// Positions are cut into groups of `group`; inside a group the K chunk is the slow index (neighbouring
+// CTAs read neighbouring pieces of the same weight rows), groups follow each other, so the tiles of group
+// 0 are complete -- and their consumers may start -- while later groups still stream.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline void sp_gemv_decode(const SpGemv& g, int item, int* ct, int* kc) {
+  const int T = g.total_ctiles, nk = g.nkchunks, G = g.group;
+  const int per_group = G * nk;
+  const int grp = item / per_group;
+  const int r = item - grp * per_group;
+  const int left = T - grp * G;
+  const int gsz = left < G ? left : G;
+  const int k = r / gsz;
+  const int p = grp * G + (r - k * gsz);
+  int c;
+  if (g.mode == kModePairSilu) {
+    c = (p & 1) ? (T >> 1) + (p >> 1) : (p >> 1);
+  } else {
+    c = p + g.rot;
+    if (c >= T) c -= T;
+  }
+  *ct = c;
+  *kc = k;
+}
+
+// publication index of column tile ct (pair mode: gate tile j and up tile j share completion counter j)
+__host__ __device__ inline int sp_gemv_cidx(const SpGemv& g, int ct) {
+  return (g.mode == kModePairSilu && ct >= g.seg[1].ctile0) ? ct - g.seg[1].ctile0 : ct;
+}
+
+__host__ __device__ inline int sp_attn_col_tile(const SpAttn& a, int col) {
+  for (int s = 0; s < a.prod_nseg; ++s)
+    if (col >= a.prod_col0[s] && col < a.prod_col0[s] + a.prod_ncols[s])
+      return a.prod_ctile0[s] + (col - a.prod_col0[s]) / a.prod_cols;
+  return 0;
+}
+
+// Absolute indices of the completion flags item `item` of phase `ph` must see before it may read its input
+// (kDepLanes / kDepQkvHead).  Returns the count, at most kSpMaxDeps (the planner guarantees the bound).
+__host__ __device__ inline int sp_item_deps(const SpPhase& ph, int item, int* out) {
+  int n = 0;
+  if (ph.dep.kind == kDepLanes) {
+    const SpGemv& g = ph.u.g;
+    int ct, kc;
+    sp_gemv_decode(g, item, &ct, &kc);
+    const int kbeg = kc * g.rows_per_item;
+    int kend = kbeg + g.rows_per_item;
+    if (kend > g.Z) kend = g.Z;
+    for (int f = kbeg / ph.dep.div; f <= (kend - 1) / ph.dep.div && n < kSpMaxDeps; ++f) out[n++] = ph.dep.flag0 + f;
+  } else if (ph.dep.kind == kDepQkvHead) {
+    const SpAttn& a = ph.u.a;
+    const int h = item, kvh = h / (a.n_head / a.n_kv);
+    const int c0[3] = {h * a.hd, a.n_head * a.hd + kvh * a.hd, (a.n_head + a.n_kv) * a.hd + kvh * a.hd};
+    for (int r = 0; r < 3; ++r) {
+      const int t0 = sp_attn_col_tile(a, c0[r]), t1 = sp_attn_col_tile(a, c0[r] + a.hd - 1);
+      for (int t = t0; t <= t1 && n < kSpMaxDeps; ++t) {
+        bool dup = false;
+        for (int j = 0; j < n; ++j) dup = dup || (out[j] == ph.dep.flag0 + t);
+        if (!dup) out[n++] = ph.dep.flag0 + t;
+      }
+    }
+  }
+  return n;
+}
+
+// host side (step_program.cu)
+struct StepScratchLayout {
+  size_t control, done, flags, counters[4], acc[4], ssq[2], total;
+  int nflags, ndone, ncounters[4];
+};
+
+}  // namespace teal

@@ -160,6 +160,10 @@ class SparseDecoder:
             self._setup_peer_exchange()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_mode = None
+        self.graph_engine = None
+        self.program = None          # StepProgram (engine="program"): the whole step as one persistent kernel
+        self.program_mode = None
+        self.program_scratch = None
         self.taps = None  # calibration taps
         self.force_tp_path = False  # tests: take the (plain GEMV -> all-reduce -> residual_add) route at world == 1
         self.ffn_inputs = None  # when a list: per-layer copies of (x, ssq) entering the MLP block (bench roofline)
@@ -274,6 +278,7 @@ class SparseDecoder:
         self.thresholds = list(thresholds)
         self.sparse = any(t is not None for t in thresholds)
         self.graph = None
+        self.program = None
 
     def calibrate(self, sparsities, n_tokens: int = 16, seed: int = 7):
         """Synthetic-model calibration through the reference's own path: run dense
@@ -399,11 +404,75 @@ class SparseDecoder:
                              self.out_tokens.data_ptr(), self.out_tokens.numel(), sp), "advance")
         self.kernels_per_step = n_launch + 2
 
-    # ------------------------------------------------------------------ public API
-    def capture(self, mode: str = "sparse", pdl: bool = True):
-        """Capture one decode step into a CUDA graph (generate.py:420's reduce-overhead equivalent)."""
+    # ------------------------------------------------------------------ step program (one kernel per token)
+    def build_program(self, mode: str = "sparse", **tuning):
+        """Plan the whole step (same buffers, same arithmetic as `_enqueue_step`) into a `StepProgram`: one persistent
+        data-flow kernel per token instead of 5 launches per layer.  `tuning`: the knobs of teal_step_desc
+        (rows_small, rows_large, group_qkv, group_gate_up, head_rows, wide_melems, reserved = CTAs per SM cap)."""
+        from . import program as _prog
+        if self.world != 1:
+            raise NotImplementedError("the step program is single-GPU (the TP exchange step is not a phase yet)")
+        if mode not in ("sparse", "dense_own"):
+            raise ValueError("step program modes: 'sparse', 'dense_own'")
         if mode == "sparse" and not self.sparse:
             raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
+        a = self.args
+        d = _lib.StepDesc()
+        d.dim, d.n_head, d.n_kv_head, d.head_dim = a.dim, self.n_head_l, self.n_kv_l, self.hd
+        d.inter, d.vocab, d.max_seq, d.eps = self.inter_l, a.vocab_size, self.max_seq, a.norm_eps
+        d.tok_emb, d.token, d.ssq_init = self.tok_emb.data_ptr(), self.token.data_ptr(), None
+        d.lm_head, d.final_norm, d.ld_head = self.lm_head.data_ptr(), self.final_norm.data_ptr(), a.dim
+        d.freqs_cis, d.pos, d.out_tokens = self.freqs.data_ptr(), self.pos.data_ptr(), self.out_tokens.data_ptr()
+        d.argmax_packed, d.out_cap = self.argmax.data_ptr(), self.out_tokens.numel()
+        d.x, d.qkv, d.att, d.h, d.logits = (t.data_ptr() for t in (self.x, self.qkv, self.att, self.h, self.logits))
+        for k, v in tuning.items():
+            if k not in _prog.TUNING_KEYS:
+                raise TypeError(f"unknown step-program knob {k!r}")
+            setattr(d, k, int(v))
+        layers = []
+        for li, W in enumerate(self.layers):
+            t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else None
+            layers.append(_prog.layer_desc(
+                wqkv=W["wqkv"].data_ptr(), wo=W["wo"].data_ptr(), w1=W["w1"].data_ptr(), w3=W["w3"].data_ptr(),
+                w2=W["w2"].data_ptr(), attn_norm=W["attn_norm"].data_ptr(), ffn_norm=W["ffn_norm"].data_ptr(),
+                k_cache=self.k_cache[li].data_ptr(), v_cache=self.v_cache[li].data_ptr(), ld_qkv=W["wqkv"].stride(1),
+                ld_o=W["wo"].stride(1), ld_1=W["w1"].stride(1), ld_3=W["w3"].stride(1), ld_2=W["w2"].stride(1), thr=t))
+        d.scratch = 256  # placeholder: sizes() only validates that it is non-null
+        prog = _prog.StepProgram(d, layers)
+        self.program_scratch = torch.zeros(prog.scratch_bytes, dtype=torch.uint8, device=self.dev)
+        d.scratch = self.program_scratch.data_ptr()
+        prog.plan().upload(self.dev)
+        torch.cuda.synchronize()
+        self.program, self.program_mode = prog, mode
+        return prog
+
+    def _enqueue_program(self):
+        self.program.run(torch.cuda.current_stream().cuda_stream)
+        self.kernels_per_step = 1
+
+    # ------------------------------------------------------------------ public API
+    def capture(self, mode: str = "sparse", pdl: bool = True, engine: str = "graph", **tuning):
+        """Capture one decode step into a CUDA graph (generate.py:420's reduce-overhead equivalent).
+        engine="graph": one launch per projection group (PDL chain); engine="program": the whole step as one
+        persistent data-flow kernel (`build_program`)."""
+        if mode == "sparse" and not self.sparse:
+            raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
+        if engine == "program":
+            if self.program is None or self.program_mode != mode or tuning:
+                self.build_program(mode, **tuning)
+            with torch.cuda.stream(self.stream):
+                saved = (self.token.clone(), self.pos.clone())
+                self._enqueue_program()  # warm-up outside capture (function attributes, occupancy query)
+                self.stream.synchronize()
+                self.token.copy_(saved[0]); self.pos.copy_(saved[1]); self.argmax.zero_()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._enqueue_program()
+            torch.cuda.synchronize()
+            self.graph, self.graph_mode, self.graph_engine = g, mode, engine
+            return g
+        if engine != "graph":
+            raise ValueError("engine: 'graph' or 'program'")
         self.lib.teal_set_pdl(1 if (pdl and mode != "dense_cublas") else 0)
         with torch.cuda.stream(self.stream):
             ops.workspace(self.dev, self.stream.cuda_stream)
@@ -418,16 +487,16 @@ class SparseDecoder:
                 self._enqueue_step(mode)
         self.lib.teal_set_pdl(0)
         torch.cuda.synchronize()
-        self.graph, self.graph_mode = g, mode
+        self.graph, self.graph_mode, self.graph_engine = g, mode, "graph"
         return g
 
     def decode_one_token(self):
         """Replay the captured step (device-side token/position; no host sync)."""
         self.graph.replay()
 
-    def generate(self, first_token: int, n_new: int, mode: str = "sparse") -> torch.Tensor:
-        if self.graph is None or self.graph_mode != mode:
-            self.capture(mode)
+    def generate(self, first_token: int, n_new: int, mode: str = "sparse", engine: str = "graph") -> torch.Tensor:
+        if self.graph is None or self.graph_mode != mode or self.graph_engine != engine:
+            self.capture(mode, engine=engine)
         self.reset(first_token)
         for _ in range(n_new):
             self.graph.replay()
