@@ -201,7 +201,12 @@ typedef struct teal_step_desc {
   int32_t group_gate_up;   /* column tiles per order group of the gate/up phase (even; default 8) */
   int32_t head_rows;       /* vocabulary rows per lm_head item (default 32) */
   int32_t wide_melems;     /* projections with >= this many million weights use 512-column tiles (default 40) */
-  int32_t reserved;
+  int32_t reserved;        /* cap on resident CTAs per SM (default: occupancy) */
+  int32_t poll_ns;         /* back-off between two polls of a completion flag, ns (default 32; negative = none) */
+  int32_t opts;            /* bit 0: a CTA that has seen a whole-phase dependency satisfied does not poll it again */
+  void* debug_times;       /* profiling: device uint64[4 * phases] = per phase {first ticket taken, first item ready
+                            * (dependencies seen), last item finished} in globaltimer ns (min, min, max; the caller
+                            * initialises {~0, ~0, 0, 0}) and the summed busy ns of its items; NULL = off */
 } teal_step_desc;
 
 typedef struct teal_item_info {

@@ -80,11 +80,11 @@ __device__ __forceinline__ float2 sp_ldcg_half2(const __half* p) {
 
 // Spin until *p has reached `want` (wrap-safe).  Forward progress is guaranteed by the ticket order; the
 // watchdog turns a protocol bug into a trap (sticky CUDA error) instead of a hung GPU.
-__device__ __forceinline__ void sp_spin_reach(const unsigned* p, unsigned want) {
+__device__ __forceinline__ void sp_spin_reach(const unsigned* p, unsigned want, unsigned poll_ns) {
   if ((int)(sp_ld_acquire(p) - want) >= 0) return;
   const long long t0 = clock64();
   while ((int)(sp_ld_acquire(p) - want) < 0) {
-    __nanosleep(32);
+    if (poll_ns) __nanosleep(poll_ns);
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
@@ -555,6 +555,11 @@ __global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsig
   // serial number of this token: only the last CTA to LEAVE a launch bumps the cell, so every CTA of a launch reads the
   // same value no matter when it starts
   const unsigned epoch = __ldcg(hdr->epoch) + 1u;
+  const unsigned poll_ns = (unsigned)hdr->poll_ns;
+  const bool cache_all = (hdr->opts & 1) != 0;
+  int dep_ok = -1;  // phase whose whole-phase dependency this CTA has already seen satisfied
+  unsigned long long* const dbg = hdr->dbg;
+  long long t_ready = 0;
 
   unsigned next_t = 0;
   if (tid == 0) next_t = atomicAdd(ticket, 1u);
@@ -584,21 +589,27 @@ __global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsig
       __syncthreads();
     }
     const int item = t - s_ph.item0;
+    if (dbg && tid == 0) atomicMin(dbg + 4 * pi, (unsigned long long)globaltimer_ns());
 
     // ---- wait for exactly what this item reads --------------------------------------------------------------
-    if (s_ph.dep.kind != kDepNone) {
+    if (s_ph.dep.kind != kDepNone && !(cache_all && s_ph.dep.kind == kDepAll && dep_ok == pi)) {
       if (tid < 32) {
         if (s_ph.dep.kind == kDepAll) {
-          if (lane == 0) sp_spin_reach(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch);
+          if (lane == 0) sp_spin_reach(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch, poll_ns);
         } else {
           int n = 0;
           if (lane == 0) n = sp_item_deps(s_ph, item, s_deps);
           n = __shfl_sync(0xffffffffu, n, 0);  // also orders lane 0's s_deps stores before the other lanes' loads
           __syncwarp();
-          if (lane < n) sp_spin_reach(flags + s_deps[lane], epoch);
+          if (lane < n) sp_spin_reach(flags + s_deps[lane], epoch, poll_ns);
         }
       }
       __syncthreads();
+      if (s_ph.dep.kind == kDepAll) dep_ok = pi;
+    }
+    if (dbg && tid == 0) {
+      t_ready = globaltimer_ns();
+      atomicMin(dbg + 4 * pi + 1, (unsigned long long)t_ready);
     }
 
     switch (s_ph.kind) {
@@ -631,6 +642,11 @@ __global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsig
         break;
     }
     __syncthreads();  // s_ctl / s_ph / dynamic shared memory are reused by the next item
+    if (dbg && tid == 0) {
+      const long long t_end = globaltimer_ns();
+      atomicMax(dbg + 4 * pi + 2, (unsigned long long)t_end);
+      atomicAdd(dbg + 4 * pi + 3, (unsigned long long)(t_end - t_ready));
+    }
   }
 
   // ---- leave: the last CTA out rewinds the ticket counter and bumps the epoch for the next launch -----------
@@ -1050,7 +1066,10 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
   H->nflags = L.nflags;
   H->ndone = L.ndone;
   H->scratch_bytes = L.total;
-  H->pad[0] = d->reserved;  // cap on resident CTAs per SM (0 = occupancy)
+  H->ctas_per_sm = d->reserved;
+  H->poll_ns = d->poll_ns == 0 ? 32 : (d->poll_ns < 0 ? 0 : d->poll_ns);
+  H->opts = d->opts;
+  H->dbg = reinterpret_cast<unsigned long long*>(d->debug_times);
   return TEAL_OK;
 }
 
@@ -1152,7 +1171,7 @@ int teal_step_program_run(const void* host_program, const void* device_program, 
     s_occ_smem = H->smem_bytes;
   }
   int per_sm = s_occ;
-  if (H->pad[0] > 0 && H->pad[0] < per_sm) per_sm = H->pad[0];
+  if (H->ctas_per_sm > 0 && H->ctas_per_sm < per_sm) per_sm = H->ctas_per_sm;
   long long grid = (long long)di.sm_count * per_sm;
   if (grid > H->total_items) grid = H->total_items;
   step_program_kernel<<<dim3((unsigned)grid), dim3(kSpThreads), (size_t)H->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(

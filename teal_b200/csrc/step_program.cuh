@@ -136,7 +136,11 @@ struct alignas(16) SpHeader {
   unsigned* done;
   int nflags, ndone;
   unsigned long long scratch_bytes;
-  int pad[2];
+  int ctas_per_sm;    // cap on resident CTAs per SM (0 = occupancy)
+  int poll_ns;        // back-off between two polls of a flag
+  int opts;           // bit 0: cache satisfied whole-phase dependencies per CTA
+  int pad;
+  unsigned long long* dbg;  // optional per-phase timestamps [nphases][4] (teal_step_desc::debug_times)
 };
 static_assert(sizeof(SpHeader) % 16 == 0, "phase table must stay 16-byte aligned");
 

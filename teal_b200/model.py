@@ -163,6 +163,7 @@ class SparseDecoder:
         self.graph_engine = None
         self.program = None          # StepProgram (engine="program"): the whole step as one persistent kernel
         self.program_mode = None
+        self.program_tuning = None
         self.program_scratch = None
         self.taps = None  # calibration taps
         self.force_tp_path = False  # tests: take the (plain GEMV -> all-reduce -> residual_add) route at world == 1
@@ -428,7 +429,7 @@ class SparseDecoder:
         for k, v in tuning.items():
             if k not in _prog.TUNING_KEYS:
                 raise TypeError(f"unknown step-program knob {k!r}")
-            setattr(d, k, int(v))
+            setattr(d, k, int(v))  # debug_times: a device address
         layers = []
         for li, W in enumerate(self.layers):
             t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else None
@@ -443,7 +444,7 @@ class SparseDecoder:
         d.scratch = self.program_scratch.data_ptr()
         prog.plan().upload(self.dev)
         torch.cuda.synchronize()
-        self.program, self.program_mode = prog, mode
+        self.program, self.program_mode, self.program_tuning = prog, mode, dict(tuning)
         return prog
 
     def _enqueue_program(self):
@@ -458,7 +459,7 @@ class SparseDecoder:
         if mode == "sparse" and not self.sparse:
             raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
         if engine == "program":
-            if self.program is None or self.program_mode != mode or tuning:
+            if self.program is None or self.program_mode != mode or self.program_tuning != tuning:
                 self.build_program(mode, **tuning)
             with torch.cuda.stream(self.stream):
                 saved = (self.token.clone(), self.pos.clone())

@@ -19,7 +19,8 @@ from ._lib import ItemInfo, LayerDesc, StepDesc
 PROJ_ORDER = ("q", "k", "v", "o", "gate", "up", "down")
 KIND_NAMES = {0: "embed", 1: "gemv", 2: "attn", 3: "lm_head", 4: "advance"}
 DEP_NONE, DEP_ALL, DEP_LANES, DEP_QKV_HEAD = 0, 1, 2, 3
-TUNING_KEYS = ("rows_small", "rows_large", "group_qkv", "group_gate_up", "head_rows", "wide_melems", "reserved")
+TUNING_KEYS = ("rows_small", "rows_large", "group_qkv", "group_gate_up", "head_rows", "wide_melems", "reserved", "poll_ns",
+               "opts", "debug_times")
 
 
 def layer_desc(*, wqkv=0, wo=0, w1=0, w3=0, w2=0, attn_norm=0, ffn_norm=0, k_cache=0, v_cache=0, ld_qkv=0, ld_o=0, ld_1=0,
