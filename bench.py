@@ -133,6 +133,10 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="skip the dense baselines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--config", type=int, default=0, help="teal_set_config id (tuning)")
+    ap.add_argument("--engine", default="graph", choices=["graph", "program"],
+                    help="graph: one launch per projection group in a CUDA graph (default, fastest measured); program: the "
+                         "whole step as one persistent data-flow kernel (teal_step_program_*, single GPU)")
+    ap.add_argument("--knob", action="append", default=[], metavar="NAME=INT", help="step-program tuning knob (repeatable)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -194,8 +198,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    engine = args.engine if world == 1 else "graph"
+    knobs = {k: int(v) for k, v in (kv.split("=") for kv in args.knob)}
+    config["engine"] = engine if not knobs else f"{engine} {knobs}"
+
     def timed(mode, steps, warmup, e2e=False):
-        dec.capture(mode)
+        if engine == "program" and mode != "dense_cublas":
+            dec.capture(mode, engine="program", **knobs)
+        else:
+            dec.capture(mode)
         dec.reset(1)
         host_in = torch.ones(1, dtype=torch.int32).pin_memory()
         host_out = torch.zeros(1, dtype=torch.int32).pin_memory()

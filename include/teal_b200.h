@@ -203,10 +203,15 @@ typedef struct teal_step_desc {
   int32_t wide_melems;     /* projections with >= this many million weights use 512-column tiles (default 40) */
   int32_t reserved;        /* cap on resident CTAs per SM (default: occupancy) */
   int32_t poll_ns;         /* back-off between two polls of a completion flag, ns (default 32; negative = none) */
-  int32_t opts;            /* bit 0: a CTA that has seen a whole-phase dependency satisfied does not poll it again */
+  int32_t opts;            /* bit 0: a CTA that has seen a whole-phase dependency satisfied does not poll it again;
+                            * bit 1: the RMSNorm scale is computed once per (CTA, phase) instead of per warp and item */
   void* debug_times;       /* profiling: device uint64[4 * phases] = per phase {first ticket taken, first item ready
                             * (dependencies seen), last item finished} in globaltimer ns (min, min, max; the caller
                             * initialises {~0, ~0, 0, 0}) and the summed busy ns of its items; NULL = off */
+  int32_t warps;           /* warps per CTA: 4 (default, 7 CTAs per SM) or 2 (14 CTAs per SM) */
+  int32_t stagger_ns;      /* CTAs released by a whole-phase wait start hash(cta) in [0,8) x stagger_ns apart (default 0) */
+  int32_t rows_kind[4];    /* K chunk per projection kind {qkv, o, gate/up, down}; 0 = rows_small / rows_large */
+  int32_t reserved2[2];
 } teal_step_desc;
 
 typedef struct teal_item_info {

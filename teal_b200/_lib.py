@@ -79,7 +79,8 @@ class StepDesc(_c.Structure):
                 ("layers", _c.POINTER(LayerDesc)),
                 ("out_cap", _c.c_int32), ("rows_small", _c.c_int32), ("rows_large", _c.c_int32),
                 ("group_qkv", _c.c_int32), ("group_gate_up", _c.c_int32), ("head_rows", _c.c_int32),
-                ("wide_melems", _c.c_int32), ("reserved", _c.c_int32), ("poll_ns", _c.c_int32), ("opts", _c.c_int32), ("debug_times", _c.c_void_p)]
+                ("wide_melems", _c.c_int32), ("reserved", _c.c_int32), ("poll_ns", _c.c_int32), ("opts", _c.c_int32), ("debug_times", _c.c_void_p), ("warps", _c.c_int32),
+                ("stagger_ns", _c.c_int32), ("rows_kind", _c.c_int32 * 4), ("reserved2", _c.c_int32 * 2)]
 
 
 class ItemInfo(_c.Structure):

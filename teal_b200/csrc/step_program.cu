@@ -89,6 +89,17 @@ __device__ __forceinline__ void sp_spin_reach(const unsigned* p, unsigned want, 
   }
 }
 
+// same, reporting whether the caller had to wait (i.e. it was released by the producer, not late to the party)
+__device__ __forceinline__ bool sp_spin_reach_ext(const unsigned* p, unsigned want, unsigned poll_ns) {
+  if ((int)(sp_ld_acquire(p) - want) >= 0) return false;
+  const long long t0 = clock64();
+  while ((int)(sp_ld_acquire(p) - want) < 0) {
+    if (poll_ns) __nanosleep(poll_ns);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+  return true;
+}
+
 // All threads of the CTA call this after the stores of publication `index`: barrier, then one thread makes the
 // CTA's stores visible device-wide (cumulative release) and raises the flag / bumps the phase counter.
 __device__ __forceinline__ void sp_publish(const SpPub& pub, int index, unsigned epoch, unsigned* flags, unsigned* done) {
@@ -104,10 +115,12 @@ __device__ __forceinline__ void sp_publish(const SpPub& pub, int index, unsigned
 // One (column tile, K chunk) of a projection: [RMSNorm ->] threshold -> ballot compaction -> gather-GEMV ->
 // smem + RED reduction -> arrival counter -> (last arriver) epilogue + publication.  Same arithmetic as
 // rowchunk_gemv_kernel (kernels/sparse_gemv.py:45-83,147-194 of the reference).
-template <int VEC, int U>
+template <int VEC, int U, int W, bool EXT>
 __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, int item, unsigned epoch, unsigned* flags,
-                                             unsigned* done, float* s_red, float* s_ssq, int* s_last) {
+                                             unsigned* done, float* s_red, float* s_ssq, int* s_last, bool rs_known,
+                                             float rs_value) {
   constexpr int COLS = 256 * VEC;
+  constexpr int kThreadsW = W * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int ct, kc;
   sp_gemv_decode(g, item, &ct, &kc);
@@ -128,7 +141,14 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
   // RMSNorm scale from the producer's per-tile sums of squares (gpt-fast/model.py:286-291)
   float rs = 1.f;
   const bool rms = g.in_mode == kInRmsNorm;
-  if (rms) {
+  bool load_ssq = rms;
+  if constexpr (EXT) {
+    if (rs_known) {  // computed once per (CTA, phase) by the caller: no 4 x CTAs hot-spot on the partials' L2 sector
+      rs = rs_value;
+      load_ssq = false;
+    }
+  }
+  if (load_ssq) {
     float t = 0.f;
     for (int i = lane; i < g.n_ssq_in; i += 32) t += __ldcg(g.ssq_in + i);
 #pragma unroll
@@ -145,7 +165,7 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
   const int kbeg = kc * g.rows_per_item;
   const int kend = min(g.Z, kbeg + g.rows_per_item);
   const int lpw = g.lpw;
-  for (int kb = kbeg + warp * lpw; kb < kend; kb += kSpWarps * lpw) {
+  for (int kb = kbeg + warp * lpw; kb < kend; kb += W * lpw) {
     const int k = kb + lane;
     const bool valid = lane < lpw && k < kend;
     float xf = 0.f;
@@ -199,10 +219,10 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
   }
   __syncthreads();
   const int acc0 = sg.out_col0 + col0;
-  for (int c = tid * 4; c < wcols; c += kSpThreads * 4) {
+  for (int c = tid * 4; c < wcols; c += kThreadsW * 4) {
     float4 a = *reinterpret_cast<const float4*>(s_red + c);
 #pragma unroll
-    for (int w = 1; w < kSpWarps; ++w) {
+    for (int w = 1; w < W; ++w) {
       const float4 b = *reinterpret_cast<const float4*>(s_red + w * COLS + c);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
@@ -226,7 +246,7 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
   float ssq = 0.f;
   if (pair) {
     const int g0 = g.seg[0].out_col0 + col0, u0 = g.seg[1].out_col0 + col0;
-    for (int c = tid * 4; c < wcols; c += kSpThreads * 4) {
+    for (int c = tid * 4; c < wcols; c += kThreadsW * 4) {
       const float4 gg = ld_cg_f4(g.acc + g0 + c), uu = ld_cg_f4(g.acc + u0 + c);
       st_cg_f4(g.acc + g0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
       st_cg_f4(g.acc + u0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -238,7 +258,7 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
       *reinterpret_cast<uint2*>(g.y + col0 + c) = o;
     }
   } else {
-    for (int c = tid * 4; c < wcols; c += kSpThreads * 4) {
+    for (int c = tid * 4; c < wcols; c += kThreadsW * 4) {
       const float4 a = ld_cg_f4(g.acc + acc0 + c);
       st_cg_f4(g.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
       __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
@@ -263,7 +283,7 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
     if (tid == 0) {
       float a = 0.f;
 #pragma unroll
-      for (int w = 0; w < kSpWarps; ++w) a += s_ssq[w];
+      for (int w = 0; w < W; ++w) a += s_ssq[w];
       g.ssq_out[cidx] = a;
     }
   }
@@ -274,7 +294,7 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
 // ------------------------------------------------------------------------------------------------ attention item
 // RoPE(q, k) + KV-cache append + attention of the one query over positions [0, pos] for ONE query head
 // (gpt-fast/model.py:170-186).  Same arithmetic as attn_decode_kernel, 4 warps.
-template <int HD>
+template <int HD, int W>
 __device__ __forceinline__ void sp_attn_item(const SpAttn& a, const SpPub& pub, int h, unsigned epoch, unsigned* flags,
                                              unsigned* done, float* smem) {
   constexpr int EPL = HD / 32;
@@ -282,8 +302,8 @@ __device__ __forceinline__ void sp_attn_item(const SpAttn& a, const SpPub& pub, 
   float* s_knew = s_q + HD;
   float* s_vnew = s_knew + HD;
   float* s_m = s_vnew + HD;
-  float* s_l = s_m + kSpWarps;
-  float* s_acc = s_l + kSpWarps;  // [kSpWarps][HD]
+  float* s_l = s_m + W;
+  float* s_acc = s_l + W;  // [W][HD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rep = a.n_head / a.n_kv;
   const int kvh = h / rep;
@@ -294,7 +314,7 @@ __device__ __forceinline__ void sp_attn_item(const SpAttn& a, const SpPub& pub, 
   const __half* kh = a.qkv + (size_t)a.n_head * HD + (size_t)kvh * HD;
   const __half* vh = a.qkv + (size_t)(a.n_head + a.n_kv) * HD + (size_t)kvh * HD;
   const __half* fr = a.freqs + (size_t)pos * HD;  // HD/2 (cos, sin) pairs
-  for (int i = tid; i < HD; i += kSpThreads) {
+  for (int i = tid; i < HD; i += (W * 32)) {
     if (i < HD / 2) {
       const float c = __half2float(fr[2 * i]), s = __half2float(fr[2 * i + 1]);
       const float2 q = sp_ldcg_half2(qh + 2 * i), k = sp_ldcg_half2(kh + 2 * i);
@@ -329,11 +349,11 @@ __device__ __forceinline__ void sp_attn_item(const SpAttn& a, const SpPub& pub, 
   const __half* kbase = a.k_cache + (size_t)kvh * max_seq * HD;
   const __half* vbase = a.v_cache + (size_t)kvh * max_seq * HD;
   constexpr int PB = 4;  // positions per iteration: independent loads (latency-bound at short context)
-  for (int p0 = warp; p0 <= pos; p0 += kSpWarps * PB) {
+  for (int p0 = warp; p0 <= pos; p0 += W * PB) {
     float kk[PB][EPL], vv[PB][EPL];
 #pragma unroll
     for (int b = 0; b < PB; ++b) {
-      const int p = p0 + b * kSpWarps;
+      const int p = p0 + b * W;
       if (p < pos) {  // positions written by earlier launches
 #pragma unroll
         for (int e = 0; e < EPL / 2; ++e) {
@@ -349,7 +369,7 @@ __device__ __forceinline__ void sp_attn_item(const SpAttn& a, const SpPub& pub, 
     }
 #pragma unroll
     for (int b = 0; b < PB; ++b) {
-      const int p = p0 + b * kSpWarps;
+      const int p = p0 + b * W;
       if (p <= pos) {
         float s = 0.f;
 #pragma unroll
@@ -370,13 +390,13 @@ __device__ __forceinline__ void sp_attn_item(const SpAttn& a, const SpPub& pub, 
 #pragma unroll
   for (int e = 0; e < EPL; ++e) s_acc[warp * HD + lane * EPL + e] = acc[e];
   __syncthreads();
-  for (int i = tid; i < HD; i += kSpThreads) {
+  for (int i = tid; i < HD; i += (W * 32)) {
     float M = -CUDART_INF_F;
 #pragma unroll
-    for (int w = 0; w < kSpWarps; ++w) M = fmaxf(M, s_m[w]);
+    for (int w = 0; w < W; ++w) M = fmaxf(M, s_m[w]);
     float L = 0.f, o = 0.f;
 #pragma unroll
-    for (int w = 0; w < kSpWarps; ++w) {
+    for (int w = 0; w < W; ++w) {
       const float f = (s_m[w] == -CUDART_INF_F) ? 0.f : __expf(s_m[w] - M);
       L = fmaf(s_l[w], f, L);
       o = fmaf(s_acc[w * HD + i], f, o);
@@ -395,7 +415,7 @@ __device__ __forceinline__ unsigned long long sp_pack_argmax(float v, int idx) {
 
 // `rows_per_item` vocabulary rows of logits = W * rmsnorm(x) (gpt-fast/model.py:141-142) + packed arg-max.
 // The normalised x (Z halves in shared memory) is rebuilt only when the CTA's previous item was not an lm_head item.
-template <int UNROLL>
+template <int UNROLL, int W>
 __device__ __forceinline__ void sp_head_item(const SpHead& hp, const SpPub& pub, int item, bool build_xs, unsigned epoch,
                                              unsigned* flags, unsigned* done, __half* xs, float* s_part,
                                              unsigned long long* s_best) {
@@ -403,7 +423,7 @@ __device__ __forceinline__ void sp_head_item(const SpHead& hp, const SpPub& pub,
   const int Z = hp.Z;
   if (build_xs) {
     float ss = 0.f;
-    for (int m = tid * 8; m < Z; m += kSpThreads * 8) {
+    for (int m = tid * 8; m < Z; m += (W * 32) * 8) {
       const uint4 v = __ldcg(reinterpret_cast<const uint4*>(hp.x + m));
       *reinterpret_cast<uint4*>(xs + m) = v;
       const __half2* h2 = reinterpret_cast<const __half2*>(&v);
@@ -419,11 +439,11 @@ __device__ __forceinline__ void sp_head_item(const SpHead& hp, const SpPub& pub,
       for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
       if (lane == 0) s_part[warp] = ss;
       __syncthreads();
-      float tot = (lane < kSpWarps) ? s_part[lane] : 0.f;
+      float tot = (lane < W) ? s_part[lane] : 0.f;
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
       const float rs = rsqrtf(tot / (float)Z + hp.eps);
-      for (int m = tid * 8; m < Z; m += kSpThreads * 8) {  // each thread renormalises the vectors it staged itself
+      for (int m = tid * 8; m < Z; m += (W * 32) * 8) {  // each thread renormalises the vectors it staged itself
         uint4 v = *reinterpret_cast<uint4*>(xs + m);
         const uint4 gw = ld_nc_u4(reinterpret_cast<const uint4*>(hp.norm_w + m));
         __half2* h2 = reinterpret_cast<__half2*>(&v);
@@ -442,7 +462,7 @@ __device__ __forceinline__ void sp_head_item(const SpHead& hp, const SpPub& pub,
   const int r1 = min(hp.V, r0 + hp.rows_per_item);
   const int nvec = Z >> 3;
   unsigned long long best = 0ull;
-  for (int v = r0 + warp; v < r1; v += kSpWarps) {
+  for (int v = r0 + warp; v < r1; v += W) {
     const uint4* wr = reinterpret_cast<const uint4*>(hp.W + (size_t)v * hp.ldw);
     float acc = 0.f;
     for (int c0 = lane; c0 < nvec; c0 += 32 * UNROLL) {
@@ -483,7 +503,7 @@ __device__ __forceinline__ void sp_head_item(const SpHead& hp, const SpPub& pub,
     if (tid == 0) {
       unsigned long long b = 0ull;
 #pragma unroll
-      for (int w = 0; w < kSpWarps; ++w) b = s_best[w] > b ? s_best[w] : b;
+      for (int w = 0; w < W; ++w) b = s_best[w] > b ? s_best[w] : b;
       if (b) atomicMax(hp.argmax, b);
     }
   }
@@ -491,6 +511,7 @@ __device__ __forceinline__ void sp_head_item(const SpHead& hp, const SpPub& pub,
 }
 
 // ------------------------------------------------------------------------------------------------ embed / advance
+template <int W>
 __device__ __forceinline__ void sp_embed_item(const SpEmbed& e, const SpPub& pub, unsigned epoch, unsigned* flags,
                                               unsigned* done, float* s_part) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -498,7 +519,7 @@ __device__ __forceinline__ void sp_embed_item(const SpEmbed& e, const SpPub& pub
   const uint4* src = reinterpret_cast<const uint4*>(e.emb + (size_t)t * e.dim);
   uint4* dst = reinterpret_cast<uint4*>(e.x);
   float ss = 0.f;
-  for (int i = tid; i < e.dim / 8; i += kSpThreads) {
+  for (int i = tid; i < e.dim / 8; i += (W * 32)) {
     const uint4 v = ld_nc_u4(src + i);
     dst[i] = v;
     const __half2* h2 = reinterpret_cast<const __half2*>(&v);
@@ -515,7 +536,7 @@ __device__ __forceinline__ void sp_embed_item(const SpEmbed& e, const SpPub& pub
   if (tid == 0) {
     float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < kSpWarps; ++w) a += s_part[w];
+    for (int w = 0; w < W; ++w) a += s_part[w];
     e.ssq_out[0] = a;
   }
   sp_publish(pub, 0, epoch, flags, done);
@@ -537,13 +558,24 @@ __device__ __forceinline__ void sp_advance_item(const SpAdvance& v) {
 extern __shared__ __align__(16) unsigned char sp_smem[];
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsigned char* __restrict__ blob) {
+// W: warps per CTA (4: 7 CTAs per SM; 2: 14 CTAs per SM, the launch-per-projection engine's shape for the small
+// projections).  EXT = false is the configuration validated on hardware in round 1 (profiles/r01_step_program_*);
+// EXT = true adds the experimental paths selected at run time by SpHeader::opts / stagger_ns:
+//   opts bit 1  the RMSNorm scale is computed once per (CTA, phase) by warp 0 right after the whole-phase wait instead
+//               of by every warp of every item (the partials are one 64-byte L2 sector read by every warp of every CTA
+//               at the same instant after a barrier)
+//   stagger_ns  a CTA released by a whole-phase wait sleeps hash(blockIdx) in [0, 8) x stagger_ns before it starts, so
+//               that the ~1000 released CTAs do not run their load / reduce phases in lock-step
+template <int W, bool EXT>
+__global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(const unsigned char* __restrict__ blob) {
+  constexpr int kThreadsW = W * 32;
   __shared__ __align__(16) SpPhase s_ph;
   __shared__ int s_ctl[2];
   __shared__ int s_deps[kSpMaxDeps];
   __shared__ int s_last;
-  __shared__ float s_small[kSpWarps];
-  __shared__ unsigned long long s_best[kSpWarps];
+  __shared__ float s_small[W];
+  __shared__ unsigned long long s_best[W];
+  __shared__ float s_rs;
 
   const SpHeader* hdr = reinterpret_cast<const SpHeader*>(blob);
   const SpPhase* phases = reinterpret_cast<const SpPhase*>(blob + sizeof(SpHeader));
@@ -560,6 +592,11 @@ __global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsig
   int dep_ok = -1;  // phase whose whole-phase dependency this CTA has already seen satisfied
   unsigned long long* const dbg = hdr->dbg;
   long long t_ready = 0;
+  // EXT state
+  const bool rs_once = EXT && (hdr->opts & 2) != 0;
+  const unsigned stagger = EXT ? ((blockIdx.x * 0x9E3779B1u) >> 29) * (unsigned)hdr->stagger_ns : 0u;
+  int rs_phase = -1;
+  float rs_value = 1.f;
 
   unsigned next_t = 0;
   if (tid == 0) next_t = atomicAdd(ticket, 1u);
@@ -584,7 +621,7 @@ __global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsig
     if (pi != loaded) {
       const uint4* src = reinterpret_cast<const uint4*>(phases + pi);
       uint4* dst = reinterpret_cast<uint4*>(&s_ph);
-      for (int i = tid; i < (int)(sizeof(SpPhase) / 16); i += kSpThreads) dst[i] = ld_nc_u4(src + i);
+      for (int i = tid; i < (int)(sizeof(SpPhase) / 16); i += kThreadsW) dst[i] = ld_nc_u4(src + i);
       loaded = pi;
       __syncthreads();
     }
@@ -595,7 +632,12 @@ __global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsig
     if (s_ph.dep.kind != kDepNone && !(cache_all && s_ph.dep.kind == kDepAll && dep_ok == pi)) {
       if (tid < 32) {
         if (s_ph.dep.kind == kDepAll) {
-          if (lane == 0) sp_spin_reach(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch, poll_ns);
+          if constexpr (EXT) {
+            if (lane == 0 && sp_spin_reach_ext(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch, poll_ns) && stagger)
+              __nanosleep(stagger);
+          } else {
+            if (lane == 0) sp_spin_reach(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch, poll_ns);
+          }
         } else {
           int n = 0;
           if (lane == 0) n = sp_item_deps(s_ph, item, s_deps);
@@ -611,29 +653,47 @@ __global__ void __launch_bounds__(kSpThreads, 7) step_program_kernel(const unsig
       t_ready = globaltimer_ns();
       atomicMin(dbg + 4 * pi + 1, (unsigned long long)t_ready);
     }
+    if constexpr (EXT) {
+      // RMSNorm scale once per (CTA, phase): warp 0 sums the producer's partials (fixed order), everybody reads one float
+      if (rs_once && s_ph.kind == kPhGemv && s_ph.u.g.in_mode == kInRmsNorm && rs_phase != pi) {
+        if (tid < 32) {
+          float v = 0.f;
+          for (int i = lane; i < s_ph.u.g.n_ssq_in; i += 32) v += __ldcg(s_ph.u.g.ssq_in + i);
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+          if (lane == 0) s_rs = rsqrtf(v / (float)s_ph.u.g.Z + s_ph.u.g.eps);
+        }
+        __syncthreads();
+        rs_value = s_rs;
+        rs_phase = pi;
+      }
+    }
+    const bool rs_known = EXT && rs_once && rs_phase == pi;
 
     switch (s_ph.kind) {
       case kPhGemv:
         if (s_ph.u.g.variant == 1)
-          sp_gemv_item<2, 4>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small, &s_last);
+          sp_gemv_item<2, 4, W, EXT>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small,
+                                     &s_last, rs_known, rs_value);
         else
-          sp_gemv_item<1, 8>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small, &s_last);
+          sp_gemv_item<1, 8, W, EXT>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small,
+                                     &s_last, rs_known, rs_value);
         xs_phase = -1;
         break;
       case kPhAttn:
         if (s_ph.u.a.hd == 128)
-          sp_attn_item<128>(s_ph.u.a, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem));
+          sp_attn_item<128, W>(s_ph.u.a, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem));
         else
-          sp_attn_item<64>(s_ph.u.a, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem));
+          sp_attn_item<64, W>(s_ph.u.a, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem));
         xs_phase = -1;
         break;
       case kPhHead:
-        sp_head_item<8>(s_ph.u.h, s_ph.pub, item, xs_phase != pi, epoch, flags, done, reinterpret_cast<__half*>(sp_smem),
-                        s_small, s_best);
+        sp_head_item<8, W>(s_ph.u.h, s_ph.pub, item, xs_phase != pi, epoch, flags, done, reinterpret_cast<__half*>(sp_smem),
+                           s_small, s_best);
         xs_phase = pi;
         break;
       case kPhEmbed:
-        sp_embed_item(s_ph.u.e, s_ph.pub, epoch, flags, done, s_small);
+        sp_embed_item<W>(s_ph.u.e, s_ph.pub, epoch, flags, done, s_small);
         break;
       case kPhAdvance:
         sp_advance_item(s_ph.u.v);
@@ -667,6 +727,8 @@ struct KindCfg {  // one per projection kind: qkv, o, gate/up, down
   int variant, cols, rows, lpw;
 };
 
+int desc_warps(const teal_step_desc* d) { return d->warps > 0 ? d->warps : kSpWarpsDefault; }
+
 struct Plan {
   KindCfg kind[4];
   StepScratchLayout L;
@@ -674,6 +736,7 @@ struct Plan {
   int total_tiles[4];   // column tiles per call (pair: both matrices)
   int pub_tiles[4];     // publications per call
   size_t smem;
+  int warps;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -687,17 +750,21 @@ int check_desc(const teal_step_desc* d) {
   if ((d->dim & 7) || d->dim > (1 << 20)) return set_error(TEAL_ERR_ALIGNMENT, "step program: dim must be a multiple of 8");
   if (d->n_layer > 0 && !d->layers) return set_error(TEAL_ERR_BAD_ARG, "step program: layers is null");
   if (!d->x || !d->scratch) return set_error(TEAL_ERR_BAD_ARG, "step program: x / scratch is null");
+  if (d->warps != 0 && d->warps != 2 && d->warps != 4) return set_error(TEAL_ERR_UNSUPPORTED, "step program: warps must be 2 or 4");
+  if (d->stagger_ns < 0 || d->stagger_ns > 100000) return set_error(TEAL_ERR_BAD_ARG, "step program: stagger_ns out of range");
   return TEAL_OK;
 }
 
-int make_kind(const teal_step_desc* d, long long elems, KindCfg* k) {
+int make_kind(const teal_step_desc* d, long long elems, int rows_override, KindCfg* k) {
+  const int W = desc_warps(d);
   const long long wide = (long long)(d->wide_melems > 0 ? d->wide_melems : 40) * 1000 * 1000;
   k->variant = elems >= wide ? 1 : 0;
   k->cols = k->variant ? 512 : 256;
   int rows = k->variant ? (d->rows_large > 0 ? d->rows_large : 128) : (d->rows_small > 0 ? d->rows_small : 64);
-  if (rows < kSpWarps || rows % kSpWarps) return set_error(TEAL_ERR_BAD_ARG, "step program: rows per item must be a multiple of 4");
-  k->lpw = rows / kSpWarps < 32 ? rows / kSpWarps : 32;
-  if (rows % (kSpWarps * k->lpw)) return set_error(TEAL_ERR_BAD_ARG, "step program: rows per item above 128 must be a multiple of 128");
+  if (rows_override > 0) rows = rows_override;
+  if (rows < W || rows % W) return set_error(TEAL_ERR_BAD_ARG, "step program: rows per item must be a multiple of the warps per CTA");
+  k->lpw = rows / W < 32 ? rows / W : 32;
+  if (rows % (W * k->lpw)) return set_error(TEAL_ERR_BAD_ARG, "step program: rows per item must be a multiple of 32 x warps once it exceeds it");
   k->rows = rows;
   return TEAL_OK;
 }
@@ -721,7 +788,7 @@ int make_plan(const teal_step_desc* d, Plan* P) {
                               (long long)d->inter * d->dim};
   const int out_cols[4] = {nqkv, d->dim, 2 * d->inter, d->dim};
   for (int k = 0; k < 4; ++k) {
-    if (int rc = make_kind(d, elems[k], &P->kind[k])) return rc;
+    if (int rc = make_kind(d, elems[k], d->rows_kind[k], &P->kind[k])) return rc;
     const int cols = P->kind[k].cols;
     if (k == 2) {
       P->pub_tiles[k] = (d->inter + cols - 1) / cols;
@@ -763,8 +830,10 @@ int make_plan(const teal_step_desc* d, Plan* P) {
   L.total = off;
 
   // dynamic shared memory: max over the phase kinds (GEMV partials, attention staging, normalised x of the lm_head)
-  size_t smem = (size_t)kSpWarps * 512 * 4;
-  const size_t attn = (size_t)(3 * d->head_dim + 2 * kSpWarps + kSpWarps * d->head_dim) * 4;
+  const int W = desc_warps(d);
+  P->warps = W;
+  size_t smem = (size_t)W * 512 * 4;
+  const size_t attn = (size_t)(3 * d->head_dim + 2 * W + W * d->head_dim) * 4;
   smem = attn > smem ? attn : smem;
   if (d->lm_head) smem = (size_t)d->dim * 2 > smem ? (size_t)d->dim * 2 : smem;
   P->smem = align_up(smem, 16);
@@ -1070,6 +1139,9 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
   H->poll_ns = d->poll_ns == 0 ? 32 : (d->poll_ns < 0 ? 0 : d->poll_ns);
   H->opts = d->opts;
   H->dbg = reinterpret_cast<unsigned long long*>(d->debug_times);
+  H->warps = P.warps;
+  H->stagger_ns = d->stagger_ns;
+  H->ext = ((d->opts & ~1) != 0 || d->stagger_ns > 0) ? 1 : 0;
   return TEAL_OK;
 }
 
@@ -1156,25 +1228,32 @@ int teal_step_program_run(const void* host_program, const void* device_program, 
     return set_error(TEAL_ERR_ALIGNMENT, "step program: device program must be 16-byte aligned");
   const DeviceInfo& di = device_info();
   if (di.err != cudaSuccess) return set_cuda_error(di.err, "device query");
-  static int s_smem_set = 0;
-  if (H->smem_bytes > 48 * 1024 && s_smem_set < H->smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(step_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H->smem_bytes);
+  // kernel instantiation: warps per CTA x {validated, experimental paths}
+  using Kern = void (*)(const unsigned char*);
+  static const Kern kKernels[2][2] = {{step_program_kernel<4, false>, step_program_kernel<4, true>},
+                                      {step_program_kernel<2, false>, step_program_kernel<2, true>}};
+  if (H->warps != 4 && H->warps != 2) return set_error(TEAL_ERR_BAD_ARG, "step program: bad warps per CTA in the plan");
+  const int wi = H->warps == 4 ? 0 : 1, ei = H->ext ? 1 : 0;
+  const Kern kern = kKernels[wi][ei];
+  const int threads = H->warps * 32;
+  static int s_smem_set[2][2] = {{0, 0}, {0, 0}};
+  if (H->smem_bytes > 48 * 1024 && s_smem_set[wi][ei] < H->smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H->smem_bytes);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute");
-    s_smem_set = H->smem_bytes;
+    s_smem_set[wi][ei] = H->smem_bytes;
   }
-  static int s_occ = 0, s_occ_smem = -1;
-  if (s_occ_smem != H->smem_bytes) {
+  static int s_occ[2][2] = {{0, 0}, {0, 0}}, s_occ_smem[2][2] = {{-1, -1}, {-1, -1}};
+  if (s_occ_smem[wi][ei] != H->smem_bytes) {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_program_kernel, kSpThreads, (size_t)H->smem_bytes) != cudaSuccess || occ < 1)
-      occ = 1;
-    s_occ = occ;
-    s_occ_smem = H->smem_bytes;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, (size_t)H->smem_bytes) != cudaSuccess || occ < 1) occ = 1;
+    s_occ[wi][ei] = occ;
+    s_occ_smem[wi][ei] = H->smem_bytes;
   }
-  int per_sm = s_occ;
+  int per_sm = s_occ[wi][ei];
   if (H->ctas_per_sm > 0 && H->ctas_per_sm < per_sm) per_sm = H->ctas_per_sm;
   long long grid = (long long)di.sm_count * per_sm;
   if (grid > H->total_items) grid = H->total_items;
-  step_program_kernel<<<dim3((unsigned)grid), dim3(kSpThreads), (size_t)H->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
+  kern<<<dim3((unsigned)grid), dim3(threads), (size_t)H->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const unsigned char*>(device_program));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e, "step_program launch");

@@ -15,8 +15,7 @@
 
 namespace teal {
 
-constexpr int kSpWarps = 4;
-constexpr int kSpThreads = kSpWarps * 32;
+constexpr int kSpWarpsDefault = 4;       // warps per CTA (teal_step_desc::warps: 4 or 2)
 constexpr int kSpMaxDeps = 32;          // completion flags one item may wait on (one polling lane each)
 constexpr unsigned kSpMagic = 0x54454131u;  // "TEA1"
 
@@ -62,7 +61,7 @@ struct SpGemv {
   int Z, mode, in_mode, out_mode, nseg, n_ssq_in;
   int variant;         // 0: 256-column tiles, 8 rows in flight; 1: 512-column tiles, 4 rows in flight
   int rows_per_item;   // K chunk
-  int lpw;             // input lanes per warp per pass (<= 32): rows_per_item = kSpWarps * lpw * passes
+  int lpw;             // input lanes per warp per pass (<= 32): rows_per_item = warps * lpw * passes
   int nkchunks, total_ctiles, target;
   int group;           // order positions per group: items run K-chunk-major inside a group, groups in sequence
   int rot;             // plain mode: order position p -> column tile (p + rot) % total_ctiles (k, v tiles before q)
@@ -138,9 +137,12 @@ struct alignas(16) SpHeader {
   unsigned long long scratch_bytes;
   int ctas_per_sm;    // cap on resident CTAs per SM (0 = occupancy)
   int poll_ns;        // back-off between two polls of a flag
-  int opts;           // bit 0: cache satisfied whole-phase dependencies per CTA
-  int pad;
+  int opts;           // bit 0: cache satisfied whole-phase dependencies per CTA; bit 1: RMSNorm scale once per (CTA, phase)
+  int warps;          // warps per CTA the plan was made for (4 or 2)
   unsigned long long* dbg;  // optional per-phase timestamps [nphases][4] (teal_step_desc::debug_times)
+  int stagger_ns;     // de-synchronise the CTAs released by a whole-phase wait
+  int ext;            // 1: needs the kernel instantiation with the experimental paths
+  int pad[2];
 };
 static_assert(sizeof(SpHeader) % 16 == 0, "phase table must stay 16-byte aligned");
 

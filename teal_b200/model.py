@@ -427,9 +427,7 @@ class SparseDecoder:
         d.argmax_packed, d.out_cap = self.argmax.data_ptr(), self.out_tokens.numel()
         d.x, d.qkv, d.att, d.h, d.logits = (t.data_ptr() for t in (self.x, self.qkv, self.att, self.h, self.logits))
         for k, v in tuning.items():
-            if k not in _prog.TUNING_KEYS:
-                raise TypeError(f"unknown step-program knob {k!r}")
-            setattr(d, k, int(v))  # debug_times: a device address
+            _prog.set_knob(d, k, v)  # debug_times: a device address
         layers = []
         for li, W in enumerate(self.layers):
             t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else None

@@ -20,7 +20,18 @@ PROJ_ORDER = ("q", "k", "v", "o", "gate", "up", "down")
 KIND_NAMES = {0: "embed", 1: "gemv", 2: "attn", 3: "lm_head", 4: "advance"}
 DEP_NONE, DEP_ALL, DEP_LANES, DEP_QKV_HEAD = 0, 1, 2, 3
 TUNING_KEYS = ("rows_small", "rows_large", "group_qkv", "group_gate_up", "head_rows", "wide_melems", "reserved", "poll_ns",
-               "opts", "debug_times")
+               "opts", "debug_times", "warps", "stagger_ns", "rows_qkv", "rows_o", "rows_gate_up", "rows_down")
+ROWS_KIND = {"rows_qkv": 0, "rows_o": 1, "rows_gate_up": 2, "rows_down": 3}
+
+
+def set_knob(desc: StepDesc, key: str, value: int) -> None:
+    """One tuning knob of ``teal_step_desc`` (rows_qkv / rows_o / rows_gate_up / rows_down index rows_kind[])."""
+    if key not in TUNING_KEYS:
+        raise TypeError(f"unknown step-program knob {key!r}")
+    if key in ROWS_KIND:
+        desc.rows_kind[ROWS_KIND[key]] = int(value)
+    else:
+        setattr(desc, key, int(value))
 
 
 def layer_desc(*, wqkv=0, wo=0, w1=0, w3=0, w2=0, attn_norm=0, ffn_norm=0, k_cache=0, v_cache=0, ld_qkv=0, ld_o=0, ld_1=0,

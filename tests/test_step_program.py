@@ -56,9 +56,11 @@ GREEDY = dict(q=0.31, k=0.2, v=0.1, o=0.02, gate=0.4, up=0.35, down=0.01)
 
 def _plan(shape, n_layer, thr=UNIFORM, **kw):
     s = SHAPES[shape]
-    tuning = {k: kw.pop(k) for k in list(kw) if k in ("rows_small", "rows_large", "group_qkv", "group_gate_up", "head_rows",
-                                                       "wide_melems")}
-    d = _fake_desc(**s, **kw, **tuning)
+    from teal_b200.program import TUNING_KEYS, set_knob
+    tuning = {k: kw.pop(k) for k in list(kw) if k in TUNING_KEYS}
+    d = _fake_desc(**s, **kw)
+    for k, v in tuning.items():
+        set_knob(d, k, v)
     layers = [_fake_layer(i, s["dim"], s["n_head"], s["n_kv"], s["hd"], s["inter"], thr) for i in range(n_layer)]
     return StepProgram(d, layers).plan()
 
@@ -119,7 +121,9 @@ def _owner(prog, flag, rng):
 @pytest.mark.parametrize("tuning", [dict(rows_small=32, rows_large=64), dict(rows_small=128, rows_large=256),
                                     dict(group_qkv=1, group_gate_up=2), dict(group_qkv=1000, group_gate_up=1000),
                                     dict(wide_melems=1), dict(wide_melems=100000), dict(head_rows=8),
-                                    dict(group_gate_up=7)])
+                                    dict(group_gate_up=7), dict(warps=2), dict(warps=2, rows_small=64, rows_large=64),
+                                    dict(warps=2, rows_qkv=32, rows_o=64, rows_gate_up=128, rows_down=192),
+                                    dict(warps=4, rows_down=256, stagger_ns=200, opts=3)])
 def test_tuning_knobs_keep_the_invariants(tuning):
     verify_schedule(_plan("tiny", 2, GREEDY, **tuning))
     verify_schedule(_plan("llama-2-7b", 1, UNIFORM, **tuning))
@@ -150,6 +154,12 @@ def test_rejects_bad_descriptions():
     with pytest.raises(AssertionError):
         StepProgram(d, lay)
     d = _fake_desc(**s, rows_small=6)
+    with pytest.raises(AssertionError):
+        StepProgram(d, lay)
+    d = _fake_desc(**s, warps=3)
+    with pytest.raises(_lib.TealLibraryError):
+        StepProgram(d, lay)
+    d = _fake_desc(**s, warps=2, rows_small=96)  # above 32 x warps it must be a multiple of 64
     with pytest.raises(AssertionError):
         StepProgram(d, lay)
     d = _fake_desc(**s)

@@ -1,9 +1,11 @@
 """Step program on the GPU: the one-kernel-per-token data-flow engine against the launch-per-projection
 engine (itself parity-checked against the oracle in test_decoder_gpu.py / test_gemv_gpu.py) and the oracle.
 
-Opt-in (TEAL_PROGRAM_GPU_TESTS=1): the engine was written after round 1's GPU budget was spent, so it has been
-compiled, SASS-checked and schedule-verified on the CPU (tests/test_step_program.py) but not yet run on hardware;
-the default decode path does not use it.
+The default configuration (4 warps per CTA) passed all of these on a B200 in round 1
+(profiles/r01_step_program_gpu_tests.log).  The variants added after the round's GPU budget was spent (2 warps per
+CTA, RMSNorm scale once per CTA and phase, staggered release) are compiled, SASS-checked and schedule-verified on
+the CPU (tests/test_step_program.py) but have not run on hardware yet: their tests are opt-in
+(TEAL_PROGRAM_GPU_TESTS=1) and no default path uses them.
 """
 import os
 
@@ -12,9 +14,9 @@ import torch
 
 from oracle import teal_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TEAL_PROGRAM_GPU_TESTS") != "1",
-                                 reason="step-program engine not yet validated on hardware (set TEAL_PROGRAM_GPU_TESTS=1)")]
+pytestmark = pytest.mark.gpu
+unvalidated = pytest.mark.skipif(os.environ.get("TEAL_PROGRAM_GPU_TESTS") != "1",
+                                 reason="step-program variant not yet run on hardware (set TEAL_PROGRAM_GPU_TESTS=1)")
 
 from test_decoder_gpu import THR, _mk  # noqa: E402  (same tiny model, same oracle)
 
@@ -51,18 +53,25 @@ def test_program_logits_match_oracle_and_graph_engine(mode, thr):
 
 
 def test_program_graph_replay_and_epochs():
-    """64 tokens through the captured one-kernel graph: flags / counters / ticket rewind survive many epochs and the
-    greedy token stream equals the launch-per-projection engine's whenever the logits are not a near tie."""
-    dec, _ = _mk(THR)
-    dec2, _ = _mk(THR)
-    a = dec.generate(5, 48, mode="sparse", engine="program").cpu().tolist()
-    b = dec2.generate(5, 48, mode="sparse", engine="graph").cpu().tolist()
-    same = sum(int(x == y) for x, y in zip(a, b))
-    assert a[0] == b[0]
-    assert same >= 40, (a, b)  # a flipped near-tie diverges the two streams; most prefixes must agree
-    assert dec.kernels_per_step == 1
+    """48 tokens through the captured one-kernel graph: flags / counters / ticket rewind survive many epochs.  The greedy
+    stream is checked against the oracle run teacher-forced on that same stream (run-to-run fp32 RED order makes
+    engine-vs-engine token streams diverge after the first near-tie, see profiles/r01_engine_numerics_check.jsonl)."""
+    dec, orc = _mk(THR)
+    n = 48
+    first = 5
+    a = dec.generate(first, n, mode="sparse", engine="program").cpu().tolist()
+    assert dec.kernels_per_step == 1 and int(dec.pos.item()) == n
     ctl = dec.program_scratch[:12].view(torch.int32).cpu().tolist()
-    assert ctl[0] == 0 and ctl[1] == 0 and ctl[2] >= 48  # ticket rewound, exit counter rewound, epoch advanced
+    assert ctl[0] == 0 and ctl[1] == 0 and ctl[2] >= n  # ticket rewound, exit counter rewound, epoch advanced
+    inputs = [first] + a[:-1]
+    agree = 0
+    with torch.no_grad():
+        for i, t in enumerate(inputs):
+            ref = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
+            agree += int(int(torch.argmax(ref)) == a[i])
+    assert agree >= int(0.75 * n), (agree, a)
+    got = dec.logits.float().cpu().reshape(-1)
+    assert float((got - ref).abs().max()) <= 2 * _tol(ref, "sparse")
 
 
 @pytest.mark.parametrize("tuning", [dict(rows_small=32, rows_large=64), dict(rows_small=128, rows_large=128),
@@ -81,6 +90,14 @@ def test_program_tuning_knobs_do_not_change_results(tuning):
             want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
         got = dec.logits.float().cpu().reshape(-1)
         assert float((got - want).abs().max()) <= _tol(want, "sparse"), (tuning, i)
+
+
+@unvalidated
+@pytest.mark.parametrize("tuning", [dict(warps=2), dict(warps=2, rows_small=32), dict(warps=2, wide_melems=1), dict(opts=2),
+                                    dict(opts=3, stagger_ns=100), dict(warps=2, opts=3, stagger_ns=50),
+                                    dict(rows_qkv=32, rows_o=128, rows_gate_up=64, rows_down=64)])
+def test_unvalidated_variants_do_not_change_results(tuning):
+    test_program_tuning_knobs_do_not_change_results(tuning)
 
 
 def _mlp_case(dim, inter, seed=0):
