@@ -111,6 +111,58 @@ __device__ __forceinline__ void sp_publish(const SpPub& pub, int index, unsigned
   }
 }
 
+__device__ __forceinline__ unsigned long long sp_ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sp_st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Experimental publication (opts bit 2): like sp_publish, but the publication that completes the phase (it sees the
+// cumulative counter reach epoch * count) sums the phase's sum-of-squares partials in the consumers' order, computes
+// the scale of the next RMSNorm and writes {epoch, scale} to kSpBcast replicas, one L2 sector each.  Consumers poll
+// one replica and get "phase complete" and the scale in ONE round trip; nobody hammers a single cell / sector.
+__device__ __forceinline__ void sp_publish_bcast(const SpPub& pub, int index, unsigned epoch, unsigned* flags, unsigned* done,
+                                                 unsigned long long* bcast) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned last = 0;
+    if (lane == 0) {
+      __threadfence();
+      if (pub.flag0 >= 0) sp_st_release(flags + pub.flag0 + index, epoch);
+      const unsigned old = atomicAdd(done + pub.cell, 1u);  // fence + relaxed RMW = release
+      last = (old + 1u == epoch * (unsigned)pub.count) ? 1u : 0u;
+      if (last) __threadfence();  // relaxed RMW + fence = acquire: the other publications' partials are visible
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    __syncwarp();  // memory ordering inside the warp: lane 0's acquire happens-before the other lanes' loads / stores
+    if (last) {
+      float v = 0.f;
+      for (int i = lane; i < pub.n_ssq; i += 32) v += __ldcg(pub.ssq + i);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      const float rs = rsqrtf(v / (float)pub.rs_Z + pub.rs_eps);
+      const unsigned long long word = ((unsigned long long)__float_as_uint(rs) << 32) | (unsigned long long)epoch;
+      sp_st_release_u64(bcast + ((size_t)pub.bcast0 * kSpBcast + lane) * kSpBcastStride, word);
+    }
+  }
+}
+
+template <bool EXT>
+__device__ __forceinline__ void sp_publish_any(const SpPub& pub, int index, unsigned epoch, unsigned* flags, unsigned* done,
+                                               unsigned long long* bcast) {
+  if constexpr (EXT) {
+    if (pub.bcast0 >= 0 && bcast) {
+      sp_publish_bcast(pub, index, epoch, flags, done, bcast);
+      return;
+    }
+  }
+  sp_publish(pub, index, epoch, flags, done);
+}
+
 // ------------------------------------------------------------------------------------------------ GEMV item
 // One (column tile, K chunk) of a projection: [RMSNorm ->] threshold -> ballot compaction -> gather-GEMV ->
 // smem + RED reduction -> arrival counter -> (last arriver) epilogue + publication.  Same arithmetic as
@@ -118,7 +170,7 @@ __device__ __forceinline__ void sp_publish(const SpPub& pub, int index, unsigned
 template <int VEC, int U, int W, bool EXT>
 __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, int item, unsigned epoch, unsigned* flags,
                                              unsigned* done, float* s_red, float* s_ssq, int* s_last, bool rs_known,
-                                             float rs_value) {
+                                             float rs_value, unsigned long long* bcast) {
   constexpr int COLS = 256 * VEC;
   constexpr int kThreadsW = W * 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -288,7 +340,7 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
     }
   }
   if (tid == 0) g.counters[cidx] = 0;
-  sp_publish(pub, cidx, epoch, flags, done);
+  sp_publish_any<EXT>(pub, cidx, epoch, flags, done, bcast);
 }
 
 // ------------------------------------------------------------------------------------------------ attention item
@@ -511,9 +563,9 @@ __device__ __forceinline__ void sp_head_item(const SpHead& hp, const SpPub& pub,
 }
 
 // ------------------------------------------------------------------------------------------------ embed / advance
-template <int W>
+template <int W, bool EXT>
 __device__ __forceinline__ void sp_embed_item(const SpEmbed& e, const SpPub& pub, unsigned epoch, unsigned* flags,
-                                              unsigned* done, float* s_part) {
+                                              unsigned* done, float* s_part, unsigned long long* bcast) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = __ldcg(e.token);
   const uint4* src = reinterpret_cast<const uint4*>(e.emb + (size_t)t * e.dim);
@@ -539,7 +591,7 @@ __device__ __forceinline__ void sp_embed_item(const SpEmbed& e, const SpPub& pub
     for (int w = 0; w < W; ++w) a += s_part[w];
     e.ssq_out[0] = a;
   }
-  sp_publish(pub, 0, epoch, flags, done);
+  sp_publish_any<EXT>(pub, 0, epoch, flags, done, bcast);
 }
 
 // greedy step bookkeeping (generate.py:49-66 with temperature -> 0): token = arg-max, append, ++pos, reset cell
@@ -576,6 +628,7 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
   __shared__ float s_small[W];
   __shared__ unsigned long long s_best[W];
   __shared__ float s_rs;
+  __shared__ int s_rs_valid;
 
   const SpHeader* hdr = reinterpret_cast<const SpHeader*>(blob);
   const SpPhase* phases = reinterpret_cast<const SpPhase*>(blob + sizeof(SpHeader));
@@ -597,9 +650,13 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
   const unsigned stagger = EXT ? ((blockIdx.x * 0x9E3779B1u) >> 29) * (unsigned)hdr->stagger_ns : 0u;
   int rs_phase = -1;
   float rs_value = 1.f;
+  unsigned long long* const bcast = EXT ? hdr->bcast : nullptr;
 
   unsigned next_t = 0;
   if (tid == 0) next_t = atomicAdd(ticket, 1u);
+  if constexpr (EXT) {
+    if (tid == 0) s_rs_valid = 0;
+  }
   int ph_idx = 0;   // thread 0 only: phase cursor (tickets of one CTA only grow)
   int loaded = -1;  // phase currently in s_ph
   int xs_phase = -1;  // lm_head phase whose normalised x sits in shared memory
@@ -633,8 +690,27 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
       if (tid < 32) {
         if (s_ph.dep.kind == kDepAll) {
           if constexpr (EXT) {
-            if (lane == 0 && sp_spin_reach_ext(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch, poll_ns) && stagger)
-              __nanosleep(stagger);
+            if (lane == 0) {
+              bool waited;
+              if (bcast && s_ph.dep.bcast0 >= 0) {  // one replica of the producer's {epoch, RMSNorm scale} word
+                const unsigned long long* cell =
+                    bcast + ((size_t)s_ph.dep.bcast0 * kSpBcast + (blockIdx.x & (kSpBcast - 1))) * kSpBcastStride;
+                unsigned long long v = sp_ld_acquire_u64(cell);
+                waited = (int)((unsigned)v - epoch) < 0;
+                if (waited) {
+                  const long long t0 = clock64();
+                  while ((int)((unsigned)(v = sp_ld_acquire_u64(cell)) - epoch) < 0) {
+                    if (poll_ns) __nanosleep(poll_ns);
+                    if (clock64() - t0 > 4000000000ll) __trap();
+                  }
+                }
+                s_rs = __uint_as_float((unsigned)(v >> 32));
+                s_rs_valid = 1;  // s_rs holds this phase's scale
+              } else {
+                waited = sp_spin_reach_ext(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch, poll_ns);
+              }
+              if (waited && stagger) __nanosleep(stagger);
+            }
           } else {
             if (lane == 0) sp_spin_reach(done + s_ph.dep.cell, epoch * (unsigned)s_ph.dep.per_epoch, poll_ns);
           }
@@ -648,6 +724,12 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
       }
       __syncthreads();
       if (s_ph.dep.kind == kDepAll) dep_ok = pi;
+      if constexpr (EXT) {
+        if (s_rs_valid) {  // scale delivered with the broadcast word (reset below, after everybody has read it)
+          rs_value = s_rs;
+          rs_phase = pi;
+        }
+      }
     }
     if (dbg && tid == 0) {
       t_ready = globaltimer_ns();
@@ -668,16 +750,16 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
         rs_phase = pi;
       }
     }
-    const bool rs_known = EXT && rs_once && rs_phase == pi;
+    const bool rs_known = EXT && rs_phase == pi;
 
     switch (s_ph.kind) {
       case kPhGemv:
         if (s_ph.u.g.variant == 1)
           sp_gemv_item<2, 4, W, EXT>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small,
-                                     &s_last, rs_known, rs_value);
+                                     &s_last, rs_known, rs_value, bcast);
         else
           sp_gemv_item<1, 8, W, EXT>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small,
-                                     &s_last, rs_known, rs_value);
+                                     &s_last, rs_known, rs_value, bcast);
         xs_phase = -1;
         break;
       case kPhAttn:
@@ -693,7 +775,7 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
         xs_phase = pi;
         break;
       case kPhEmbed:
-        sp_embed_item<W>(s_ph.u.e, s_ph.pub, epoch, flags, done, s_small);
+        sp_embed_item<W, EXT>(s_ph.u.e, s_ph.pub, epoch, flags, done, s_small, bcast);
         break;
       case kPhAdvance:
         sp_advance_item(s_ph.u.v);
@@ -702,6 +784,9 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
         break;
     }
     __syncthreads();  // s_ctl / s_ph / dynamic shared memory are reused by the next item
+    if constexpr (EXT) {
+      if (tid == 0) s_rs_valid = 0;  // ordered before the next item's reads by the barrier after the ticket hand-out
+    }
     if (dbg && tid == 0) {
       const long long t_end = globaltimer_ns();
       atomicMax(dbg + 4 * pi + 2, (unsigned long long)t_end);
@@ -827,6 +912,12 @@ int make_plan(const teal_step_desc* d, Plan* P) {
   int max_tiles = 64;
   for (int k = 0; k < 4; ++k) max_tiles = P->total_tiles[k] > max_tiles ? P->total_tiles[k] : max_tiles;
   for (int b = 0; b < 2; ++b) { L.ssq[b] = off; off = align_up(off + (size_t)max_tiles * 4, 64); }
+  L.bcast = 0;
+  if (d->opts & 4) {  // phase-complete broadcast words: one 128-byte line per replica
+    off = align_up(off, 128);
+    L.bcast = off;
+    off += (size_t)nphases * kSpBcast * kSpBcastStride * 8;
+  }
   L.total = off;
 
   // dynamic shared memory: max over the phase kinds (GEMV partials, attention staging, normalised x of the lm_head)
@@ -844,6 +935,7 @@ struct Producer {  // who produced the residual stream the next RMSNorm consumes
   const float* ssq;
   int n_ssq, cell, per_epoch;
   bool valid;
+  int bcast0;  // its broadcast block (opts bit 2) or -1
 };
 
 int fill_seg(SpSeg* s, const void* w, long long ldw, int ncols, int out_col0, double thr, int cols, int* ctile0) {
@@ -894,7 +986,20 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
   const int hd = d->head_dim, adim = d->n_head * hd, kvd = d->n_kv_head * hd, nqkv = adim + 2 * kvd;
 
   int n = 0, item0 = 0, flag0 = 0, toggle = 0;
-  Producer cur = {nullptr, 0, 0, 0, false};
+  Producer cur = {nullptr, 0, 0, 0, false, -1};
+  const bool use_bcast = (d->opts & 4) != 0;
+  // a phase whose completion opens an RMSNorm (or the lm_head): broadcast {epoch, scale of the next norm}
+  auto producer_of_x = [&](SpPhase& p, float* ssq, int n_ssq) {
+    cur = {ssq, n_ssq, n, p.pub.count, true, -1};
+    if (use_bcast) {
+      p.pub.bcast0 = n;
+      p.pub.ssq = ssq;
+      p.pub.n_ssq = n_ssq;
+      p.pub.rs_Z = d->dim;
+      p.pub.rs_eps = (float)d->eps;
+      cur.bcast0 = n;
+    }
+  };
   auto open = [&](int kind, int layer) -> SpPhase& {
     SpPhase& p = ph[n];
     p.kind = kind;
@@ -902,6 +1007,8 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
     p.item0 = item0;
     p.pub.cell = n;
     p.pub.flag0 = -1;
+    p.pub.bcast0 = -1;
+    p.dep.bcast0 = -1;
     return p;
   };
   auto close = [&](SpPhase& p, bool with_flags) {
@@ -921,6 +1028,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
       p.dep.kind = kDepAll;
       p.dep.cell = cur.cell;
       p.dep.per_epoch = cur.per_epoch;
+      p.dep.bcast0 = cur.bcast0;
     } else {  // x preset by the caller
       if (!d->ssq_init) return set_error(TEAL_ERR_BAD_ARG, "step program: ssq_init is required when tok_emb is null");
       g.ssq_in = d->ssq_init;
@@ -940,7 +1048,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
     p.u.e.x = reinterpret_cast<__half*>(d->x);
     p.u.e.ssq_out = ssqb[toggle];
     p.u.e.dim = d->dim;
-    cur = {ssqb[toggle], 1, n, 1, true};
+    producer_of_x(p, ssqb[toggle], 1);
     toggle ^= 1;
     close(p, true);
   }
@@ -1028,7 +1136,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
       o.dep.flag0 = a_flag0;
       o.dep.div = hd;
       if (ko.rows / hd + 2 > kSpMaxDeps) return set_error(TEAL_ERR_UNSUPPORTED, "step program: o-projection K chunk spans too many heads");
-      cur = {ssqb[toggle], ot0, n, ot0, true};
+      producer_of_x(o, ssqb[toggle], ot0);
       toggle ^= 1;
       close(o, true);
     }
@@ -1075,7 +1183,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
       dn.dep.flag0 = g_flag0;
       dn.dep.div = kg.cols;
       if (kd.rows / kg.cols + 2 > kSpMaxDeps) return set_error(TEAL_ERR_UNSUPPORTED, "step program: down-projection K chunk spans too many tiles");
-      cur = {ssqb[toggle], dt0, n, dt0, true};
+      producer_of_x(dn, ssqb[toggle], dt0);
       toggle ^= 1;
       close(dn, true);
     }
@@ -1105,6 +1213,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
       hp.dep.kind = kDepAll;
       hp.dep.cell = cur.cell;
       hp.dep.per_epoch = cur.per_epoch;
+      hp.dep.bcast0 = cur.bcast0;
     }
     const int head_cell = n, head_items = hp.nitems;
     close(hp, false);
@@ -1142,6 +1251,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
   H->warps = P.warps;
   H->stagger_ns = d->stagger_ns;
   H->ext = ((d->opts & ~1) != 0 || d->stagger_ns > 0) ? 1 : 0;
+  H->bcast = use_bcast ? reinterpret_cast<unsigned long long*>(sc + L.bcast) : nullptr;
   return TEAL_OK;
 }
 

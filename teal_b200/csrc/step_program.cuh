@@ -17,7 +17,9 @@ namespace teal {
 
 constexpr int kSpWarpsDefault = 4;       // warps per CTA (teal_step_desc::warps: 4 or 2)
 constexpr int kSpMaxDeps = 32;          // completion flags one item may wait on (one polling lane each)
-constexpr unsigned kSpMagic = 0x54454131u;  // "TEA1"
+constexpr unsigned kSpMagic = 0x54454132u;  // "TEA2"
+constexpr int kSpBcast = 32;            // replicas of a phase-complete broadcast word
+constexpr int kSpBcastStride = 16;      // in 8-byte words: one 128-byte line per replica
 
 enum { kPhEmbed = 0, kPhGemv = 1, kPhAttn = 2, kPhHead = 3, kPhAdvance = 4 };
 enum { kDepNone = 0, kDepAll = 1, kDepLanes = 2, kDepQkvHead = 3 };
@@ -29,7 +31,8 @@ struct SpDep {
   int per_epoch;
   int flag0;       // kDepLanes / kDepQkvHead: first completion flag of the producer phase
   int div;         // kDepLanes: input lanes per producer flag (producer column-tile width, or head_dim)
-  int pad[3];
+  int bcast0;      // kDepAll, experimental: replica block of the producer's "phase complete" broadcast word (-1: none)
+  int pad[2];
 };
 
 // What a finished tile / head / item publishes.
@@ -37,7 +40,12 @@ struct SpPub {
   int flag0;       // flags[flag0 + i] = epoch when publication i of this phase is complete (-1: no flags)
   int cell;        // done[cell] += 1 per publication
   int count;       // publications per epoch
-  int pad;
+  int bcast0;      // experimental: the publication that completes the phase writes {epoch, RMSNorm scale} to
+                   // kSpBcast replicas (one L2 sector each) instead of every consumer polling one cell (-1: off)
+  const float* ssq;  // ... computing the scale of the NEXT RMSNorm from this phase's sum-of-squares partials
+  int n_ssq, rs_Z;
+  float rs_eps;
+  int pad[3];
 };
 
 struct SpSeg {
@@ -142,7 +150,7 @@ struct alignas(16) SpHeader {
   unsigned long long* dbg;  // optional per-phase timestamps [nphases][4] (teal_step_desc::debug_times)
   int stagger_ns;     // de-synchronise the CTAs released by a whole-phase wait
   int ext;            // 1: needs the kernel instantiation with the experimental paths
-  int pad[2];
+  unsigned long long* bcast;  // [nphases][kSpBcast] broadcast words, kSpBcastStride apart (opts bit 2), or null
 };
 static_assert(sizeof(SpHeader) % 16 == 0, "phase table must stay 16-byte aligned");
 
@@ -216,7 +224,7 @@ __host__ __device__ inline int sp_item_deps(const SpPhase& ph, int item, int* ou
 
 // host side (step_program.cu)
 struct StepScratchLayout {
-  size_t control, done, flags, counters[4], acc[4], ssq[2], total;
+  size_t control, done, flags, counters[4], acc[4], ssq[2], bcast, total;
   int nflags, ndone, ncounters[4];
 };
 
