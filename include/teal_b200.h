@@ -211,7 +211,9 @@ typedef struct teal_step_desc {
   int32_t warps;           /* warps per CTA: 4 (default, 7 CTAs per SM) or 2 (14 CTAs per SM) */
   int32_t stagger_ns;      /* CTAs released by a whole-phase wait start hash(cta) in [0,8) x stagger_ns apart (default 0) */
   int32_t rows_kind[4];    /* K chunk per projection kind {qkv, o, gate/up, down}; 0 = rows_small / rows_large */
-  int32_t reserved2[2];
+  int32_t tiles_per_item;  /* experimental: an item sweeps this many column tiles of one K chunk (1..4, default 1): x is
+                            * loaded once and the first rows of the next tile are in flight while a tile is reduced */
+  int32_t reserved2;
 } teal_step_desc;
 
 typedef struct teal_item_info {
@@ -224,6 +226,10 @@ typedef struct teal_item_info {
   int32_t dep_kind, dep_cell, dep_per_epoch; /* 0 none, 1 all publications of a phase, 2/3 flag list */
   int32_t n_deps;
   int32_t deps[32];
+  int32_t n_pubs;                         /* publications this item contributes to (column tiles it sweeps) */
+  int32_t pub_indices[4];
+  int32_t pub_flags[4];
+  int32_t ctiles[4];
 } teal_item_info;
 
 int teal_step_program_sizes(const teal_step_desc* desc, size_t* program_bytes, size_t* scratch_bytes);

@@ -80,14 +80,17 @@ class StepDesc(_c.Structure):
                 ("out_cap", _c.c_int32), ("rows_small", _c.c_int32), ("rows_large", _c.c_int32),
                 ("group_qkv", _c.c_int32), ("group_gate_up", _c.c_int32), ("head_rows", _c.c_int32),
                 ("wide_melems", _c.c_int32), ("reserved", _c.c_int32), ("poll_ns", _c.c_int32), ("opts", _c.c_int32), ("debug_times", _c.c_void_p), ("warps", _c.c_int32),
-                ("stagger_ns", _c.c_int32), ("rows_kind", _c.c_int32 * 4), ("reserved2", _c.c_int32 * 2)]
+                ("stagger_ns", _c.c_int32), ("rows_kind", _c.c_int32 * 4), ("tiles_per_item", _c.c_int32), ("reserved2", _c.c_int32)]
 
 
 class ItemInfo(_c.Structure):
     """``teal_item_info`` of include/teal_b200.h."""
     _fields_ = [(n, _c.c_int32) for n in ("phase", "kind", "layer", "item", "ctile", "kchunk", "k_begin", "k_end",
                                            "pub_index", "pub_flag", "pub_cell", "arrivals", "dep_kind", "dep_cell",
-                                           "dep_per_epoch", "n_deps")] + [("deps", _c.c_int32 * 32)]
+                                           "dep_per_epoch", "n_deps")] + [("deps", _c.c_int32 * 32), ("n_pubs", _c.c_int32),
+                                                                            ("pub_indices", _c.c_int32 * 4),
+                                                                            ("pub_flags", _c.c_int32 * 4),
+                                                                            ("ctiles", _c.c_int32 * 4)]
 
 
 _SIGS.update({

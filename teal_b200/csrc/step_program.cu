@@ -343,6 +343,212 @@ __device__ __forceinline__ void sp_gemv_item(const SpGemv& g, const SpPub& pub, 
   sp_publish_any<EXT>(pub, cidx, epoch, flags, done, bcast);
 }
 
+// ------------------------------------------------------------------------------------------------ multi-tile GEMV item
+// Experimental (teal_step_desc::tiles_per_item > 1): one item sweeps up to kSpMaxTpi column tiles of ONE K chunk.
+// The x lanes are loaded once (one L2 round trip, one dependency check, one ticket for tpi tiles); the first rows of
+// tile t+1 are issued BEFORE tile t is reduced, so the reduction chain (smem -> RED -> fence -> counter -> epilogue)
+// overlaps DRAM latency instead of leaving the CTA's share of HBM idle.  Same arithmetic per tile as sp_gemv_item.
+template <int VEC, int W, bool EXT>
+__device__ __forceinline__ void sp_gemv_tail(const SpGemv& g, const SpPub& pub, int ct, const SpSeg& sg, int col0, int wcols,
+                                             float2 (&acc)[VEC][4], unsigned epoch, unsigned* flags, unsigned* done,
+                                             float* s_red, float* s_ssq, int* s_last, unsigned long long* bcast) {
+  constexpr int COLS = 256 * VEC;
+  constexpr int kThreadsW = W * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float* d = s_red + warp * COLS + lane * 8 + 256 * v;
+    *reinterpret_cast<float4*>(d) = make_float4(acc[v][0].x, acc[v][0].y, acc[v][1].x, acc[v][1].y);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(acc[v][2].x, acc[v][2].y, acc[v][3].x, acc[v][3].y);
+  }
+  __syncthreads();
+  const int acc0 = sg.out_col0 + col0;
+  for (int c = tid * 4; c < wcols; c += kThreadsW * 4) {
+    float4 a = *reinterpret_cast<const float4*>(s_red + c);
+#pragma unroll
+    for (int w = 1; w < W; ++w) {
+      const float4 b = *reinterpret_cast<const float4*>(s_red + w * COLS + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) red_add_v4(g.acc + acc0 + c, a);
+  }
+  __syncthreads();
+  const bool pair = g.mode == kModePairSilu;
+  const int cidx = sp_gemv_cidx(g, ct);
+  if (tid == 0) {
+    fence_acq_rel_gpu();
+    const unsigned old = atomicAdd(g.counters + cidx, 1u);
+    const int last = ((int)old + 1 == g.target) ? 1 : 0;
+    if (last) fence_acq_rel_gpu();
+    *s_last = last;
+  }
+  __syncthreads();
+  if (*s_last) {  // CTA-uniform
+    float ssq = 0.f;
+    if (pair) {
+      const int g0 = g.seg[0].out_col0 + col0, u0 = g.seg[1].out_col0 + col0;
+      for (int c = tid * 4; c < wcols; c += kThreadsW * 4) {
+        const float4 gg = ld_cg_f4(g.acc + g0 + c), uu = ld_cg_f4(g.acc + u0 + c);
+        st_cg_f4(g.acc + g0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        st_cg_f4(g.acc + u0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        const __half2 h0 = __halves2half2(silu_mul_f16(gg.x, uu.x), silu_mul_f16(gg.y, uu.y));
+        const __half2 h1 = __halves2half2(silu_mul_f16(gg.z, uu.z), silu_mul_f16(gg.w, uu.w));
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&h0);
+        o.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(g.y + col0 + c) = o;
+      }
+    } else {
+      for (int c = tid * 4; c < wcols; c += kThreadsW * 4) {
+        const float4 a = ld_cg_f4(g.acc + acc0 + c);
+        st_cg_f4(g.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        if (g.out_mode == kOutAddResidual) {
+          const uint2 r = __ldcg(reinterpret_cast<const uint2*>(g.resid + acc0 + c));
+          h0 = __hadd2(*reinterpret_cast<const __half2*>(&r.x), h0);
+          h1 = __hadd2(*reinterpret_cast<const __half2*>(&r.y), h1);
+        }
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&h0);
+        o.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(g.y + acc0 + c) = o;
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        ssq = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, ssq))));
+      }
+    }
+    if (g.ssq_out) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+      if (lane == 0) s_ssq[warp] = ssq;
+      __syncthreads();
+      if (tid == 0) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) a += s_ssq[w];
+        g.ssq_out[cidx] = a;
+      }
+    }
+    if (tid == 0) g.counters[cidx] = 0;
+    sp_publish_any<EXT>(pub, cidx, epoch, flags, done, bcast);
+  }
+}
+
+__device__ __forceinline__ void sp_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int VEC, int U, int W>
+__device__ __forceinline__ void sp_gemv_item_multi(const SpGemv& g, const SpPub& pub, int item, unsigned epoch, unsigned* flags,
+                                                   unsigned* done, float* s_red, float* s_ssq, int* s_last, bool rs_known,
+                                                   float rs_value, unsigned long long* bcast) {
+  constexpr int COLS = 256 * VEC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int p0, ntiles, kc;
+  sp_gemv_decode_multi(g, item, &p0, &ntiles, &kc);
+  const uint64_t policy = make_evict_first_policy();
+
+  float rs = 1.f;
+  const bool rms = g.in_mode == kInRmsNorm;
+  if (rms) {
+    if (rs_known) {
+      rs = rs_value;
+    } else {
+      float t = 0.f;
+      for (int i = lane; i < g.n_ssq_in; i += 32) t += __ldcg(g.ssq_in + i);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+      rs = rsqrtf(t / (float)g.Z + g.eps);
+    }
+  }
+  // ---- the CTA's K chunk: ONE pass (the planner guarantees rows_per_item == W * lpw for multi-tile items) ----------
+  const int kbeg = kc * g.rows_per_item;
+  const int kend = min(g.Z, kbeg + g.rows_per_item);
+  const int kb = kbeg + warp * g.lpw;
+  const int k = kb + lane;
+  const bool valid = lane < g.lpw && k < kend;
+  float xf = 0.f;
+  if (valid) {
+    const __half xh = sp_ldcg_half(g.x + k);
+    xf = rms ? __half2float(__hmul(__float2half_rn(__half2float(xh) * rs), g.norm_w[k])) : __half2float(xh);
+  }
+
+  // ---- descriptor of the tile at order position p0 -------------------------------------------------------------
+  int ct = sp_gemv_pos_tile(g, p0);
+  int sidx = 0;
+#pragma unroll
+  for (int j = 1; j < 3; ++j) sidx += (j < g.nseg && ct >= g.seg[j].ctile0) ? 1 : 0;
+  int col0 = (ct - g.seg[sidx].ctile0) * COLS;
+  int wcols = min(COLS, g.seg[sidx].ncols - col0);
+  unsigned mask = __ballot_sync(0xffffffffu, valid && !(fabsf(xf) <= g.seg[sidx].thr));
+
+#pragma unroll 1
+  for (int t = 0; t < ntiles; ++t) {
+    const SpSeg& sg = g.seg[sidx];
+    const __half* wbase = sg.w + col0 + lane * 8;
+    const long long ldw = sg.ldw;
+    bool vact[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) vact[v] = lane * 8 + 256 * v < wcols;
+    float2 acc[VEC][4];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[v][c] = make_float2(0.f, 0.f);
+    while (mask) {
+      int bit[U];
+      uint4 wv[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bit[u] = mask ? (__ffs(mask) - 1) : -1;
+        mask &= mask - 1;
+        const __half* src = wbase + (long long)(kb + (bit[u] >= 0 ? bit[u] : 0)) * ldw;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          wv[u][v] = (bit[u] >= 0 && vact[v]) ? sp_ld_stream_u4(src + 256 * v, policy) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (bit[u] >= 0) {
+          const float xs = __shfl_sync(0xffffffffu, xf, bit[u]);
+          const float2 x2 = make_float2(xs, xs);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if (vact[v]) {
+              sp_ffma2(acc[v][0], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].x)), x2);
+              sp_ffma2(acc[v][1], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].y)), x2);
+              sp_ffma2(acc[v][2], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].z)), x2);
+              sp_ffma2(acc[v][3], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].w)), x2);
+            }
+          }
+        }
+      }
+    }
+    // ---- before reducing tile t: start the DRAM reads of tile t+1's first rows (into L2: no registers are tied up
+    // across the reduction, the reduction chain overlaps DRAM latency and HBM keeps working for this CTA) -------------
+    const int ct_cur = ct, col0_cur = col0, wcols_cur = wcols;
+    if (t + 1 < ntiles) {
+      ct = sp_gemv_pos_tile(g, p0 + t + 1);
+      sidx = 0;
+#pragma unroll
+      for (int j = 1; j < 3; ++j) sidx += (j < g.nseg && ct >= g.seg[j].ctile0) ? 1 : 0;
+      const SpSeg& sn = g.seg[sidx];
+      col0 = (ct - sn.ctile0) * COLS;
+      wcols = min(COLS, sn.ncols - col0);
+      mask = __ballot_sync(0xffffffffu, valid && !(fabsf(xf) <= sn.thr));
+      unsigned m = mask;
+      const __half* nbase = sn.w + col0 + lane * 8;
+#pragma unroll 1
+      for (int u = 0; u < 2 * U && m; ++u) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const __half* src = nbase + (long long)(kb + b) * sn.ldw;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if (lane * 8 + 256 * v < wcols) sp_prefetch_l2(src + 256 * v);
+      }
+    }
+    sp_gemv_tail<VEC, W, true>(g, pub, ct_cur, sg, col0_cur, wcols_cur, acc, epoch, flags, done, s_red, s_ssq, s_last, bcast);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ attention item
 // RoPE(q, k) + KV-cache append + attention of the one query over positions [0, pos] for ONE query head
 // (gpt-fast/model.py:170-186).  Same arithmetic as attn_decode_kernel, 4 warps.
@@ -716,7 +922,7 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
           }
         } else {
           int n = 0;
-          if (lane == 0) n = sp_item_deps(s_ph, item, s_deps);
+          if (lane == 0) n = sp_item_deps<EXT>(s_ph, item, s_deps);
           n = __shfl_sync(0xffffffffu, n, 0);  // also orders lane 0's s_deps stores before the other lanes' loads
           __syncwarp();
           if (lane < n) sp_spin_reach(flags + s_deps[lane], epoch, poll_ns);
@@ -754,7 +960,16 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
 
     switch (s_ph.kind) {
       case kPhGemv:
-        if (s_ph.u.g.variant == 1)
+        if (EXT && s_ph.u.g.tpi > 1) {
+          if constexpr (EXT) {
+            if (s_ph.u.g.variant == 1)
+              sp_gemv_item_multi<2, 4, W>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small,
+                                          &s_last, rs_known, rs_value, bcast);
+            else
+              sp_gemv_item_multi<1, 8, W>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small,
+                                          &s_last, rs_known, rs_value, bcast);
+          }
+        } else if (s_ph.u.g.variant == 1)
           sp_gemv_item<2, 4, W, EXT>(s_ph.u.g, s_ph.pub, item, epoch, flags, done, reinterpret_cast<float*>(sp_smem), s_small,
                                      &s_last, rs_known, rs_value, bcast);
         else
@@ -809,7 +1024,7 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? 7 : 14) step_program_kernel(c
 
 // ------------------------------------------------------------------------------------------------ planner (host)
 struct KindCfg {  // one per projection kind: qkv, o, gate/up, down
-  int variant, cols, rows, lpw;
+  int variant, cols, rows, lpw, warps;
 };
 
 int desc_warps(const teal_step_desc* d) { return d->warps > 0 ? d->warps : kSpWarpsDefault; }
@@ -837,6 +1052,7 @@ int check_desc(const teal_step_desc* d) {
   if (!d->x || !d->scratch) return set_error(TEAL_ERR_BAD_ARG, "step program: x / scratch is null");
   if (d->warps != 0 && d->warps != 2 && d->warps != 4) return set_error(TEAL_ERR_UNSUPPORTED, "step program: warps must be 2 or 4");
   if (d->stagger_ns < 0 || d->stagger_ns > 100000) return set_error(TEAL_ERR_BAD_ARG, "step program: stagger_ns out of range");
+  if (d->tiles_per_item < 0 || d->tiles_per_item > kSpMaxTpi) return set_error(TEAL_ERR_BAD_ARG, "step program: tiles_per_item must be 0..4");
   return TEAL_OK;
 }
 
@@ -849,6 +1065,7 @@ int make_kind(const teal_step_desc* d, long long elems, int rows_override, KindC
   if (rows_override > 0) rows = rows_override;
   if (rows < W || rows % W) return set_error(TEAL_ERR_BAD_ARG, "step program: rows per item must be a multiple of the warps per CTA");
   k->lpw = rows / W < 32 ? rows / W : 32;
+  k->warps = W;
   if (rows % (W * k->lpw)) return set_error(TEAL_ERR_BAD_ARG, "step program: rows per item must be a multiple of 32 x warps once it exceeds it");
   k->rows = rows;
   return TEAL_OK;
@@ -952,7 +1169,7 @@ int fill_seg(SpSeg* s, const void* w, long long ldw, int ncols, int out_col0, do
   return TEAL_OK;
 }
 
-void finish_gemv(SpPhase& ph, const KindCfg& kc, int total_ctiles, int group, int rot) {
+void finish_gemv(SpPhase& ph, const KindCfg& kc, int total_ctiles, int group, int rot, int tpi) {
   SpGemv& g = ph.u.g;
   g.variant = kc.variant;
   g.rows_per_item = kc.rows;
@@ -963,9 +1180,18 @@ void finish_gemv(SpPhase& ph, const KindCfg& kc, int total_ctiles, int group, in
   g.target = pair ? 2 * g.nkchunks : g.nkchunks;
   if (group <= 0 || group > total_ctiles) group = total_ctiles;
   if (pair && (group & 1)) group += 1;
+  // multi-tile items: one pass over the K chunk only, whole items per group (pair mode: gate j and up j share an item)
+  if (tpi < 1 || kc.rows != kc.warps * kc.lpw) tpi = 1;  // K chunks that need several passes keep one tile per item
+  if (tpi > kSpMaxTpi) tpi = kSpMaxTpi;
+  if (pair && tpi > 1 && (tpi & 1)) tpi += 1;
+  if (tpi > 1) {
+    group = (group + tpi - 1) / tpi * tpi;
+    if (group > total_ctiles) group = total_ctiles;  // a single (possibly ragged) group
+  }
+  g.tpi = tpi;
   g.group = group;
   g.rot = rot;
-  ph.nitems = total_ctiles * g.nkchunks;
+  ph.nitems = sp_gemv_items(g);
   ph.pub.count = pair ? total_ctiles / 2 : total_ctiles;
 }
 
@@ -1086,7 +1312,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
         rot = g.seg[1].ctile0;
       }
       if (ct0 > L.ncounters[0]) return set_error(TEAL_ERR_UNSUPPORTED, "step program: QKV tile count exceeds the scratch layout");
-      finish_gemv(q, kq, ct0, d->group_qkv > 0 ? d->group_qkv : 4, rot % ct0);
+      finish_gemv(q, kq, ct0, d->group_qkv > 0 ? d->group_qkv : 4, rot % ct0, d->tiles_per_item);
       const int q_flag0 = flag0;
       const SpGemv qg = g;
       close(q, true);
@@ -1131,7 +1357,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
       og.nseg = 1;
       int ot0 = 0;
       if (int rc = fill_seg(&og.seg[0], l.wo, l.ld_o, d->dim, 0, l.thr[3], ko.cols, &ot0)) return rc;
-      finish_gemv(o, ko, ot0, 0, 0);
+      finish_gemv(o, ko, ot0, 0, 0, d->tiles_per_item);
       o.dep.kind = kDepLanes;
       o.dep.flag0 = a_flag0;
       o.dep.div = hd;
@@ -1158,7 +1384,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
       int gt0 = 0;
       if (int rc = fill_seg(&g.seg[0], l.w1, l.ld_1, d->inter, 0, l.thr[4], kg.cols, &gt0)) return rc;
       if (int rc = fill_seg(&g.seg[1], l.w3, l.ld_3, d->inter, d->inter, l.thr[5], kg.cols, &gt0)) return rc;
-      finish_gemv(gu, kg, gt0, d->group_gate_up > 0 ? d->group_gate_up : 8, 0);
+      finish_gemv(gu, kg, gt0, d->group_gate_up > 0 ? d->group_gate_up : 8, 0, d->tiles_per_item);
       const int g_flag0 = flag0;
       close(gu, true);
       // ---- down projection + residual -------------------------------------------------------------------
@@ -1178,7 +1404,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
       dg.nseg = 1;
       int dt0 = 0;
       if (int rc = fill_seg(&dg.seg[0], l.w2, l.ld_2, d->dim, 0, l.thr[6], kd.cols, &dt0)) return rc;
-      finish_gemv(dn, kd, dt0, 0, 0);
+      finish_gemv(dn, kd, dt0, 0, 0, d->tiles_per_item);
       dn.dep.kind = kDepLanes;
       dn.dep.flag0 = g_flag0;
       dn.dep.div = kg.cols;
@@ -1250,7 +1476,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
   H->dbg = reinterpret_cast<unsigned long long*>(d->debug_times);
   H->warps = P.warps;
   H->stagger_ns = d->stagger_ns;
-  H->ext = ((d->opts & ~1) != 0 || d->stagger_ns > 0) ? 1 : 0;
+  H->ext = ((d->opts & ~1) != 0 || d->stagger_ns > 0 || d->tiles_per_item > 1) ? 1 : 0;
   H->bcast = use_bcast ? reinterpret_cast<unsigned long long*>(sc + L.bcast) : nullptr;
   return TEAL_OK;
 }
@@ -1312,22 +1538,42 @@ int teal_step_program_item(const void* host_program, int ticket, teal_item_info*
   out->dep_kind = p.dep.kind;
   out->dep_cell = p.dep.cell;
   out->dep_per_epoch = p.dep.per_epoch;
+  out->n_pubs = 0;
   if (p.kind == kPhGemv) {
-    int ct, kc;
-    sp_gemv_decode(p.u.g, out->item, &ct, &kc);
+    int ct, kc, nt = 1;
+    if (p.u.g.tpi > 1) {
+      int p0;
+      sp_gemv_decode_multi(p.u.g, out->item, &p0, &nt, &kc);
+      for (int t = 0; t < nt; ++t) out->ctiles[t] = sp_gemv_pos_tile(p.u.g, p0 + t);
+      ct = out->ctiles[0];
+    } else {
+      sp_gemv_decode(p.u.g, out->item, &ct, &kc);
+      out->ctiles[0] = ct;
+    }
     out->ctile = ct;
     out->kchunk = kc;
     out->k_begin = kc * p.u.g.rows_per_item;
     out->k_end = out->k_begin + p.u.g.rows_per_item < p.u.g.Z ? out->k_begin + p.u.g.rows_per_item : p.u.g.Z;
     out->pub_index = sp_gemv_cidx(p.u.g, ct);
     out->arrivals = p.u.g.target;
+    out->n_pubs = nt;
+    for (int t = 0; t < nt; ++t) {
+      out->pub_indices[t] = sp_gemv_cidx(p.u.g, out->ctiles[t]);
+      out->pub_flags[t] = p.pub.flag0 >= 0 ? p.pub.flag0 + out->pub_indices[t] : -1;
+    }
   } else if (p.kind == kPhAdvance) {
     out->pub_cell = -1;
   } else {
     out->pub_index = p.kind == kPhEmbed ? 0 : out->item;
   }
   if (p.pub.flag0 >= 0 && out->pub_index >= 0) out->pub_flag = p.pub.flag0 + out->pub_index;
-  out->n_deps = sp_item_deps(p, out->item, out->deps);
+  if (p.kind != kPhGemv && out->pub_index >= 0) {
+    out->n_pubs = 1;
+    out->pub_indices[0] = out->pub_index;
+    out->pub_flags[0] = out->pub_flag;
+    out->ctiles[0] = -1;
+  }
+  out->n_deps = sp_item_deps<true>(p, out->item, out->deps);
   return TEAL_OK;
 }
 

@@ -18,6 +18,7 @@ namespace teal {
 constexpr int kSpWarpsDefault = 4;       // warps per CTA (teal_step_desc::warps: 4 or 2)
 constexpr int kSpMaxDeps = 32;          // completion flags one item may wait on (one polling lane each)
 constexpr unsigned kSpMagic = 0x54454132u;  // "TEA2"
+constexpr int kSpMaxTpi = 4;            // column tiles one item may sweep (same K chunk: x and survivor masks are reused)
 constexpr int kSpBcast = 32;            // replicas of a phase-complete broadcast word
 constexpr int kSpBcastStride = 16;      // in 8-byte words: one 128-byte line per replica
 
@@ -74,7 +75,7 @@ struct SpGemv {
   int group;           // order positions per group: items run K-chunk-major inside a group, groups in sequence
   int rot;             // plain mode: order position p -> column tile (p + rot) % total_ctiles (k, v tiles before q)
   float eps;
-  int pad;
+  int tpi;             // column tiles per item (experimental, <= kSpMaxTpi; 0 / 1 = one tile per item)
   SpSeg seg[3];
 };
 
@@ -182,6 +183,43 @@ __host__ __device__ inline void sp_gemv_decode(const SpGemv& g, int item, int* c
   *kc = k;
 }
 
+// order position -> column tile
+__host__ __device__ inline int sp_gemv_pos_tile(const SpGemv& g, int p) {
+  const int T = g.total_ctiles;
+  if (g.mode == kModePairSilu) return (p & 1) ? (T >> 1) + (p >> 1) : (p >> 1);
+  int c = p + g.rot;
+  if (c >= T) c -= T;
+  return c;
+}
+
+// Multi-tile items (experimental): an item sweeps up to `tpi` consecutive order positions of one group for ONE K chunk
+// (the x lanes are loaded once; the first rows of tile t+1 are on their way from DRAM while tile t is reduced).
+// group % tpi == 0 unless the phase is a single group; the last group may end with a shorter item.
+__host__ __device__ inline void sp_gemv_decode_multi(const SpGemv& g, int item, int* p0, int* ntiles, int* kc) {
+  const int T = g.total_ctiles, nk = g.nkchunks, G = g.group, tpi = g.tpi;
+  const int per_full = (G / tpi) * nk;            // items of a full group
+  const int full_groups = (G % tpi == 0) ? T / G : 0;  // a group that is not whole items is the only group (G == T)
+  int grp = full_groups ? item / per_full : 0;
+  if (grp > full_groups) grp = full_groups;
+  const int r = item - grp * per_full;
+  const int left = T - grp * G;
+  const int gsz = left < G ? left : G;
+  const int ipk = (gsz + tpi - 1) / tpi;          // items per K chunk in this group
+  const int k = r / ipk;
+  const int j = r - k * ipk;
+  *p0 = grp * G + j * tpi;
+  const int rem = gsz - j * tpi;
+  *ntiles = rem < tpi ? rem : tpi;
+  *kc = k;
+}
+__host__ __device__ inline int sp_gemv_items(const SpGemv& g) {
+  if (g.tpi <= 1) return g.total_ctiles * g.nkchunks;
+  const int T = g.total_ctiles, G = g.group, tpi = g.tpi;
+  const int full_groups = (G % tpi == 0) ? T / G : 0;
+  const int tail = T - full_groups * G;
+  return (full_groups * (G / tpi) + (tail + tpi - 1) / tpi) * g.nkchunks;
+}
+
 // publication index of column tile ct (pair mode: gate tile j and up tile j share completion counter j)
 __host__ __device__ inline int sp_gemv_cidx(const SpGemv& g, int ct) {
   return (g.mode == kModePairSilu && ct >= g.seg[1].ctile0) ? ct - g.seg[1].ctile0 : ct;
@@ -196,12 +234,18 @@ __host__ __device__ inline int sp_attn_col_tile(const SpAttn& a, int col) {
 
 // Absolute indices of the completion flags item `item` of phase `ph` must see before it may read its input
 // (kDepLanes / kDepQkvHead).  Returns the count, at most kSpMaxDeps (the planner guarantees the bound).
+template <bool MULTI = false>
 __host__ __device__ inline int sp_item_deps(const SpPhase& ph, int item, int* out) {
   int n = 0;
   if (ph.dep.kind == kDepLanes) {
     const SpGemv& g = ph.u.g;
     int ct, kc;
-    sp_gemv_decode(g, item, &ct, &kc);
+    if (MULTI && g.tpi > 1) {
+      int nt;
+      sp_gemv_decode_multi(g, item, &ct, &nt, &kc);
+    } else {
+      sp_gemv_decode(g, item, &ct, &kc);
+    }
     const int kbeg = kc * g.rows_per_item;
     int kend = kbeg + g.rows_per_item;
     if (kend > g.Z) kend = g.Z;

@@ -20,7 +20,8 @@ PROJ_ORDER = ("q", "k", "v", "o", "gate", "up", "down")
 KIND_NAMES = {0: "embed", 1: "gemv", 2: "attn", 3: "lm_head", 4: "advance"}
 DEP_NONE, DEP_ALL, DEP_LANES, DEP_QKV_HEAD = 0, 1, 2, 3
 TUNING_KEYS = ("rows_small", "rows_large", "group_qkv", "group_gate_up", "head_rows", "wide_melems", "reserved", "poll_ns",
-               "opts", "debug_times", "warps", "stagger_ns", "rows_qkv", "rows_o", "rows_gate_up", "rows_down")
+               "opts", "debug_times", "warps", "stagger_ns", "rows_qkv", "rows_o", "rows_gate_up", "rows_down",
+               "tiles_per_item")
 ROWS_KIND = {"rows_qkv": 0, "rows_o": 1, "rows_gate_up": 2, "rows_down": 3}
 
 
@@ -143,17 +144,19 @@ def verify_schedule(prog: StepProgram) -> Dict[str, object]:
         else:
             assert it.n_deps == 0
         if it.kind == 1:
-            cover.setdefault((it.phase, it.ctile), []).append((it.k_begin, it.k_end))
+            for ct in list(it.ctiles)[: it.n_pubs]:
+                cover.setdefault((it.phase, ct), []).append((it.k_begin, it.k_end))
         if it.pub_cell >= 0:
-            key = (it.phase, it.pub_index)
-            arrivals[key] = arrivals.get(key, 0) + 1
-            need[key] = it.arrivals
-            assert arrivals[key] <= it.arrivals, (t, key)
-            if arrivals[key] == it.arrivals:
-                if it.pub_flag >= 0:
-                    assert it.pub_flag not in flag_owner, (t, it.pub_flag, "flag raised twice")
-                    flag_owner[it.pub_flag] = t
-                cell_done.setdefault(it.pub_cell, []).append(t)
+            for pub_index, pub_flag in zip(list(it.pub_indices)[: it.n_pubs], list(it.pub_flags)[: it.n_pubs]):
+                key = (it.phase, pub_index)
+                arrivals[key] = arrivals.get(key, 0) + 1
+                need[key] = it.arrivals
+                assert arrivals[key] <= it.arrivals, (t, key)
+                if arrivals[key] == it.arrivals:
+                    if pub_flag >= 0:
+                        assert pub_flag not in flag_owner, (t, pub_flag, "flag raised twice")
+                        flag_owner[pub_flag] = t
+                    cell_done.setdefault(it.pub_cell, []).append(t)
     for key, got in arrivals.items():
         assert got == need[key], (key, got, need[key])
     for (phase, ct), spans in cover.items():

@@ -123,7 +123,9 @@ def _owner(prog, flag, rng):
                                     dict(wide_melems=1), dict(wide_melems=100000), dict(head_rows=8),
                                     dict(group_gate_up=7), dict(warps=2), dict(warps=2, rows_small=64, rows_large=64),
                                     dict(warps=2, rows_qkv=32, rows_o=64, rows_gate_up=128, rows_down=192),
-                                    dict(warps=4, rows_down=256, stagger_ns=200, opts=3), dict(opts=4), dict(warps=2, opts=7)])
+                                    dict(warps=4, rows_down=256, stagger_ns=200, opts=3), dict(opts=4), dict(warps=2, opts=7),
+                                    dict(tiles_per_item=2), dict(tiles_per_item=4, warps=2, rows_large=64),
+                                    dict(tiles_per_item=3, group_qkv=5, group_gate_up=6), dict(tiles_per_item=2, wide_melems=1)])
 def test_tuning_knobs_keep_the_invariants(tuning):
     verify_schedule(_plan("tiny", 2, GREEDY, **tuning))
     verify_schedule(_plan("llama-2-7b", 1, UNIFORM, **tuning))

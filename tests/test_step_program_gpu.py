@@ -96,7 +96,9 @@ def test_program_tuning_knobs_do_not_change_results(tuning):
 @pytest.mark.parametrize("tuning", [dict(warps=2), dict(warps=2, rows_small=32), dict(warps=2, wide_melems=1), dict(opts=2),
                                     dict(opts=3, stagger_ns=100), dict(warps=2, opts=3, stagger_ns=50),
                                     dict(rows_qkv=32, rows_o=128, rows_gate_up=64, rows_down=64), dict(opts=4), dict(opts=5),
-                                    dict(warps=2, opts=7, stagger_ns=50)])
+                                    dict(warps=2, opts=7, stagger_ns=50), dict(tiles_per_item=2),
+                                    dict(tiles_per_item=4, warps=2, rows_small=64, rows_large=64),
+                                    dict(tiles_per_item=3, group_qkv=5, group_gate_up=6)])
 def test_unvalidated_variants_do_not_change_results(tuning):
     test_program_tuning_knobs_do_not_change_results(tuning)
 

@@ -26,6 +26,11 @@ SWEEP3 = [dict(warps=2), dict(warps=2, rows_large=64), dict(warps=2, rows_large=
           dict(opts=2, stagger_ns=300), dict(warps=2, rows_qkv=32, rows_o=32), dict(warps=2, rows_gate_up=128, rows_down=128),
           dict(warps=2, opts=3, head_rows=64), dict(warps=2, group_gate_up=4), dict(warps=2, group_gate_up=16),
           dict(warps=2, reserved=12), dict(warps=2, reserved=10)]
+# multi-tile items (x loaded once per K chunk, next tile's first rows prefetched into L2 before the reduction)
+SWEEP4 = [dict(tiles_per_item=2), dict(tiles_per_item=4), dict(tiles_per_item=2, opts=4), dict(tiles_per_item=4, opts=4),
+          dict(tiles_per_item=2, warps=2, rows_small=64, rows_large=64), dict(tiles_per_item=4, warps=2, rows_small=64, rows_large=64),
+          dict(tiles_per_item=4, wide_melems=1), dict(tiles_per_item=2, wide_melems=1, opts=4),
+          dict(tiles_per_item=4, group_gate_up=16, group_qkv=8)]
 SWEEP = [dict(reserved=6), dict(reserved=5), dict(reserved=4), dict(rows_small=128), dict(rows_small=32),
          dict(rows_large=256), dict(rows_large=64), dict(group_gate_up=2), dict(group_gate_up=16), dict(group_gate_up=56),
          dict(group_qkv=1), dict(group_qkv=24), dict(wide_melems=1), dict(wide_melems=1000), dict(head_rows=16),
@@ -39,7 +44,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--sparsity", type=float, default=0.5)
     ap.add_argument("--quick", action="store_true", help="no knob sweep")
-    ap.add_argument("--sweep", type=int, default=1, help="1: structural knobs, 2: polling / caching knobs, 3: 2-warp CTAs / scale-once / stagger")
+    ap.add_argument("--sweep", type=int, default=1, help="1: structural knobs, 2: polling / caching knobs, 3: 2-warp CTAs / scale-once / stagger, 4: multi-tile items")
     ap.add_argument("--check", action="store_true", help="teacher-forced logits of the two engines side by side first")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -100,7 +105,7 @@ def main():
                       "x_absmax": float(a[2].abs().max())})
     base_tok = None
     for mode, engine, tuning in [("sparse", "graph", {}), ("sparse", "program", {}), ("dense_own", "graph", {}),
-                                 ("dense_own", "program", {})] + ([] if args.quick else [("sparse", "program", s) for s in {1: SWEEP, 2: SWEEP2, 3: SWEEP3}[args.sweep]]):
+                                 ("dense_own", "program", {})] + ([] if args.quick else [("sparse", "program", s) for s in {1: SWEEP, 2: SWEEP2, 3: SWEEP3, 4: SWEEP4}[args.sweep]]):
         try:
             ms, toks = timed(mode, engine, **tuning)
             if mode == "sparse" and engine == "graph":
