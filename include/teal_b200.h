@@ -251,9 +251,19 @@ int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out,
 int teal_sparse_gemv_f16_simple(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw,
                                 double threshold, void* stream);
 
-/* Tuning knob for benchmarks: 0 = library default (gather_gemv, cp.async per-warp rings);
- * 1..6 = TMA-bulk-ring variants; 10+T = gather_gemv with T column tiles per matrix. */
+/* Kernel selection for benchmarks and parity tests: 0 = library default (rowchunk_gemv: many small CTAs, variant
+ * chosen by launch size); 30+v = rowchunk variant v (v >= 12: generation 2); 100+v = variant v without wave
+ * balancing; 1..6 = TMA-bulk-ring kernel; 10+T = gather_gemv (cp.async rings) with T column tiles per matrix. */
 int teal_set_config(int config_id);
+
+/* Opt-in experimental knobs of the default dispatch (process-wide, like teal_set_config).
+ *   TEAL_TUNE_GENERATION  1 (default, hardware-validated) | 2 (rowchunk_gemv2_kernel: shared-memory survivor list,
+ *                         rolling load ring, FHFMA; compiled and SASS-checked, not yet run on hardware)
+ *   TEAL_TUNE_SPEC_ROWS   generation 2: rows per warp the first-wave CTAs pull into L2 before their producer is done
+ *                         (0 = off, default)
+ *   TEAL_TUNE_SPEC_MODE   1 = prefetch.global.L2 per 128-byte line (default), 2 = cp.async.bulk.prefetch.L2 per row */
+enum { TEAL_TUNE_GENERATION = 0, TEAL_TUNE_SPEC_ROWS = 1, TEAL_TUNE_SPEC_MODE = 2, TEAL_TUNE_COUNT = 3 };
+int teal_set_tuning(int knob, int value);
 
 /* Launch the GEMV kernels with programmatic dependent launch (prologue overlaps the previous
  * kernel's tail).  Off by default; the decode pipeline switches it on. */

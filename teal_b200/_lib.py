@@ -52,6 +52,7 @@ _SIGS = {
     "teal_sparse_gemv_f16_simple": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                                _c.c_int64, _c.c_double, _c.c_void_p]),
     "teal_set_config": (_c.c_int, [_c.c_int]),
+    "teal_set_tuning": (_c.c_int, [_c.c_int, _c.c_int]),
     "teal_set_pdl": (_c.c_int, [_c.c_int]),
     "teal_set_bytes_probe": (_c.c_int, [_c.c_void_p]),
     "teal_set_debug_timestamps": (_c.c_int, [_c.c_void_p]),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libteal_b200.so")
-SOURCES = ["api.cu", "sparse_gemv.cu", "gather_gemv.cu", "rowchunk_gemv.cu", "decode_kernels.cu", "step_program.cu"]
+SOURCES = ["api.cu", "dispatch.cu", "sparse_gemv.cu", "gather_gemv.cu", "rowchunk_gemv.cu", "decode_kernels.cu", "step_program.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]  # no --use_fast_math: denormals and exact division matter for parity
 

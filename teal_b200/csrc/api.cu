@@ -83,6 +83,7 @@ int teal_workspace_init(void* workspace, size_t workspace_bytes_, void* stream) 
 }
 
 int teal_set_config(int config_id) { return set_config(config_id); }
+int teal_set_tuning(int knob, int value) { return set_tuning(knob, value); }
 int teal_set_bytes_probe(void* device_u64x2) {
   set_bytes_probe(reinterpret_cast<unsigned long long*>(device_u64x2));
   return TEAL_OK;

@@ -16,6 +16,7 @@ constexpr int kMaxThr = 4;                        // distinct thresholds per cal
 constexpr int kMaxStages = 32;
 constexpr int kMaxPieces = 8;
 constexpr int kMaxCounters = 4096;                // column tiles per call
+constexpr int kNumTmaConfigs = 6;                 // tile configurations of the TMA-bulk-ring kernel (config ids 1..6)
 
 enum { kModePlain = 0, kModePairSilu = 1, kModeSurvivors = 2 };
 enum { kInPlain = 0, kInRmsNorm = 1 };        // how x is produced from the input vector
@@ -121,7 +122,13 @@ struct RcParams {
   int n_ssq_in, rows_per_cta, nkchunks, total_ctiles, target;
   float eps;
   RcSeg seg[kMaxSeg];
+  // generation 2 only (appended: the offsets of everything above are those of the hardware-validated build)
+  int lanes_per_warp;  // contiguous input lanes owned by one warp (<= 32 * kRc2MaxPass)
+  int spec_rows;       // speculative L2 prefetch: first rows of every warp's lane range ...
+  int spec_ctas;       // ... issued by CTAs [0, spec_ctas) only (the first wave), before griddepcontrol.wait
+  int spec_mode;       // 1 = prefetch.global.L2 per 128-byte line, 2 = cp.async.bulk.prefetch.L2 per row segment
 };
+constexpr int kRc2MaxPass = 4;  // 32-lane groups one warp of a generation-2 CTA may own
 
 // ---------------------------------------------------------------------------------- host
 struct DeviceInfo {
@@ -144,6 +151,8 @@ void set_pdl(bool on);
 bool pdl_enabled();
 int sub_cols_override();
 bool wave_balance_enabled();
+int set_tuning(int knob, int value);
+int tuning(int knob);
 void set_bytes_probe(unsigned long long* p);
 unsigned long long* bytes_probe();
 int launch_gather_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream,
@@ -168,7 +177,9 @@ int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int*
                    cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------- device
-#ifdef __CUDACC__
+// TEAL_EMU = the CPU emulation build of tests/emu (test infrastructure): the inline-PTX helpers the emulated kernels
+// use have a C++ twin; the nvcc build never sees them.
+#if defined(__CUDACC__) || defined(TEAL_EMU)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -210,9 +221,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 __device__ __forceinline__ uint64_t make_evict_first_policy() {
+#ifdef TEAL_EMU
+  return 0;
+#else
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
+#endif
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
@@ -234,6 +249,18 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+#ifdef TEAL_EMU
+__device__ __forceinline__ void fence_acq_rel_gpu() { __threadfence(); }
+__device__ __forceinline__ long long globaltimer_ns() { return clock64(); }
+__device__ __forceinline__ void griddep_wait() {}
+__device__ __forceinline__ void griddep_launch_dependents() {}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) { return make_float4(__ldcg(p), __ldcg(p + 1), __ldcg(p + 2), __ldcg(p + 3)); }
+__device__ __forceinline__ void st_cg_f4(float* p, float4 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+}
+__device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) { uint4 r; memcpy(&r, p, sizeof r); return r; }
+#else
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ long long globaltimer_ns() {
   long long t;
@@ -273,6 +300,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
                "f"(v.z), "f"(v.w)
                : "memory");
 }
+#endif  // TEAL_EMU
 
 // fp16(silu(fp16(g))) * fp16(u), rounded like the reference's `F.silu(gate) * up` on fp16 tensors
 // (gpt-fast/model.py:259): gate and up are fp16 op outputs, silu rounds to fp16, the product rounds

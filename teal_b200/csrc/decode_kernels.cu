@@ -200,7 +200,11 @@ template <int UNROLL>
 __global__ void __launch_bounds__(kHeadThreads, 2) dense_rowmajor_gemv_kernel(
     const __half* __restrict__ x, const __half* __restrict__ norm_w, float eps, const __half* __restrict__ W,
     __half* __restrict__ y, unsigned long long* __restrict__ argmax_packed, int Z, int V, long long ldw) {
+#ifdef TEAL_EMU
+  unsigned char* smem_raw = ::emu::dyn_smem();
+#else
   extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
   __half* xs = reinterpret_cast<__half*>(smem_raw);  // normalised x, Z halves
   __shared__ float s_part[kHeadThreads / 32];
   __shared__ unsigned long long s_best[kHeadThreads / 32];
@@ -363,6 +367,11 @@ struct TpPeers {
   unsigned* flags[kMaxTpWorld];    // flag array of every rank: flags[r][s] = last epoch published by sender s
 };
 
+#ifdef TEAL_EMU  // CPU emulation build of tests/emu: C++ twins of the inline PTX below
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) { ::emu::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ uint4 ld_volatile_u4(const void* p) { uint4 r; memcpy(&r, p, sizeof r); return r; }
+#else
 __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -376,6 +385,7 @@ __device__ __forceinline__ uint4 ld_volatile_u4(const void* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
   return r;
 }
+#endif
 
 __global__ void __launch_bounds__(1024, 1) tp_allreduce_residual_kernel(const __grid_constant__ TpPeers peers, int rank,
                                                                         int ws, __half* __restrict__ x,

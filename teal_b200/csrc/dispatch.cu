@@ -1,0 +1,81 @@
+// Host-side kernel selection and process-wide knobs of libteal_b200 (no device code): which of the three GEMV
+// designs serves a call, the workspace layout, the benchmark / experiment switches.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace teal {
+
+static int g_forced_config = 0;
+static long long* g_dbg_time = nullptr;
+
+static bool g_pdl = false;
+void set_debug_timestamps(long long* buf) { g_dbg_time = buf; }
+long long* debug_timestamps() { return g_dbg_time; }
+int forced_config() { return g_forced_config; }
+void set_pdl(bool on) { g_pdl = on; }
+bool pdl_enabled() { return g_pdl; }
+static unsigned long long* g_probe = nullptr;
+void set_bytes_probe(unsigned long long* q) { g_probe = q; }
+unsigned long long* bytes_probe() { return g_probe; }
+static bool g_wave_balance = true;
+bool wave_balance_enabled() { return g_wave_balance; }
+static int g_sub_cols = 0;  // config ids k*1000 + id additionally cap the per-warp sub-tile of gather_gemv at k*256 columns
+int sub_cols_override() { return g_sub_cols; }
+static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1};  // generation 1, no speculation, per-line prefetch
+int tuning(int knob) { return (knob >= 0 && knob < TEAL_TUNE_COUNT) ? g_tuning[knob] : 0; }
+int set_tuning(int knob, int value) {
+  if (knob < 0 || knob >= TEAL_TUNE_COUNT) return set_error(TEAL_ERR_BAD_ARG, "tuning knob out of range");
+  if (knob == TEAL_TUNE_GENERATION && value != 1 && value != 2) return set_error(TEAL_ERR_BAD_ARG, "generation must be 1 or 2");
+  if (knob == TEAL_TUNE_SPEC_ROWS && (value < 0 || value > 32)) return set_error(TEAL_ERR_BAD_ARG, "spec_rows must be 0..32");
+  if (knob == TEAL_TUNE_SPEC_MODE && value != 1 && value != 2) return set_error(TEAL_ERR_BAD_ARG, "spec_mode must be 1 or 2");
+  g_tuning[knob] = value;
+  return TEAL_OK;
+}
+
+int set_config(int id) {
+  g_wave_balance = true;
+  if (id >= 100 && id < 200) { g_wave_balance = false; id -= 70; }  // 100 + v: rowchunk variant v without wave balancing
+  g_sub_cols = 0;
+  if (id >= 1000) { g_sub_cols = (id / 1000) * 256; id %= 1000; }  // e.g. 2014: sub-tile 512, 4 tiles
+  if (id < 0 || (id > kNumTmaConfigs && (id < 11 || id > 26) && (id < 30 || id > 49)) || g_sub_cols > 1024)
+    return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
+  g_forced_config = id;
+  return TEAL_OK;
+}
+
+// Config ids: 0 = default = rowchunk_gemv (many small CTAs), 30 + v = rowchunk variant v
+// (bit 0: 512-column tiles, bits 1-2: rows per CTA = 128 << n);
+// 1..6 = the TMA-bulk-ring kernel (sparse_gemv.cu); 10 + T = gather_gemv (cp.async rings) with T tiles per matrix.
+// The two alternative kernels are kept as measured design points; they do not
+// implement the sum-of-squares hand-off, so the fused-RMSNorm entry points always use rowchunk_gemv.
+int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream) {
+  const int id = g_forced_config;
+  const bool needs_rc = p.in_mode != kInPlain || p.ssq_out || p.keep_out || p.mode == kModeSurvivors;
+  if (id >= 1 && id <= kNumTmaConfigs && !needs_rc && p.out_mode == kOutPlain && !p.x_out)
+    return launch_gemv(p, workspace, ws_bytes, out_cols_total, stream);
+  if (id >= 11 && id <= 26 && !needs_rc)
+    return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, id - 10);
+  int variant;
+  if (id >= 30 && id <= 49) {
+    variant = id - 30;
+  } else {  // measured on B200 (profiles/r01_bench_gemv_history.jsonl): wide tiles pay off once a launch moves >= ~40 MB
+    long long elems = 0;
+    for (int s = 0; s < p.nseg; ++s) elems += (long long)p.Z * p.seg[s].ncols;
+    variant = (elems >= 40ll * 1000 * 1000) ? 1 : 2;
+    if (g_tuning[TEAL_TUNE_GENERATION] == 2) variant = (variant == 1) ? 13 : 15;  // opt-in, see rowchunk_gemv2_kernel
+  }
+  return launch_rowchunk(p, workspace, ws_bytes, out_cols_total, stream, variant);
+}
+
+size_t workspace_bytes(int max_out_cols) {
+  size_t acc = ((size_t)max_out_cols * 4 + 255) & ~(size_t)255;
+  return (size_t)kMaxCounters * 4 + acc + (size_t)kSsqParts * 4;  // [counters][acc][ssq scratch]
+}
+float* workspace_ssq_scratch(void* workspace, size_t ws_bytes) {
+  return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + ws_bytes - (size_t)kSsqParts * 4);
+}
+
+}  // namespace teal

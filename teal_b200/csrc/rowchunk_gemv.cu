@@ -37,16 +37,26 @@ namespace {
 
 
 __device__ __forceinline__ void rc_ffma2(float2& acc, const float2 w, const float2 x) {
+#ifdef TEAL_EMU
+  acc.x = fmaf(w.x, x.x, acc.x);
+  acc.y = fmaf(w.y, x.y, acc.y);
+#else
   asm("fma.rn.f32x2 %0, %1, %2, %0;"
       : "+l"(*reinterpret_cast<unsigned long long*>(&acc))
       : "l"(*reinterpret_cast<const unsigned long long*>(&w)), "l"(*reinterpret_cast<const unsigned long long*>(&x)));
+#endif
 }
 // streaming 16-byte load: read-only path, no L1 allocation, L2 evict-first (weights are read once per token)
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p, uint64_t policy) {
   uint4 r;
+#ifdef TEAL_EMU
+  (void)policy;
+  memcpy(&r, p, sizeof r);
+#else
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p), "l"(policy));
+#endif
   return r;
 }
 
@@ -245,6 +255,325 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
   if (tid == 0) p.counters[cidx] = 0;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Generation 2 (opt-in: teal_set_tuning(TEAL_TUNE_GENERATION, 2); compiled and SASS-checked, NOT yet run on
+// hardware -- the default dispatch never selects it).  Same tiling, workspace protocol and epilogue as
+// rowchunk_gemv_kernel, so every parity test applies unchanged; what differs is the per-CTA critical path,
+// which is what a 3-18 us projection is made of:
+//   * survivors are compacted into a per-warp list in SHARED MEMORY (fp16 bits of x | lane offset << 16): the
+//     gather loop is one broadcast LDS + one IMAD.WIDE per row instead of ffs / brev / shfl / 64-bit address
+//     arithmetic per 16-byte load (~75 -> ~25 instructions per row of a 512-column tile);
+//   * the U rows in flight per lane form a ROLLING register ring: row i+U is requested the moment row i has been
+//     consumed, instead of U loads / one full DRAM latency / U consumes;
+//   * FH: fp16 x fp16 + fp32 in one FHFMA (fma.rn.f32.f16, exact product, one rounding: bit-identical to
+//     converting both factors and using FFMA), no conversion instructions;
+//   * x, the RMSNorm weights and the sum-of-squares partials are requested together (one L2 round trip, not
+//     three); the norm weights -- constants -- before griddepcontrol.wait;
+//   * optional speculation (spec_rows > 0): while the CTA waits for its producer (HBM is idle in the producer's
+//     tail), the first-wave CTAs pull the first rows of their lane ranges into L2 without knowing which survive.
+template <int VEC, int WARPS>
+__device__ __forceinline__ void rc2_finish(const RcParams& p, const RcSeg& sg, int ct, int col0, int wcols,
+                                           const float2 (&acc)[VEC][4], float (*s_red)[256 * VEC], float* s_ssq, int* s_last) {
+  constexpr int kThreadsCta = WARPS * 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    float* d = &s_red[warp][lane * 8 + 256 * v];
+    *reinterpret_cast<float4*>(d) = make_float4(acc[v][0].x, acc[v][0].y, acc[v][1].x, acc[v][1].y);
+    *reinterpret_cast<float4*>(d + 4) = make_float4(acc[v][2].x, acc[v][2].y, acc[v][3].x, acc[v][3].y);
+  }
+  __syncthreads();
+  const int acc0 = sg.acc_col0 + col0;
+  for (int c = tid * 4; c < wcols; c += kThreadsCta * 4) {
+    float4 a = *reinterpret_cast<const float4*>(&s_red[0][c]);
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) {
+      const float4 b = *reinterpret_cast<const float4*>(&s_red[w][c]);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) red_add_v4(p.acc + acc0 + c, a);
+  }
+  __syncthreads();  // REDs of all threads happen-before the barrier; thread 0's release fence is cumulative over them
+  const int pair = p.mode == kModePairSilu;
+  const int cidx = pair ? (ct - sg.ctile0) : ct;
+  if (tid == 0) {
+    fence_acq_rel_gpu();
+    const unsigned old = atomicAdd(&p.counters[cidx], 1u);
+    const int last = ((int)old + 1 == p.target) ? 1 : 0;
+    if (last) fence_acq_rel_gpu();
+    *s_last = last;
+  }
+  __syncthreads();
+  if (!*s_last) return;
+
+  float ssq = 0.f;
+  if (pair) {
+    const int g0 = p.seg[0].acc_col0 + col0, u0 = p.seg[1].acc_col0 + col0;
+    for (int c = tid * 4; c < wcols; c += kThreadsCta * 4) {
+      const float4 g = ld_cg_f4(p.acc + g0 + c), u = ld_cg_f4(p.acc + u0 + c);
+      st_cg_f4(p.acc + g0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      st_cg_f4(p.acc + u0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      const __half2 h0 = __halves2half2(silu_mul_f16(g.x, u.x), silu_mul_f16(g.y, u.y));
+      const __half2 h1 = __halves2half2(silu_mul_f16(g.z, u.z), silu_mul_f16(g.w, u.w));
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.y + col0 + c) = o;
+    }
+  } else {
+    const int y0 = sg.y_col0 + col0;
+    for (int c = tid * 4; c < wcols; c += kThreadsCta * 4) {
+      const float4 a = ld_cg_f4(p.acc + acc0 + c);
+      st_cg_f4(p.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      if (p.out_mode == kOutAddResidual) {  // h = x + y in fp16 (gpt-fast/model.py:160-161)
+        const uint2 r = *reinterpret_cast<const uint2*>(p.resid + y0 + c);
+        h0 = __hadd2(*reinterpret_cast<const __half2*>(&r.x), h0);
+        h1 = __hadd2(*reinterpret_cast<const __half2*>(&r.y), h1);
+      }
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.y + y0 + c) = o;
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      ssq = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, ssq))));
+    }
+  }
+  if (p.ssq_out) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+    if (lane == 0) s_ssq[warp] = ssq;
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) a += s_ssq[w];
+      p.ssq_out[cidx] = a;
+      for (int sidx = cidx + p.total_ctiles; sidx < kSsqParts; sidx += p.total_ctiles) p.ssq_out[sidx] = 0.f;
+    }
+  }
+  if (tid == 0) p.counters[cidx] = 0;
+}
+
+namespace {
+// f32 += f16 * f16 (FHFMA): the product of two fp16 values is exact in fp32, so this is fma(float(w), float(x), acc)
+__device__ __forceinline__ void rc_fhfma2(float2& acc, uint32_t w2, unsigned short xh) {
+#ifdef TEAL_EMU
+  const float x = __half2float(__ushort_as_half(xh));
+  acc.x = fmaf(__half2float(__ushort_as_half((unsigned short)(w2 & 0xffffu))), x, acc.x);
+  acc.y = fmaf(__half2float(__ushort_as_half((unsigned short)(w2 >> 16))), x, acc.y);
+#else
+  asm("{\n"
+      ".reg .b16 lo, hi;\n"
+      "mov.b32 {lo, hi}, %2;\n"
+      "fma.rn.f32.f16 %0, lo, %3, %0;\n"
+      "fma.rn.f32.f16 %1, hi, %3, %1;\n"
+      "}\n"
+      : "+f"(acc.x), "+f"(acc.y)
+      : "r"(w2), "h"(xh));
+#endif
+}
+#ifdef TEAL_EMU
+// the emulation touches every byte a prefetch names, so an out-of-range speculative address is caught by ASan / a fault
+__device__ __forceinline__ void rc_prefetch_l2(const void* p) { (void)*reinterpret_cast<const volatile char*>(p); }
+__device__ __forceinline__ void rc_bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  for (uint32_t i = 0; i < bytes; i += 16) (void)*(reinterpret_cast<const volatile char*>(p) + i);
+}
+__device__ __forceinline__ __half rc_ldcg_half(const __half* p) { return __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(p))); }
+__device__ __forceinline__ uint32_t rc_lds_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, uint32_t row_bytes) { return base + (uint64_t)row * row_bytes; }
+#else
+__device__ __forceinline__ void rc_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void rc_bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ __half rc_ldcg_half(const __half* p) {
+  unsigned short v;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+  return __ushort_as_half(v);
+}
+// volatile asm on purpose: the compiler must neither duplicate the address arithmetic per 16-byte load nor move the
+// list read across the weight loads
+__device__ __forceinline__ uint32_t rc_lds_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, uint32_t row_bytes) {
+  uint64_t a;
+  asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(row), "r"(row_bytes), "l"(base));
+  return a;
+}
+#endif
+}  // namespace
+
+// The gather loop of generation 2.  `list` (shared-space address) holds n entries {fp16 bits of x | lane offset << 16};
+// row i+U is requested as soon as row i has been consumed (ring slot i % U, statically indexed by the unrolled u).
+template <int VEC, int U, bool FH, bool FULL>
+__device__ __forceinline__ void rc2_gather(float2 (&acc)[VEC][4], const uint32_t* list, int n, uint64_t wrow, uint32_t ldwb,
+                                           uint64_t policy, const bool (&vact)[VEC]) {
+  uint4 buf[U][VEC];
+  uint32_t ent[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    ent[u] = 0u;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) buf[u][v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+#define RC2_ISSUE(u, i)                                                                                          \
+  {                                                                                                              \
+    ent[u] = rc_lds_u32(list + (i));                                                                             \
+    const uint64_t src = rc_row_address(wrow, ent[u] >> 16, ldwb);                                               \
+    _Pragma("unroll") for (int v = 0; v < VEC; ++v) if (FULL || vact[v])                                         \
+        buf[u][v] = ld_stream_u4(reinterpret_cast<const char*>(src) + 512 * v, policy);                          \
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < n) RC2_ISSUE(u, u)
+  for (int base = 0; base < n; base += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u;
+      if (i < n) {  // warp-uniform
+        const unsigned short xb = (unsigned short)(ent[u] & 0xffffu);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          if (FH) {
+            rc_fhfma2(acc[v][0], buf[u][v].x, xb);
+            rc_fhfma2(acc[v][1], buf[u][v].y, xb);
+            rc_fhfma2(acc[v][2], buf[u][v].z, xb);
+            rc_fhfma2(acc[v][3], buf[u][v].w, xb);
+          } else {
+            const float xs = __half2float(__ushort_as_half(xb));
+            const float2 x2 = make_float2(xs, xs);
+            rc_ffma2(acc[v][0], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].x)), x2);
+            rc_ffma2(acc[v][1], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].y)), x2);
+            rc_ffma2(acc[v][2], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].z)), x2);
+            rc_ffma2(acc[v][3], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].w)), x2);
+          }
+        }
+        if (i + U < n) RC2_ISSUE(u, i + U)
+      }
+    }
+  }
+#undef RC2_ISSUE
+}
+
+template <int VEC, int U, int WARPS, bool FH>
+__global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv2_kernel(const __grid_constant__ RcParams p) {
+  constexpr int COLS = 256 * VEC;
+  constexpr int kCap = kRc2MaxPass * 32;
+  __shared__ __align__(16) float s_red[WARPS][COLS];
+  __shared__ uint32_t s_list[WARPS][kCap];  // the warp's compacted survivors: fp16 bits of x | (lane offset << 16)
+  __shared__ float s_ssq[WARPS];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ct = (int)(blockIdx.x % (unsigned)p.total_ctiles);
+  const int kc = (int)(blockIdx.x / (unsigned)p.total_ctiles);
+  int s = 0;
+#pragma unroll
+  for (int j = 1; j < kMaxSeg; ++j) s += (j < p.nseg && ct >= p.seg[j].ctile0) ? 1 : 0;
+  const RcSeg& sg = p.seg[s];
+  const int col0 = (ct - sg.ctile0) * COLS;
+  const int wcols = min(COLS, sg.ncols - col0);
+  const float thr = sg.thr;
+  bool vact[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) vact[v] = lane * 8 + 256 * v < wcols;
+  const uint32_t ldwb = (uint32_t)sg.ldw * 2u;  // bytes per weight row (the launcher checks that it fits)
+  const uint64_t policy = make_evict_first_policy();
+
+  // ---- the warp's contiguous lane range [kb, ke) of the CTA's K chunk --------------------------------------
+  const int kbeg = kc * p.rows_per_cta;
+  const int kend = min(p.Z, kbeg + p.rows_per_cta);
+  const int kb = min(kend, kbeg + warp * p.lanes_per_warp);
+  const int ke = min(kend, kb + p.lanes_per_warp);
+  const char* wrow0 = reinterpret_cast<const char*>(sg.w + col0 + lane * 8) + (uint64_t)(uint32_t)kb * ldwb;
+  const bool rms = p.in_mode == kInRmsNorm;
+
+  // ---- before the producer is done: constants, and (first wave only) speculative rows into L2 ---------------
+  __half nw[kRc2MaxPass];
+#pragma unroll
+  for (int q = 0; q < kRc2MaxPass; ++q) {
+    const int k = kb + q * 32 + lane;
+    nw[q] = (rms && k < ke) ? p.norm_w[k] : __ushort_as_half((unsigned short)0);
+  }
+  if (p.spec_rows > 0 && (int)blockIdx.x < p.spec_ctas && p.mode != kModeSurvivors) {
+    const int nrows = min(p.spec_rows, ke - kb);
+    if (p.spec_mode == 2) {  // one bulk prefetch per row segment, lane r takes row r
+      if (lane < nrows)
+        rc_bulk_prefetch_l2(reinterpret_cast<const char*>(sg.w + col0) + (uint64_t)(uint32_t)(kb + lane) * ldwb, (uint32_t)wcols * 2u);
+    } else {                 // one prefetch per 128-byte line: a warp-wide instruction covers 32 / LPR rows
+      constexpr int LPR = COLS / 64;
+      const int line = lane % LPR;
+      if (line * 64 < wcols)
+        for (int r = lane / LPR; r < nrows; r += 32 / LPR)
+          rc_prefetch_l2(reinterpret_cast<const char*>(sg.w + col0 + line * 64) + (uint64_t)(uint32_t)(kb + r) * ldwb);
+    }
+  }
+
+  griddep_wait();
+  griddep_launch_dependents();
+
+  // ---- x lanes and the producer's sum-of-squares partials: all requests in flight together (L2) -------------
+  __half xh[kRc2MaxPass];
+#pragma unroll
+  for (int q = 0; q < kRc2MaxPass; ++q) {
+    const int k = kb + q * 32 + lane;
+    xh[q] = (k < ke) ? rc_ldcg_half(p.x + k) : __ushort_as_half((unsigned short)0);
+  }
+  float rs = 1.f;
+  if (rms) {
+    float t = 0.f;
+    for (int i = lane; i < p.n_ssq_in; i += 32) t += __ldcg(p.ssq_in + i);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    rs = rsqrtf(t / (float)p.Z + p.eps);
+  }
+
+  // ---- threshold + compaction into the warp's shared-memory list --------------------------------------------
+  int n = 0;
+#pragma unroll
+  for (int q = 0; q < kRc2MaxPass; ++q) {
+    const int k = kb + q * 32 + lane;
+    if (kb + q * 32 < ke) {  // warp-uniform
+      __half xv = xh[q];
+      if (rms) {  // fp32 norm, cast to fp16, multiply by the fp16 weight in fp16 (gpt-fast/model.py:286-291)
+        xv = __hmul(__float2half_rn(__half2float(xv) * rs), nw[q]);
+        if (p.x_out && ct == 0 && k < ke) p.x_out[k] = xv;
+      }
+      const bool keep = (k < ke) && !(fabsf(__half2float(xv)) <= thr);  // strict >, NaN kept
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (p.keep_out && ct == 0 && k < ke) p.keep_out[k] = keep ? 1 : 0;
+      if (keep) s_list[warp][n + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)__half_as_ushort(xv) | ((uint32_t)(q * 32 + lane) << 16);
+      n += __popc(mask);
+    }
+  }
+  __syncwarp();
+  const int my_nnz = n;
+  if (p.mode == kModeSurvivors) n = 0;  // parity hook: thresholds only, no weights
+
+  // ---- gather: U rows in flight per lane, a rolling ring of registers ---------------------------------------
+  float2 acc[VEC][4];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[v][c] = make_float2(0.f, 0.f);
+  const uint32_t* list = &s_list[warp][0];
+  const uint64_t wrow = reinterpret_cast<uint64_t>(wrow0);
+  if (wcols == COLS)  // CTA-uniform: a full tile needs no per-lane column predicates
+    rc2_gather<VEC, U, FH, true>(acc, list, n, wrow, ldwb, policy, vact);
+  else
+    rc2_gather<VEC, U, FH, false>(acc, list, n, wrow, ldwb, policy, vact);
+  if (p.probe && lane == 0) {  // measurement probe: gathered vs dense weight bytes
+    atomicAdd(p.probe, (unsigned long long)my_nnz * (unsigned long long)wcols * 2ull);
+    if (warp == 0) atomicAdd(p.probe + 1, (unsigned long long)max(0, kend - kbeg) * (unsigned long long)wcols * 2ull);
+  }
+  if (p.mode == kModeSurvivors) return;
+  rc2_finish<VEC, WARPS>(p, sg, ct, col0, wcols, acc, s_red, s_ssq, &s_last);
+}
+
 // Sum-of-squares partials of a vector that did not come out of a GEMV finaliser (embedding row, tests).
 __global__ void ssq_kernel(const __half* __restrict__ x, int Z, float* __restrict__ ssq_out, int nparts) {
   griddep_wait();
@@ -320,8 +649,9 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (gp.ssq_out && gp.mode == kModePairSilu) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out is not defined for the gate/up pair");
   if (gp.out_mode == kOutAddResidual && (!gp.resid || (reinterpret_cast<uintptr_t>(gp.resid) & 7)))
     return set_error(TEAL_ERR_ALIGNMENT, "residual must be non-null and 8-byte aligned");
-  struct Variant { int vec, u, warps, rows; void (*kern)(const RcParams); };
-#define TEAL_RC(V, UU, W, R) {V, UU, W, R, rowchunk_gemv_kernel<V, UU, W>}
+  struct Variant { int vec, u, warps, rows, gen; void (*kern)(const RcParams); };
+#define TEAL_RC(V, UU, W, R) {V, UU, W, R, 1, rowchunk_gemv_kernel<V, UU, W>}
+#define TEAL_RC2(V, UU, W, R, FH) {V, UU, W, R, 2, rowchunk_gemv2_kernel<V, UU, W, FH>}
   static const Variant kVariants[] = {
       TEAL_RC(1, 8, 4, 128),   // 0
       TEAL_RC(2, 4, 4, 128),   // 1
@@ -335,8 +665,18 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       TEAL_RC(2, 8, 1, 32),    // 9
       TEAL_RC(1, 8, 4, 256),   // 10
       TEAL_RC(1, 16, 1, 32),   // 11
+      // generation 2 (compacted list in shared memory, rolling register ring; not yet run on hardware)
+      TEAL_RC2(2, 4, 4, 128, false),  // 12: the shape of variant 1, FFMA2 arithmetic
+      TEAL_RC2(2, 4, 4, 128, true),   // 13: ... FHFMA arithmetic (generation-2 default for >= 40 M-element launches)
+      TEAL_RC2(1, 8, 2, 64, false),   // 14: the shape of variant 2
+      TEAL_RC2(1, 8, 2, 64, true),    // 15: (generation-2 default for the small projections)
+      TEAL_RC2(2, 4, 4, 256, true),   // 16: two 32-lane groups per warp (half as many REDs / arrivals)
+      TEAL_RC2(1, 8, 4, 128, true),   // 17
+      TEAL_RC2(2, 6, 4, 128, true),   // 18: 6 KB in flight per warp
+      TEAL_RC2(1, 8, 2, 128, true),   // 19
   };
 #undef TEAL_RC
+#undef TEAL_RC2
   constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
   if (variant < 0 || variant >= kNumVariants) variant = 0;
   const Variant& var = kVariants[variant];
@@ -386,6 +726,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       if (nk < 1) continue;
       int r = (int)((gp.Z + nk - 1) / nk);
       if (r < 32 * var.warps) r = 32 * var.warps;
+      if (var.gen == 2 && r > 32 * kRc2MaxPass * var.warps) continue;  // a generation-2 warp owns <= kRc2MaxPass lane groups
       const long long cost = (r > rows) ? (r - rows) : 2ll * (rows - r);  // prefer the nominal chunk, lean towards larger
       if (cost < best_cost) { best_cost = cost; best_rows = r; }
     }
@@ -393,6 +734,19 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   }
   p.rows_per_cta = rows;
   p.nkchunks = (gp.Z + rows - 1) / rows;
+  if (var.gen == 2) {
+    if (rows > 32 * kRc2MaxPass * var.warps) return set_error(TEAL_ERR_UNSUPPORTED, "rowchunk generation 2: K chunk too long");
+    for (int s = 0; s < p.nseg && gp.mode != kModeSurvivors; ++s)
+      if (p.seg[s].ldw <= 0 || p.seg[s].ldw >= (1ll << 30)) return set_error(TEAL_ERR_UNSUPPORTED, "rowchunk generation 2: ldw out of range");
+    p.lanes_per_warp = (rows + var.warps - 1) / var.warps;
+    p.spec_rows = tuning(TEAL_TUNE_SPEC_ROWS);
+    p.spec_mode = tuning(TEAL_TUNE_SPEC_MODE);
+    if (p.spec_rows > 0) {  // only the CTAs that start while the producer drains (the first wave) speculate
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.kern, var.warps * 32, 0) != cudaSuccess || occ < 1) occ = 1;
+      p.spec_ctas = device_info().sm_count * occ;
+    }
+  }
   p.target = pair ? 2 * p.nkchunks : p.nkchunks;
   const long long grid = (long long)p.total_ctiles * p.nkchunks;
   if (grid > 0x7fffffffll) return set_error(TEAL_ERR_UNSUPPORTED, "grid too large");
@@ -430,8 +784,11 @@ int launch_ssq(const __half* x, int Z, float* ssq_out, int nparts, cudaStream_t 
 }
 
 int launch_mask_to_indices(const unsigned char* keep, int Z, int* idx, int* cnt, cudaStream_t stream) {
-  mask_to_indices_kernel<<<1, 1024, 0, stream>>>(keep, Z, idx, cnt);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mask_to_indices_kernel, keep, Z, idx, cnt);
   if (e != cudaSuccess) return set_cuda_error(e, "mask_to_indices launch");
   return TEAL_OK;
 }

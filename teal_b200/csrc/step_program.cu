@@ -46,6 +46,16 @@ namespace teal {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ device helpers
+#ifdef TEAL_EMU  // CPU emulation build of tests/emu: C++ twins of the inline PTX below (acquire loads yield the fiber)
+__device__ __forceinline__ void sp_ffma2(float2& acc, const float2 w, const float2 x) {
+  acc.x = fmaf(w.x, x.x, acc.x);
+  acc.y = fmaf(w.y, x.y, acc.y);
+}
+__device__ __forceinline__ uint4 sp_ld_stream_u4(const void* p, uint64_t) { uint4 r; memcpy(&r, p, sizeof r); return r; }
+__device__ __forceinline__ unsigned sp_ld_acquire(const unsigned* p) { ::emu::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void sp_st_release(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ void sp_red_release_inc(unsigned* p) { __atomic_fetch_add(p, 1u, __ATOMIC_RELEASE); }
+#else
 __device__ __forceinline__ void sp_ffma2(float2& acc, const float2 w, const float2 x) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;"
       : "+l"(*reinterpret_cast<unsigned long long*>(&acc))
@@ -69,6 +79,7 @@ __device__ __forceinline__ void sp_st_release(unsigned* p, unsigned v) {
 __device__ __forceinline__ void sp_red_release_inc(unsigned* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
+#endif
 // fp16 written by another CTA of this launch: read at L2
 __device__ __forceinline__ __half sp_ldcg_half(const __half* p) {
   return __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(p)));
@@ -111,6 +122,10 @@ __device__ __forceinline__ void sp_publish(const SpPub& pub, int index, unsigned
   }
 }
 
+#ifdef TEAL_EMU
+__device__ __forceinline__ unsigned long long sp_ld_acquire_u64(const unsigned long long* p) { ::emu::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void sp_st_release_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
 __device__ __forceinline__ unsigned long long sp_ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -119,6 +134,7 @@ __device__ __forceinline__ unsigned long long sp_ld_acquire_u64(const unsigned l
 __device__ __forceinline__ void sp_st_release_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 
 // Experimental publication (opts bit 2): like sp_publish, but the publication that completes the phase (it sees the
 // cumulative counter reach epoch * count) sums the phase's sum-of-squares partials in the consumers' order, computes
@@ -433,7 +449,11 @@ __device__ __forceinline__ void sp_gemv_tail(const SpGemv& g, const SpPub& pub, 
   }
 }
 
+#ifdef TEAL_EMU
+__device__ __forceinline__ void sp_prefetch_l2(const void* p) { (void)*reinterpret_cast<const volatile char*>(p); }
+#else
 __device__ __forceinline__ void sp_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 
 template <int VEC, int U, int W>
 __device__ __forceinline__ void sp_gemv_item_multi(const SpGemv& g, const SpPub& pub, int item, unsigned epoch, unsigned* flags,
@@ -813,7 +833,11 @@ __device__ __forceinline__ void sp_advance_item(const SpAdvance& v) {
   }
 }
 
+#ifdef TEAL_EMU
+#define sp_smem (::emu::dyn_smem())
+#else
 extern __shared__ __align__(16) unsigned char sp_smem[];
+#endif
 
 // ------------------------------------------------------------------------------------------------ the kernel
 // W: warps per CTA (4: 7 CTAs per SM; 2: 14 CTAs per SM, the launch-per-projection engine's shape for the small
@@ -1609,9 +1633,12 @@ int teal_step_program_run(const void* host_program, const void* device_program, 
   if (H->ctas_per_sm > 0 && H->ctas_per_sm < per_sm) per_sm = H->ctas_per_sm;
   long long grid = (long long)di.sm_count * per_sm;
   if (grid > H->total_items) grid = H->total_items;
-  kern<<<dim3((unsigned)grid), dim3(threads), (size_t)H->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const unsigned char*>(device_program));
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = (size_t)H->smem_bytes;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const unsigned char*>(device_program));
   if (e != cudaSuccess) return set_cuda_error(e, "step_program launch");
   return TEAL_OK;
 }

@@ -274,3 +274,15 @@ class SparseQKVGEMV(BaseKernel):
 def set_config(config_id: int) -> None:
     """Benchmark knob: force a tile configuration (0 = default heuristic)."""
     _lib.check(_lib.load().teal_set_config(int(config_id)), "teal_set_config")
+
+
+TUNING_KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2}  # TEAL_TUNE_* of include/teal_b200.h
+TUNING_DEFAULTS = {"generation": 1, "spec_rows": 0, "spec_mode": 1}
+
+
+def set_tuning(**knobs: int) -> None:
+    """Opt-in experimental knobs of the default dispatch (``teal_set_tuning``), e.g. ``set_tuning(generation=2,
+    spec_rows=4)``; ``set_tuning()`` restores the defaults (generation 1: the hardware-validated kernel)."""
+    lib = _lib.load()
+    for name, value in (knobs or TUNING_DEFAULTS).items():
+        _lib.check(lib.teal_set_tuning(TUNING_KNOBS[name], int(value)), f"teal_set_tuning({name})")

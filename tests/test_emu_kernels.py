@@ -1,0 +1,203 @@
+"""The CUDA kernels' LOGIC on the CPU: the production .cu sources compiled as C++ against tests/emu/cuda_emu.h (fibers
+for threads, real atomics, warp collectives through per-warp slots) and driven through the same C ABI, checked against
+the oracle.  This is how kernels that have not run on a B200 yet (generation-2 row-chunk kernel, experimental
+step-program paths) are exercised in the CPU suite; the hardware-validated kernels run through the same emulation
+first, which validates the emulator itself.  It proves indexing / masks / pipelines / protocols, not the memory model
+and not speed.  The -m gpu tests remain the parity tests proper."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import teal_oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import harness as H  # noqa: E402
+
+V1_CFGS = [30, 31, 32, 33, 35, 38, 40]      # hardware-validated row-chunk variants (emulator self-check)
+GEN2_CFGS = [42, 43, 44, 45, 46, 47, 48, 49]
+
+
+@pytest.fixture(autouse=True)
+def _defaults():
+    H.lib()
+    H.set_config(0)
+    H.set_tuning()
+    H.lib().teal_emu_set_sm_count(4)
+    H.lib().teal_emu_set_concurrent(0)
+    yield
+    H.set_config(0)
+    H.set_tuning()
+
+
+def _mk(Z, N, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(1, 1, Z, generator=g) * scale).half()
+    W = (torch.randn(N, Z, generator=g) * 0.05).half()
+    return x, W
+
+
+def _tol(y32):
+    rms = float(y32.float().pow(2).mean().sqrt())
+    return y32.abs() * 2.0 ** -10 + 2.5e-4 * max(rms, 1e-6) + 1e-7
+
+
+def _gemv(x, W, thr, ws):
+    N, Z = W.shape
+    Wc = H.column_major(W.numpy())
+    y = H.aligned((N,), np.float16, 0)
+    xa = H.aligned((Z,), np.float16, x.reshape(-1).numpy())
+    H.check(H.lib().teal_sparse_gemv_f16(H.ptr(xa), H.ptr(Wc), H.ptr(y), Z, N, N, thr, H.ptr(ws.buf), ws.nbytes, None), "gemv")
+    ws.assert_clean()
+    return torch.from_numpy(y.copy())
+
+
+def _check_gemv(Z, N, thr, seed=0):
+    x, W = _mk(Z, N, seed)
+    ws = H.Workspace()
+    y = _gemv(x, W, thr, ws)
+    want = O.sparse_linear_f32(x, W, thr).reshape(-1)
+    err = (y.float() - want).abs()
+    assert (err <= _tol(want)).all(), (Z, N, thr, float(err.max()))
+
+
+SHAPES = [(200, 264), (512, 1024), (1000, 776), (96, 8), (2048, 520)]
+
+
+@pytest.mark.parametrize("cfg", V1_CFGS)
+def test_emulator_reproduces_the_validated_kernels(cfg):
+    H.set_config(cfg)
+    for Z, N in SHAPES[:3]:
+        _check_gemv(Z, N, 0.6745, seed=cfg)
+
+
+@pytest.mark.parametrize("cfg", GEN2_CFGS)
+@pytest.mark.parametrize("spec", [(0, 1), (4, 1), (8, 2), (32, 1)])
+def test_gen2_gemv_matches_oracle(cfg, spec):
+    H.set_config(cfg)
+    H.set_tuning(generation=2, spec_rows=spec[0], spec_mode=spec[1])
+    for Z, N in SHAPES:
+        _check_gemv(Z, N, 0.6745, seed=cfg + spec[0])
+
+
+@pytest.mark.parametrize("cfg", [43, 45, 46])
+@pytest.mark.parametrize("thr", [0.0, 100.0, 0.05, 2.0])
+def test_gen2_sparsity_extremes(cfg, thr):
+    H.set_config(cfg)
+    H.set_tuning(generation=2, spec_rows=4)
+    _check_gemv(1000, 776, thr, seed=3)
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+def test_default_dispatch_and_survivors_bit_exact(gen):
+    H.set_tuning(generation=gen)
+    for Z, thr in [(8, 0.5), (200, 0.3), (4096, 0.6745), (4096, 0.0), (4096, 100.0), (11008, 0.0203768)]:
+        g = torch.Generator().manual_seed(Z)
+        x = torch.randn(1, 1, Z, generator=g).half()
+        if thr < 0.1 and thr > 0:
+            x = (x.float() * 0.03).half()
+        xa = H.aligned((Z,), np.float16, x.reshape(-1).numpy())
+        idx = H.aligned((Z,), np.int32, 0)
+        cnt = H.aligned((1,), np.int32, 0)
+        H.check(H.lib().teal_survivors_f16(H.ptr(xa), Z, thr, H.ptr(idx), H.ptr(cnt), None), "survivors")
+        want = O.survivor_indices(x, thr)
+        assert int(cnt[0]) == len(want) and np.array_equal(idx[: len(want)], want), (gen, Z, thr)
+    _check_gemv(512, 1024, 0.6745)
+
+
+def _tie_vector():
+    # |x| == fp16(t) with fp16(t) > t: the oracle (fp16 compare) drops it
+    t = 0.02038193
+    t16 = float(torch.tensor(t, dtype=torch.float16))
+    x = torch.tensor([t16, -t16, t16 * 1.001, 0.0, float("nan"), -0.0, 1.0, -1.0], dtype=torch.float16).reshape(1, 1, -1)
+    return x, t
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+def test_tie_rule_and_nan(gen):
+    H.set_tuning(generation=gen)
+    x, t = _tie_vector()
+    Z = x.numel()
+    xa = H.aligned((Z,), np.float16, x.reshape(-1).numpy())
+    idx = H.aligned((Z,), np.int32, 0)
+    cnt = H.aligned((1,), np.int32, 0)
+    H.check(H.lib().teal_survivors_f16(H.ptr(xa), Z, t, H.ptr(idx), H.ptr(cnt), None), "survivors")
+    got = idx[: int(cnt[0])].tolist()
+    assert got == [2, 4, 6, 7]          # the two ties and the zeros are dropped, NaN is gathered (poisons y like mask*x)
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_qkv_region_thresholds(gen, uniform):
+    H.set_tuning(generation=gen, spec_rows=4 if gen == 2 else 0)
+    Z, N, kv = 256, 640, 128                       # N_q = 384: the k/v regions do not start on a 256-column tile
+    x, W = _mk(Z, N, 5)
+    tq, tk, tv = (0.5, 0.5, 0.5) if uniform else (0.3, 0.8, 1.2)
+    Wc = H.column_major(W.numpy())
+    y = H.aligned((N,), np.float16, 0)
+    xa = H.aligned((Z,), np.float16, x.reshape(-1).numpy())
+    ws = H.Workspace()
+    H.check(H.lib().teal_sparse_qkv_gemv_f16(H.ptr(xa), H.ptr(Wc), H.ptr(y), Z, N, N, kv, tq, tk, tv, H.ptr(ws.buf), ws.nbytes, None), "qkv")
+    ws.assert_clean()
+    want = torch.cat([O.sparse_linear_f32(x, W[: N - 2 * kv], tq).reshape(-1), O.sparse_linear_f32(x, W[N - 2 * kv: N - kv], tk).reshape(-1),
+                      O.sparse_linear_f32(x, W[N - kv:], tv).reshape(-1)])
+    assert ((torch.from_numpy(y.copy()).float() - want).abs() <= _tol(want)).all()
+
+
+@pytest.mark.parametrize("gen", [1, 2])
+def test_fused_layer_half_steps(gen):
+    """RMSNorm+gate/up+SiLU*mul -> down+residual (+ sum of squares) -> RMSNorm+QKV from the partials: the decode step's
+    GEMV chain (gpt-fast/model.py:159-161,258-259,286-291) on one small layer."""
+    H.set_tuning(generation=gen, spec_rows=8 if gen == 2 else 0, spec_mode=2)
+    L = H.lib()
+    dim, inter, eps = 256, 776, 1e-5
+    g = torch.Generator().manual_seed(11)
+    resid = torch.randn(1, 1, dim, generator=g).half()
+    nw = (1 + 0.1 * torch.randn(dim, generator=g)).half()
+    W1, W3 = [(torch.randn(inter, dim, generator=g) * 0.05).half() for _ in range(2)]
+    W2 = (torch.randn(dim, inter, generator=g) * 0.05).half()
+    tg, tu, td = 0.4, 0.6, 0.02
+    ws = H.Workspace()
+    xa = H.aligned((dim,), np.float16, resid.reshape(-1).numpy())
+    nwa = H.aligned((dim,), np.float16, nw.numpy())
+    h = H.aligned((inter,), np.float16, 0)
+    xn = H.aligned((dim,), np.float16, 0)
+    W1c, W3c, W2c = H.column_major(W1.numpy()), H.column_major(W3.numpy()), H.column_major(W2.numpy())
+    # ssq_in = NULL: the library computes the partials itself (ssq_kernel) into the workspace scratch
+    H.check(L.teal_norm_sparse_gate_up_f16(H.ptr(xa), H.ptr(nwa), eps, None, H.ptr(W1c), H.ptr(W3c), H.ptr(h), H.ptr(xn), dim, inter,
+                                           inter, inter, tg, tu, H.ptr(ws.buf), ws.nbytes, None), "norm_gate_up")
+    ws.assert_clean()
+    xn_ref = O.rms_norm(resid, nw, eps)
+    assert np.array_equal(xn.view(np.uint16), xn_ref.reshape(-1).numpy().view(np.uint16)) or \
+        float((torch.from_numpy(xn.copy()).float() - xn_ref.reshape(-1).float()).abs().max()) <= 2e-3
+    xn_t = torch.from_numpy(xn.copy()).reshape(1, 1, -1)
+    g32, u32 = O.sparse_linear_f32(xn_t, W1, tg), O.sparse_linear_f32(xn_t, W3, tu)
+    h_ref = (torch.nn.functional.silu(g32.half()) * u32.half()).reshape(-1)           # fp16 silu, fp16 product (model.py:259)
+    h_t = torch.from_numpy(h.copy())
+    assert ((h_t.float() - h_ref.float()).abs() <= h_ref.float().abs() * 2.0 ** -8 + 2e-3).all()
+    # down + residual + sum of squares
+    y = H.aligned((dim,), np.float16, 0)
+    ssq = H.aligned((64,), np.float32, 7.0)                                            # stale garbage must be overwritten
+    H.check(L.teal_sparse_gemv_residual_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq), inter, dim, dim, td,
+                                            H.ptr(ws.buf), ws.nbytes, None), "down_residual")
+    ws.assert_clean()
+    d32 = O.sparse_linear_f32(h_t.reshape(1, 1, -1), W2, td).reshape(-1)
+    want = (resid.reshape(-1) + d32.half()).float()
+    y_t = torch.from_numpy(y.copy())
+    assert ((y_t.float() - want).abs() <= want.abs() * 2.0 ** -9 + 2e-3).all()
+    assert abs(float(ssq.sum()) - float((y_t.float() ** 2).sum())) <= 1e-4 * float((y_t.float() ** 2).sum())
+    # consumer: RMSNorm from the partials + QKV
+    N, kv = 384, 64
+    Wq = (torch.randn(N, dim, generator=g) * 0.05).half()
+    Wqc = H.column_major(Wq.numpy())
+    q = H.aligned((N,), np.float16, 0)
+    xn2 = H.aligned((dim,), np.float16, 0)
+    H.check(L.teal_norm_sparse_qkv_gemv_f16(H.ptr(y), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(Wqc), H.ptr(q), H.ptr(xn2), dim, N, N, kv,
+                                            0.5, 0.5, 0.5, H.ptr(ws.buf), ws.nbytes, None), "norm_qkv")
+    ws.assert_clean()
+    xn2_ref = O.rms_norm(y_t.reshape(1, 1, -1), nw, eps).reshape(-1)
+    assert float((torch.from_numpy(xn2.copy()).float() - xn2_ref.float()).abs().max()) <= 4e-3
+    q_ref = O.sparse_linear_f32(torch.from_numpy(xn2.copy()).reshape(1, 1, -1), Wq, 0.5).reshape(-1)
+    assert ((torch.from_numpy(q.copy()).float() - q_ref).abs() <= _tol(q_ref)).all()
