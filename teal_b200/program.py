@@ -51,8 +51,8 @@ def layer_desc(*, wqkv=0, wo=0, w1=0, w3=0, w2=0, attn_norm=0, ffn_norm=0, k_cac
 class StepProgram:
     """A planned step: host blob + (optionally) its device copy."""
 
-    def __init__(self, desc: StepDesc, layers: Sequence[LayerDesc]):
-        self.lib = _lib.load()
+    def __init__(self, desc: StepDesc, layers: Sequence[LayerDesc], lib=None):
+        self.lib = lib if lib is not None else _lib.load()  # `lib`: tests plan / run against the CPU emulation build
         self._layers = (LayerDesc * max(1, len(layers)))(*layers)  # keep-alive: desc points into it
         desc.layers = ctypes.cast(self._layers, ctypes.POINTER(LayerDesc))
         desc.n_layer = len(layers)

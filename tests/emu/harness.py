@@ -79,3 +79,106 @@ KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2}
 def set_tuning(generation=1, spec_rows=0, spec_mode=1):
     for k, v in (("generation", generation), ("spec_rows", spec_rows), ("spec_mode", spec_mode)):
         check(lib().teal_set_tuning(KNOBS[k], int(v)), f"teal_set_tuning({k})")
+
+
+class EmuDecoder:
+    """The buffers and call sequence of teal_b200.model.SparseDecoder (`_enqueue_step`, `build_program`) on numpy
+    arrays against the emulation library: one decode step = the same C-ABI calls in the same order."""
+    PROJS = ("q", "k", "v", "o", "gate", "up", "down")
+
+    def __init__(self, cfg: dict, sd: dict, thresholds, max_seq: int = 64):
+        import torch
+        from oracle import teal_oracle as O
+        self.cfg, self.L = cfg, lib()
+        self.dim, self.n_head, self.n_kv = cfg["dim"], cfg["n_head"], cfg["n_local_heads"]
+        self.hd = self.dim // self.n_head
+        self.kv = self.n_kv * self.hd
+        self.nqkv = self.dim + 2 * self.kv
+        self.inter, self.vocab, self.eps, self.max_seq = cfg["intermediate_size"], cfg["vocab_size"], cfg["norm_eps"], max_seq
+        self.thresholds = thresholds
+        f16 = np.float16
+        npy = lambda t: t.detach().to(torch.float16).numpy()
+        self.tok_emb = aligned(sd["tok_embeddings.weight"].shape, f16, npy(sd["tok_embeddings.weight"]))
+        self.lm_head = aligned(sd["output.weight"].shape, f16, npy(sd["output.weight"]))
+        self.final_norm = aligned((self.dim,), f16, npy(sd["norm.weight"]))
+        self.layers = []
+        for i in range(cfg["n_layer"]):
+            p = f"layers.{i}."
+            self.layers.append(dict(
+                wqkv=column_major(npy(sd[p + "attention.wqkv.weight"])), wo=column_major(npy(sd[p + "attention.wo.weight"])),
+                w1=column_major(npy(sd[p + "feed_forward.w1.weight"])), w3=column_major(npy(sd[p + "feed_forward.w3.weight"])),
+                w2=column_major(npy(sd[p + "feed_forward.w2.weight"])),
+                attn_norm=aligned((self.dim,), f16, npy(sd[p + "attention_norm.weight"])),
+                ffn_norm=aligned((self.dim,), f16, npy(sd[p + "ffn_norm.weight"])),
+                k_cache=aligned((self.n_kv, max_seq, self.hd), f16, 0), v_cache=aligned((self.n_kv, max_seq, self.hd), f16, 0)))
+        self.freqs = aligned((max_seq, self.hd // 2, 2), f16, npy(O.precompute_freqs_cis(max_seq, self.hd, cfg["rope_base"])))
+        self.token, self.pos = aligned((1,), np.int32, 0), aligned((1,), np.int32, 0)
+        self.out_tokens, self.argmax = aligned((256,), np.int32, 0), aligned((1,), np.uint64, 0)
+        self.x, self.qkv, self.att = aligned((self.dim,), f16, 0), aligned((self.nqkv,), f16, 0), aligned((self.dim,), f16, 0)
+        self.h, self.logits = aligned((self.inter,), f16, 0), aligned((self.vocab,), f16, 0)
+        self.ssq = aligned((64,), np.float32, 0)
+        self.ws = Workspace()
+        self.program = None
+
+    def reset(self, token):
+        self.token[0], self.pos[0], self.argmax[0] = token, 0, 0
+        for W in self.layers:
+            W["k_cache"][...] = 0
+            W["v_cache"][...] = 0
+
+    def step(self, sparse=True):
+        """SparseDecoder._enqueue_step (world == 1): embed | per layer norm+qkv, attention, o+residual, norm+gate/up,
+        down+residual | lm_head + arg-max | advance."""
+        L, ws = self.L, self.ws
+        wsp, wsn, ssq = ptr(ws.buf), ws.nbytes, ptr(self.ssq)
+        check(L.teal_embed_f16(ptr(self.tok_emb), ptr(self.token), ptr(self.x), ssq, self.dim, None), "embed")
+        for li, W in enumerate(self.layers):
+            t = self.thresholds[li] if (sparse and self.thresholds[li] is not None) else {p: -1.0 for p in self.PROJS}
+            check(L.teal_norm_sparse_qkv_gemv_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), None,
+                                                  self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], wsp, wsn, None), "norm_qkv")
+            check(L.teal_attn_decode_f16(ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att),
+                                         self.n_head, self.n_kv, self.hd, self.max_seq, None), "attn")
+            check(L.teal_sparse_gemv_residual_f16(ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim,
+                                                  t["o"], wsp, wsn, None), "o_proj")
+            check(L.teal_norm_sparse_gate_up_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), ptr(self.h), None,
+                                                 self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], wsp, wsn, None), "gate_up")
+            check(L.teal_sparse_gemv_residual_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter, self.dim, self.dim,
+                                                  t["down"], wsp, wsn, None), "down_proj")
+        check(L.teal_dense_gemv_f16(ptr(self.x), ptr(self.final_norm), self.eps, ptr(self.lm_head), ptr(self.logits), ptr(self.argmax),
+                                    self.dim, self.vocab, self.dim, None), "lm_head")
+        check(L.teal_advance(ptr(self.argmax), ptr(self.token), ptr(self.pos), ptr(self.out_tokens), self.out_tokens.size, None), "advance")
+        ws.assert_clean()
+
+    def build_program(self, sparse=True, **tuning):
+        """SparseDecoder.build_program against the emulation library (host blob == "device" blob)."""
+        from teal_b200 import _lib as binding
+        from teal_b200 import program as prog
+        d = binding.StepDesc()
+        d.dim, d.n_head, d.n_kv_head, d.head_dim = self.dim, self.n_head, self.n_kv, self.hd
+        d.inter, d.vocab, d.max_seq, d.eps = self.inter, self.vocab, self.max_seq, self.eps
+        a = lambda arr: arr.ctypes.data
+        d.tok_emb, d.token, d.ssq_init = a(self.tok_emb), a(self.token), None
+        d.lm_head, d.final_norm, d.ld_head = a(self.lm_head), a(self.final_norm), self.dim
+        d.freqs_cis, d.pos, d.out_tokens = a(self.freqs), a(self.pos), a(self.out_tokens)
+        d.argmax_packed, d.out_cap = a(self.argmax), self.out_tokens.size
+        d.x, d.qkv, d.att, d.h, d.logits = a(self.x), a(self.qkv), a(self.att), a(self.h), a(self.logits)
+        for k, v in tuning.items():
+            prog.set_knob(d, k, v)
+        layers = []
+        for li, W in enumerate(self.layers):
+            t = self.thresholds[li] if (sparse and self.thresholds[li] is not None) else None
+            layers.append(prog.layer_desc(wqkv=a(W["wqkv"]), wo=a(W["wo"]), w1=a(W["w1"]), w3=a(W["w3"]), w2=a(W["w2"]),
+                                          attn_norm=a(W["attn_norm"]), ffn_norm=a(W["ffn_norm"]), k_cache=a(W["k_cache"]),
+                                          v_cache=a(W["v_cache"]), ld_qkv=self.nqkv, ld_o=self.dim, ld_1=self.inter, ld_3=self.inter,
+                                          ld_2=self.dim, thr=t))
+        d.scratch = 256
+        p = prog.StepProgram(d, layers, lib=self.L)
+        self.program_scratch = aligned((p.scratch_bytes,), np.uint8, 0)
+        d.scratch = a(self.program_scratch)
+        p.plan()
+        self.program = p
+        return p
+
+    def step_program(self):
+        p = self.program
+        check(self.L.teal_step_program_run(p.host, ctypes.cast(p.host, ctypes.c_void_p), None), "step_program_run")

@@ -201,3 +201,82 @@ def test_fused_layer_half_steps(gen):
     assert float((torch.from_numpy(xn2.copy()).float() - xn2_ref.float()).abs().max()) <= 4e-3
     q_ref = O.sparse_linear_f32(torch.from_numpy(xn2.copy()).reshape(1, 1, -1), Wq, 0.5).reshape(-1)
     assert ((torch.from_numpy(q.copy()).float() - q_ref).abs() <= _tol(q_ref)).all()
+
+
+# ------------------------------------------------------------------------------------------------ whole decode step
+CFG = dict(block_size=256, vocab_size=512, n_layer=2, n_head=4, dim=256, n_local_heads=2, intermediate_size=704,
+           rope_base=10000, norm_eps=1e-5)
+THR = [dict(q=0.55, k=0.4, v=0.7, o=0.02, gate=0.6, up=0.5, down=0.01),
+       dict(q=0.6, k=0.6, v=0.6, o=0.03, gate=0.5, up=0.5, down=0.02)]
+TOKS = [3, 17, 42, 8]
+
+
+def _state_dict(cfg, seed=0):   # the model of tests/test_decoder_gpu.py
+    g = torch.Generator().manual_seed(seed)
+    hd = cfg["dim"] // cfg["n_head"]
+    nqkv = (cfg["n_head"] + 2 * cfg["n_local_heads"]) * hd
+    sd = {"tok_embeddings.weight": torch.randn(cfg["vocab_size"], cfg["dim"], generator=g),
+          "output.weight": torch.randn(cfg["vocab_size"], cfg["dim"], generator=g) * 0.05,
+          "norm.weight": 1 + 0.1 * torch.randn(cfg["dim"], generator=g)}
+    for i in range(cfg["n_layer"]):
+        p = f"layers.{i}."
+        sd[p + "attention.wqkv.weight"] = torch.randn(nqkv, cfg["dim"], generator=g) * 0.05
+        sd[p + "attention.wo.weight"] = torch.randn(cfg["dim"], cfg["dim"], generator=g) * 0.05
+        sd[p + "feed_forward.w1.weight"] = torch.randn(cfg["intermediate_size"], cfg["dim"], generator=g) * 0.05
+        sd[p + "feed_forward.w3.weight"] = torch.randn(cfg["intermediate_size"], cfg["dim"], generator=g) * 0.05
+        sd[p + "feed_forward.w2.weight"] = torch.randn(cfg["dim"], cfg["intermediate_size"], generator=g) * 0.05
+        sd[p + "attention_norm.weight"] = 1 + 0.1 * torch.randn(cfg["dim"], generator=g)
+        sd[p + "ffn_norm.weight"] = 1 + 0.1 * torch.randn(cfg["dim"], generator=g)
+    return {k: v.half() for k, v in sd.items()}
+
+
+_ORACLE_LOGITS = {}
+
+
+def _oracle_logits(sparse):
+    if sparse not in _ORACLE_LOGITS:
+        orc = O.OracleDecoder(CFG, _state_dict(CFG), THR if sparse else [None] * CFG["n_layer"], max_seq=64)
+        with torch.no_grad():
+            _ORACLE_LOGITS[sparse] = [orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1) for i, t in enumerate(TOKS)]
+    return _ORACLE_LOGITS[sparse]
+
+
+def _run_and_compare(dec, sparse, step):
+    want = _oracle_logits(sparse)
+    dec.reset(TOKS[0])
+    for i, t in enumerate(TOKS):
+        dec.token[0] = t
+        step()
+        got = torch.from_numpy(dec.logits.astype(np.float32))
+        scale = float(want[i].abs().max())
+        tol = (6e-2 if sparse else 2e-2) * scale + 2e-2             # the bound of tests/test_step_program_gpu.py
+        assert float((got - want[i]).abs().max()) <= tol, (i, float((got - want[i]).abs().max()), tol)
+        assert int(dec.pos[0]) == i + 1 and int(dec.out_tokens[i]) == int(dec.token[0])
+        assert int(dec.token[0]) == int(torch.argmax(got))         # fused arg-max == torch.argmax of the fp16 logits
+
+
+@pytest.mark.parametrize("gen,sparse", [(1, False), (1, True), (2, False), (2, True)])
+def test_decode_step_launch_per_projection(gen, sparse):
+    H.set_tuning(generation=gen, spec_rows=4 if gen == 2 else 0)
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    _run_and_compare(dec, sparse, lambda: dec.step(sparse))
+
+
+PROGRAM_KNOBS = [
+    dict(),                                                        # hardware-validated default (emulator self-check)
+    dict(rows_small=32, rows_large=64), dict(group_qkv=1, group_gate_up=2), dict(wide_melems=1), dict(head_rows=7),
+    # written after the GPU budget was spent -- never run on hardware:
+    dict(warps=2), dict(warps=2, rows_small=32), dict(opts=2), dict(opts=3, stagger_ns=100), dict(warps=2, opts=3, stagger_ns=50),
+    dict(rows_qkv=32, rows_o=128, rows_gate_up=64, rows_down=64), dict(opts=4), dict(opts=5), dict(warps=2, opts=7, stagger_ns=50),
+    dict(tiles_per_item=2), dict(tiles_per_item=4, warps=2, rows_small=64, rows_large=64),
+    dict(tiles_per_item=3, group_qkv=5, group_gate_up=6), dict(tiles_per_item=2, wide_melems=1, opts=4),
+]
+
+
+@pytest.mark.parametrize("knobs", PROGRAM_KNOBS, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()) or "default")
+def test_step_program_one_kernel_per_token(knobs):
+    H.lib().teal_emu_set_sm_count(2)
+    H.lib().teal_emu_set_concurrent(1)          # persistent kernel: all CTAs alive together, they wait on each other
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    dec.build_program(True, **knobs)
+    _run_and_compare(dec, True, dec.step_program)
