@@ -252,13 +252,15 @@ int teal_sparse_gemv_f16_simple(const void* x, const void* wt, void* y, int Z, i
                                 double threshold, void* stream);
 
 /* Kernel selection for benchmarks and parity tests: 0 = library default (rowchunk_gemv: many small CTAs, variant
- * chosen by launch size); 30+v = rowchunk variant v (v >= 12: generation 2); 100+v = variant v without wave
+ * chosen by launch size); 30+v = rowchunk variant v (v >= 12: generation 2, v >= 20: warp-wise); 100+v = variant v without wave
  * balancing; 1..6 = TMA-bulk-ring kernel; 10+T = gather_gemv (cp.async rings) with T column tiles per matrix. */
 int teal_set_config(int config_id);
 
 /* Opt-in experimental knobs of the default dispatch (process-wide, like teal_set_config).
  *   TEAL_TUNE_GENERATION  1 (default, hardware-validated) | 2 (rowchunk_gemv2_kernel: shared-memory survivor list,
- *                         rolling load ring, FHFMA; compiled and SASS-checked, not yet run on hardware)
+ *                         rolling load ring, FHFMA) | 3 (the same with warp-wise completion: every warp reduces and
+ *                         arrives on its own, no __syncthreads); 2 and 3 pass the CPU emulation of tests/emu and are
+ *                         SASS-checked, but have not run on hardware yet
  *   TEAL_TUNE_SPEC_ROWS   generation 2: rows per warp the first-wave CTAs pull into L2 before their producer is done
  *                         (0 = off, default)
  *   TEAL_TUNE_SPEC_MODE   1 = prefetch.global.L2 per 128-byte line (default), 2 = cp.async.bulk.prefetch.L2 per row */

@@ -28,7 +28,7 @@ static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1};  // generation 1, no speculati
 int tuning(int knob) { return (knob >= 0 && knob < TEAL_TUNE_COUNT) ? g_tuning[knob] : 0; }
 int set_tuning(int knob, int value) {
   if (knob < 0 || knob >= TEAL_TUNE_COUNT) return set_error(TEAL_ERR_BAD_ARG, "tuning knob out of range");
-  if (knob == TEAL_TUNE_GENERATION && value != 1 && value != 2) return set_error(TEAL_ERR_BAD_ARG, "generation must be 1 or 2");
+  if (knob == TEAL_TUNE_GENERATION && (value < 1 || value > 3)) return set_error(TEAL_ERR_BAD_ARG, "generation must be 1, 2 or 3");
   if (knob == TEAL_TUNE_SPEC_ROWS && (value < 0 || value > 32)) return set_error(TEAL_ERR_BAD_ARG, "spec_rows must be 0..32");
   if (knob == TEAL_TUNE_SPEC_MODE && value != 1 && value != 2) return set_error(TEAL_ERR_BAD_ARG, "spec_mode must be 1 or 2");
   g_tuning[knob] = value;
@@ -40,7 +40,7 @@ int set_config(int id) {
   if (id >= 100 && id < 200) { g_wave_balance = false; id -= 70; }  // 100 + v: rowchunk variant v without wave balancing
   g_sub_cols = 0;
   if (id >= 1000) { g_sub_cols = (id / 1000) * 256; id %= 1000; }  // e.g. 2014: sub-tile 512, 4 tiles
-  if (id < 0 || (id > kNumTmaConfigs && (id < 11 || id > 26) && (id < 30 || id > 49)) || g_sub_cols > 1024)
+  if (id < 0 || (id > kNumTmaConfigs && (id < 11 || id > 26) && (id < 30 || id > 59)) || g_sub_cols > 1024)
     return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
   g_forced_config = id;
   return TEAL_OK;
@@ -59,13 +59,14 @@ int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_
   if (id >= 11 && id <= 26 && !needs_rc)
     return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, id - 10);
   int variant;
-  if (id >= 30 && id <= 49) {
+  if (id >= 30 && id <= 59) {
     variant = id - 30;
   } else {  // measured on B200 (profiles/r01_bench_gemv_history.jsonl): wide tiles pay off once a launch moves >= ~40 MB
     long long elems = 0;
     for (int s = 0; s < p.nseg; ++s) elems += (long long)p.Z * p.seg[s].ncols;
     variant = (elems >= 40ll * 1000 * 1000) ? 1 : 2;
     if (g_tuning[TEAL_TUNE_GENERATION] == 2) variant = (variant == 1) ? 13 : 15;  // opt-in, see rowchunk_gemv2_kernel
+    if (g_tuning[TEAL_TUNE_GENERATION] == 3) variant = (variant == 1) ? 20 : 21;  // ... with warp-wise completion
   }
   return launch_rowchunk(p, workspace, ws_bytes, out_cols_total, stream, variant);
 }

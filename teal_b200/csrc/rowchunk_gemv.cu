@@ -355,6 +355,85 @@ __device__ __forceinline__ void rc2_finish(const RcParams& p, const RcSeg& sg, i
   if (tid == 0) p.counters[cidx] = 0;
 }
 
+// Warp-wise completion (generation 2, WW): every WARP is an independent worker -- it adds its own partial to the L2
+// accumulator straight from registers and arrives at the tile's counter on its own (target = K chunks x warps), so
+// there is no shared-memory reduction, no __syncthreads, and the RED -> fence -> counter round trips of one warp overlap
+// the other warps' streaming instead of idling the whole CTA.  The last-arriving warp finalises the tile (16 columns
+// per lane of a 512-column tile).  Costs WARPS x more RED traffic at L2 (2 KB per 16 KB of weights).
+template <int VEC>
+__device__ __forceinline__ void rc2_finish_warp(const RcParams& p, const RcSeg& sg, int ct, int col0, int wcols,
+                                                const float2 (&acc)[VEC][4]) {
+  constexpr int COLS = 256 * VEC;
+  const int lane = threadIdx.x & 31;
+  const int acc0 = sg.acc_col0 + col0;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int c = lane * 8 + 256 * v;
+    if (c < wcols) {
+      const float4 a = make_float4(acc[v][0].x, acc[v][0].y, acc[v][1].x, acc[v][1].y);
+      const float4 b = make_float4(acc[v][2].x, acc[v][2].y, acc[v][3].x, acc[v][3].y);
+      if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) red_add_v4(p.acc + acc0 + c, a);
+      if (b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f) red_add_v4(p.acc + acc0 + c + 4, b);
+    }
+  }
+  __syncwarp();  // the lanes' REDs happen-before lane 0's cumulative release fence
+  const int pair = p.mode == kModePairSilu;
+  const int cidx = pair ? (ct - sg.ctile0) : ct;
+  int last = 0;
+  if (lane == 0) {
+    fence_acq_rel_gpu();
+    const unsigned old = atomicAdd(&p.counters[cidx], 1u);
+    last = ((int)old + 1 == p.target) ? 1 : 0;
+    if (last) fence_acq_rel_gpu();
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+
+  float ssq = 0.f;
+  if (pair) {
+    const int g0 = p.seg[0].acc_col0 + col0, u0 = p.seg[1].acc_col0 + col0;
+    for (int c = lane * 4; c < wcols; c += 128) {
+      const float4 g = ld_cg_f4(p.acc + g0 + c), u = ld_cg_f4(p.acc + u0 + c);
+      st_cg_f4(p.acc + g0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      st_cg_f4(p.acc + u0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      const __half2 h0 = __halves2half2(silu_mul_f16(g.x, u.x), silu_mul_f16(g.y, u.y));
+      const __half2 h1 = __halves2half2(silu_mul_f16(g.z, u.z), silu_mul_f16(g.w, u.w));
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.y + col0 + c) = o;
+    }
+  } else {
+    const int y0 = sg.y_col0 + col0;
+    for (int c = lane * 4; c < wcols; c += 128) {
+      const float4 a = ld_cg_f4(p.acc + acc0 + c);
+      st_cg_f4(p.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      if (p.out_mode == kOutAddResidual) {  // h = x + y in fp16 (gpt-fast/model.py:160-161)
+        const uint2 r = *reinterpret_cast<const uint2*>(p.resid + y0 + c);
+        h0 = __hadd2(*reinterpret_cast<const __half2*>(&r.x), h0);
+        h1 = __hadd2(*reinterpret_cast<const __half2*>(&r.y), h1);
+      }
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.y + y0 + c) = o;
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      ssq = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, ssq))));
+    }
+  }
+  if (p.ssq_out) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+    if (lane == 0) {
+      p.ssq_out[cidx] = ssq;
+      for (int sidx = cidx + p.total_ctiles; sidx < kSsqParts; sidx += p.total_ctiles) p.ssq_out[sidx] = 0.f;
+    }
+  }
+  if (lane == 0) p.counters[cidx] = 0;
+  (void)COLS;
+}
+
 namespace {
 // f32 += f16 * f16 (FHFMA): the product of two fp16 values is exact in fp32, so this is fma(float(w), float(x), acc)
 __device__ __forceinline__ void rc_fhfma2(float2& acc, uint32_t w2, unsigned short xh) {
@@ -459,11 +538,11 @@ __device__ __forceinline__ void rc2_gather(float2 (&acc)[VEC][4], const uint32_t
 #undef RC2_ISSUE
 }
 
-template <int VEC, int U, int WARPS, bool FH>
+template <int VEC, int U, int WARPS, bool FH, bool WW>
 __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv2_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
   constexpr int kCap = kRc2MaxPass * 32;
-  __shared__ __align__(16) float s_red[WARPS][COLS];
+  __shared__ __align__(16) float s_red[WW ? 1 : WARPS][WW ? 4 : COLS];  // warp-wise completion needs no staging
   __shared__ uint32_t s_list[WARPS][kCap];  // the warp's compacted survivors: fp16 bits of x | (lane offset << 16)
   __shared__ float s_ssq[WARPS];
   __shared__ int s_last;
@@ -571,7 +650,11 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv2_kernel(const __grid
     if (warp == 0) atomicAdd(p.probe + 1, (unsigned long long)max(0, kend - kbeg) * (unsigned long long)wcols * 2ull);
   }
   if (p.mode == kModeSurvivors) return;
-  rc2_finish<VEC, WARPS>(p, sg, ct, col0, wcols, acc, s_red, s_ssq, &s_last);
+  if constexpr (WW) {
+    rc2_finish_warp<VEC>(p, sg, ct, col0, wcols, acc);
+  } else {
+    rc2_finish<VEC, WARPS>(p, sg, ct, col0, wcols, acc, s_red, s_ssq, &s_last);
+  }
 }
 
 // Sum-of-squares partials of a vector that did not come out of a GEMV finaliser (embedding row, tests).
@@ -649,9 +732,10 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (gp.ssq_out && gp.mode == kModePairSilu) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out is not defined for the gate/up pair");
   if (gp.out_mode == kOutAddResidual && (!gp.resid || (reinterpret_cast<uintptr_t>(gp.resid) & 7)))
     return set_error(TEAL_ERR_ALIGNMENT, "residual must be non-null and 8-byte aligned");
-  struct Variant { int vec, u, warps, rows, gen; void (*kern)(const RcParams); };
-#define TEAL_RC(V, UU, W, R) {V, UU, W, R, 1, rowchunk_gemv_kernel<V, UU, W>}
-#define TEAL_RC2(V, UU, W, R, FH) {V, UU, W, R, 2, rowchunk_gemv2_kernel<V, UU, W, FH>}
+  struct Variant { int vec, u, warps, rows, gen, ww; void (*kern)(const RcParams); };
+#define TEAL_RC(V, UU, W, R) {V, UU, W, R, 1, 0, rowchunk_gemv_kernel<V, UU, W>}
+#define TEAL_RC2(V, UU, W, R, FH) {V, UU, W, R, 2, 0, rowchunk_gemv2_kernel<V, UU, W, FH, false>}
+#define TEAL_RC2W(V, UU, W, R) {V, UU, W, R, 2, 1, rowchunk_gemv2_kernel<V, UU, W, true, true>}
   static const Variant kVariants[] = {
       TEAL_RC(1, 8, 4, 128),   // 0
       TEAL_RC(2, 4, 4, 128),   // 1
@@ -674,9 +758,15 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       TEAL_RC2(1, 8, 4, 128, true),   // 17
       TEAL_RC2(2, 6, 4, 128, true),   // 18: 6 KB in flight per warp
       TEAL_RC2(1, 8, 2, 128, true),   // 19
+      // generation 2, warp-wise completion (every warp an independent worker: no smem reduction, no __syncthreads)
+      TEAL_RC2W(2, 4, 4, 128),        // 20: 32 lanes per warp
+      TEAL_RC2W(1, 8, 2, 64),         // 21
+      TEAL_RC2W(2, 4, 4, 256),        // 22: 64 lanes per warp (half the REDs and arrivals)
+      TEAL_RC2W(1, 8, 4, 256),        // 23
   };
 #undef TEAL_RC
 #undef TEAL_RC2
+#undef TEAL_RC2W
   constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
   if (variant < 0 || variant >= kNumVariants) variant = 0;
   const Variant& var = kVariants[variant];
@@ -734,7 +824,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   }
   p.rows_per_cta = rows;
   p.nkchunks = (gp.Z + rows - 1) / rows;
-  if (var.gen == 2) {
+  if (var.gen == 2) {  // (variants of generations 2 and 3: the same kernel template)
     if (rows > 32 * kRc2MaxPass * var.warps) return set_error(TEAL_ERR_UNSUPPORTED, "rowchunk generation 2: K chunk too long");
     for (int s = 0; s < p.nseg && gp.mode != kModeSurvivors; ++s)
       if (p.seg[s].ldw <= 0 || p.seg[s].ldw >= (1ll << 30)) return set_error(TEAL_ERR_UNSUPPORTED, "rowchunk generation 2: ldw out of range");
@@ -747,7 +837,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       p.spec_ctas = device_info().sm_count * occ;
     }
   }
-  p.target = pair ? 2 * p.nkchunks : p.nkchunks;
+  p.target = (pair ? 2 * p.nkchunks : p.nkchunks) * (var.ww ? var.warps : 1);
   const long long grid = (long long)p.total_ctiles * p.nkchunks;
   if (grid > 0x7fffffffll) return set_error(TEAL_ERR_UNSUPPORTED, "grid too large");
 

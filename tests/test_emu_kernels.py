@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu
 import harness as H  # noqa: E402
 
 V1_CFGS = [30, 31, 32, 33, 35, 38, 40]      # hardware-validated row-chunk variants (emulator self-check)
-GEN2_CFGS = [42, 43, 44, 45, 46, 47, 48, 49]
+GEN2_CFGS = [42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53]   # 50+: warp-wise completion
 
 
 @pytest.fixture(autouse=True)
@@ -82,7 +82,7 @@ def test_gen2_gemv_matches_oracle(cfg, spec):
         _check_gemv(Z, N, 0.6745, seed=cfg + spec[0])
 
 
-@pytest.mark.parametrize("cfg", [43, 45, 46])
+@pytest.mark.parametrize("cfg", [43, 45, 46, 50, 53])
 @pytest.mark.parametrize("thr", [0.0, 100.0, 0.05, 2.0])
 def test_gen2_sparsity_extremes(cfg, thr):
     H.set_config(cfg)
@@ -90,7 +90,7 @@ def test_gen2_sparsity_extremes(cfg, thr):
     _check_gemv(1000, 776, thr, seed=3)
 
 
-@pytest.mark.parametrize("gen", [1, 2])
+@pytest.mark.parametrize("gen", [1, 2, 3])
 def test_default_dispatch_and_survivors_bit_exact(gen):
     H.set_tuning(generation=gen)
     for Z, thr in [(8, 0.5), (200, 0.3), (4096, 0.6745), (4096, 0.0), (4096, 100.0), (11008, 0.0203768)]:
@@ -115,7 +115,7 @@ def _tie_vector():
     return x, t
 
 
-@pytest.mark.parametrize("gen", [1, 2])
+@pytest.mark.parametrize("gen", [1, 2, 3])
 def test_tie_rule_and_nan(gen):
     H.set_tuning(generation=gen)
     x, t = _tie_vector()
@@ -128,10 +128,10 @@ def test_tie_rule_and_nan(gen):
     assert got == [2, 4, 6, 7]          # the two ties and the zeros are dropped, NaN is gathered (poisons y like mask*x)
 
 
-@pytest.mark.parametrize("gen", [1, 2])
+@pytest.mark.parametrize("gen", [1, 2, 3])
 @pytest.mark.parametrize("uniform", [True, False])
 def test_qkv_region_thresholds(gen, uniform):
-    H.set_tuning(generation=gen, spec_rows=4 if gen == 2 else 0)
+    H.set_tuning(generation=gen, spec_rows=4 if gen >= 2 else 0)
     Z, N, kv = 256, 640, 128                       # N_q = 384: the k/v regions do not start on a 256-column tile
     x, W = _mk(Z, N, 5)
     tq, tk, tv = (0.5, 0.5, 0.5) if uniform else (0.3, 0.8, 1.2)
@@ -146,11 +146,11 @@ def test_qkv_region_thresholds(gen, uniform):
     assert ((torch.from_numpy(y.copy()).float() - want).abs() <= _tol(want)).all()
 
 
-@pytest.mark.parametrize("gen", [1, 2])
+@pytest.mark.parametrize("gen", [1, 2, 3])
 def test_fused_layer_half_steps(gen):
     """RMSNorm+gate/up+SiLU*mul -> down+residual (+ sum of squares) -> RMSNorm+QKV from the partials: the decode step's
     GEMV chain (gpt-fast/model.py:159-161,258-259,286-291) on one small layer."""
-    H.set_tuning(generation=gen, spec_rows=8 if gen == 2 else 0, spec_mode=2)
+    H.set_tuning(generation=gen, spec_rows=8 if gen >= 2 else 0, spec_mode=2)
     L = H.lib()
     dim, inter, eps = 256, 776, 1e-5
     g = torch.Generator().manual_seed(11)
@@ -255,9 +255,9 @@ def _run_and_compare(dec, sparse, step):
         assert int(dec.token[0]) == int(torch.argmax(got))         # fused arg-max == torch.argmax of the fp16 logits
 
 
-@pytest.mark.parametrize("gen,sparse", [(1, False), (1, True), (2, False), (2, True)])
+@pytest.mark.parametrize("gen,sparse", [(1, False), (1, True), (2, False), (2, True), (3, False), (3, True)])
 def test_decode_step_launch_per_projection(gen, sparse):
-    H.set_tuning(generation=gen, spec_rows=4 if gen == 2 else 0)
+    H.set_tuning(generation=gen, spec_rows=4 if gen >= 2 else 0)
     dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
     _run_and_compare(dec, sparse, lambda: dec.step(sparse))
 

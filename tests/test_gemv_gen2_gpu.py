@@ -16,14 +16,15 @@ pytestmark = [pytest.mark.gpu,
 import test_decoder_gpu as D  # noqa: E402
 import test_gemv_gpu as T  # noqa: E402
 
-GEN2_CFGS = [42, 43, 44, 45, 46, 47, 48, 49]          # 30 + variant 12..19
-SPEC = [dict(spec_rows=0), dict(spec_rows=4, spec_mode=1), dict(spec_rows=8, spec_mode=2), dict(spec_rows=32, spec_mode=1)]
+GEN2_CFGS = [42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53]   # 30 + variant 12..23 (50+: warp-wise completion)
+SPEC = [dict(generation=2, spec_rows=0), dict(generation=2, spec_rows=4, spec_mode=1), dict(generation=2, spec_rows=8, spec_mode=2),
+        dict(generation=2, spec_rows=32, spec_mode=1), dict(generation=3, spec_rows=0), dict(generation=3, spec_rows=8, spec_mode=1)]
 
 
-@pytest.fixture(params=SPEC, ids=lambda s: "spec%d_mode%d" % (s["spec_rows"], s.get("spec_mode", 1)))
+@pytest.fixture(params=SPEC, ids=lambda s: "gen%d_spec%d_mode%d" % (s["generation"], s["spec_rows"], s.get("spec_mode", 1)))
 def gen2(request):
     ops = T._ops()
-    ops.set_tuning(generation=2, **request.param)
+    ops.set_tuning(**request.param)
     yield request.param
     ops.set_tuning()
     ops.set_config(0)
