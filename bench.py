@@ -137,6 +137,9 @@ def main():
                     help="graph: one launch per projection group in a CUDA graph (default, fastest measured); program: the "
                          "whole step as one persistent data-flow kernel (teal_step_program_*, single GPU)")
     ap.add_argument("--knob", action="append", default=[], metavar="NAME=INT", help="step-program tuning knob (repeatable)")
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=INT",
+                    help="opt-in experimental dispatch knob (teal_set_tuning): generation=2|3, spec_rows=R, spec_mode=1|2 "
+                         "(default: generation 1, the hardware-validated kernels)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -181,6 +184,10 @@ def main():
     from teal_b200 import ops
     from teal_b200.model import SparseDecoder
     ops.set_config(args.config)
+    tune = {k: int(v) for k, v in (kv.split("=") for kv in args.tune)}
+    if tune:
+        ops.set_tuning(**tune)
+        config["tuning"] = tune
     K, Wm = args.steps, args.warmup
     max_seq = max(256, K + Wm + 16)
     dec = SparseDecoder(margs, device=f"cuda:{local_rank}", max_seq=max_seq, rank=rank, world=world, process_group=pg,
@@ -331,7 +338,8 @@ def main():
                 traffic = json.load(f).get(args.workload, {}).get("traffic_bytes") if world == 1 else None
         except Exception:
             traffic = None
-        rf = {"bound": "hbm", "kernel": "rowchunk_gemv_kernel<2,4,4> (fused RMSNorm + gate/up gather-GEMV + SiLU*mul)", "achieved": alg / us / 1e3,
+        kname = {1: "rowchunk_gemv_kernel<2,4,4>", 2: "rowchunk_gemv2_kernel<2,4,4,FH>", 3: "rowchunk_gemv2_kernel<2,4,4,FH,WW>"}[tune.get("generation", 1)]
+        rf = {"bound": "hbm", "kernel": f"{kname} (fused RMSNorm + gate/up gather-GEMV + SiLU*mul)", "achieved": alg / us / 1e3,
               "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
               "us_per_launch": us, "alg_bytes_per_launch": alg, "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),
               "timing": "CUDA events on the launching stream, graph of n_layer launches, each layer on its own weights and its own real decode input (L2 defeated)"}

@@ -31,6 +31,9 @@ SWEEP4 = [dict(tiles_per_item=2), dict(tiles_per_item=4), dict(tiles_per_item=2,
           dict(tiles_per_item=2, warps=2, rows_small=64, rows_large=64), dict(tiles_per_item=4, warps=2, rows_small=64, rows_large=64),
           dict(tiles_per_item=4, wide_melems=1), dict(tiles_per_item=2, wide_melems=1, opts=4),
           dict(tiles_per_item=4, group_gate_up=16, group_qkv=8)]
+GRAPH_TUNES = [dict(generation=2), dict(generation=2, spec_rows=2), dict(generation=2, spec_rows=4), dict(generation=2, spec_rows=8),
+               dict(generation=2, spec_rows=8, spec_mode=2), dict(generation=2, spec_rows=16, spec_mode=2), dict(generation=3),
+               dict(generation=3, spec_rows=4), dict(generation=3, spec_rows=8, spec_mode=2)]
 SWEEP = [dict(reserved=6), dict(reserved=5), dict(reserved=4), dict(rows_small=128), dict(rows_small=32),
          dict(rows_large=256), dict(rows_large=64), dict(group_gate_up=2), dict(group_gate_up=16), dict(group_gate_up=56),
          dict(group_qkv=1), dict(group_qkv=24), dict(wide_melems=1), dict(wide_melems=1000), dict(head_rows=16),
@@ -47,6 +50,9 @@ def main():
     ap.add_argument("--sweep", type=int, default=1, help="1: structural knobs, 2: polling / caching knobs, 3: 2-warp CTAs / scale-once / stagger, 4: multi-tile items")
     ap.add_argument("--check", action="store_true", help="teacher-forced logits of the two engines side by side first")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--graph-tunes", action="store_true",
+                    help="also time the launch-per-projection graph under every opt-in dispatch setting (row-chunk generations 2 / 3, "
+                         "speculative L2 prefetch rows) -- the round-2 A/B of kernels written without GPU access")
     args = ap.parse_args()
     t0 = time.time()
     margs = ModelArgs.from_name(args.workload)
@@ -117,6 +123,22 @@ def main():
                   "kernels_per_step": dec.kernels_per_step, "tokens_equal_to_graph_engine": agree})
         except Exception as e:  # noqa: BLE001 - keep the remaining configurations
             emit({"mode": mode, "engine": engine, "tuning": tuning, "error": repr(e)[:300]})
+
+
+    if args.graph_tunes:
+        import teal_b200.ops as ops
+        for tune in GRAPH_TUNES:
+            for mode in ("sparse", "dense_own"):
+                try:
+                    ops.set_tuning(**tune)
+                    ms, toks = timed(mode, "graph")
+                    agree = sum(int(a == b) for a, b in zip(toks, base_tok)) if (mode == "sparse" and base_tok) else None
+                    emit({"mode": mode, "engine": "graph", "dispatch_tuning": tune, "ms_per_step": round(ms, 4), "tok_s": round(1e3 / ms, 1),
+                          "tokens_equal_to_graph_engine": agree})
+                except Exception as e:  # noqa: BLE001
+                    emit({"mode": mode, "engine": "graph", "dispatch_tuning": tune, "error": repr(e)[:300]})
+                finally:
+                    ops.set_tuning()
 
 
 if __name__ == "__main__":

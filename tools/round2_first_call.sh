@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# First GPU call of the next round: validate on hardware everything that was written after round 1's GPU budget was
+# spent (it passes the CPU emulation of tests/emu, nothing more), then A/B it against the validated default.
+#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# Every step is bounded by its own timeout; results land in gpurun_out/r02_*.
+set -u
+mkdir -p gpurun_out
+export TEAL_PROGRAM_GPU_TESTS=1 TEAL_GEN2_GPU_TESTS=1
+# 1. validated suite first (must stay green), then the opt-in tests of the unvalidated kernels
+timeout 600 python -m pytest tests -m gpu -x -q -k "not gen2 and not unvalidated" > gpurun_out/r02_gpu_tests_validated.log 2>&1; echo "validated suite rc=$?"
+timeout 900 python -m pytest tests/test_gemv_gen2_gpu.py -q > gpurun_out/r02_gpu_tests_gen2.log 2>&1; echo "gen2/gen3 tests rc=$?"
+timeout 300 python -m pytest tests/test_step_program_gpu.py -q -k unvalidated > gpurun_out/r02_gpu_tests_program_variants.log 2>&1; echo "step-program variants rc=$?"
+# 2. decode-step A/B on Llama-3-8B @50 %: graph engine under every dispatch setting, then the step-program sweeps
+timeout 420 python tools/bench_engines.py --quick --graph-tunes --out gpurun_out/r02_graph_tunes.jsonl > /dev/null 2>&1; echo "graph tunes rc=$?"
+timeout 300 python tools/bench_engines.py --sweep 3 --out gpurun_out/r02_program_sweep3.jsonl > /dev/null 2>&1; echo "sweep3 rc=$?"
+timeout 300 python tools/bench_engines.py --sweep 4 --out gpurun_out/r02_program_sweep4.jsonl > /dev/null 2>&1; echo "sweep4 rc=$?"
+# 3. per-projection micro-benchmark: validated variants vs generation 2 / 3
+timeout 300 python tools/bench_gemv.py --configs 31,32,43,45,46,50,51,52 --shapes 4096x14336,14336x4096,4096x4096,4096x6144 \
+    --out gpurun_out/r02_bench_gemv.jsonl > /dev/null 2>&1; echo "bench_gemv rc=$?"
+tail -n 40 gpurun_out/r02_graph_tunes.jsonl
