@@ -801,7 +801,8 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   // Wave quantisation: pick the K-chunk so that the grid is (just under) a whole number of full waves of
   // resident CTAs -- 1792 CTAs on 1036 slots ran 1.73 waves, i.e. the second wave left 27 % of the chip idle.
   if (gp.mode != kModeSurvivors && wave_balance_enabled()) {
-    static int occ_cache[16] = {0};
+    static int occ_cache[kNumVariants] = {0};  // (was a fixed [16]: variants >= 16 wrote past it -- the exit-time crash of
+                                               // profiles/r01_generations_quick_ab.jsonl's run)
     if (!occ_cache[variant]) {
       int occ = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.kern, var.warps * 32, 0) != cudaSuccess || occ < 1) occ = 1;
