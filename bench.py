@@ -137,6 +137,9 @@ def main():
                     help="graph: one launch per projection group in a CUDA graph (default, fastest measured); program: the "
                          "whole step as one persistent data-flow kernel (teal_step_program_*, single GPU)")
     ap.add_argument("--knob", action="append", default=[], metavar="NAME=INT", help="step-program tuning knob (repeatable)")
+    ap.add_argument("--top-k", type=int, default=0, help="with --temperature: sample like the reference's generate.py default "
+                    "(--temperature 0.8 --top-k 200) instead of greedy arg-max (opt-in: the sampling kernel has not run on hardware yet)")
+    ap.add_argument("--temperature", type=float, default=0.0)
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=INT",
                     help="opt-in experimental dispatch knob (teal_set_tuning): generation=2|3, spec_rows=R, spec_mode=1|2 "
                          "(default: generation 1, the hardware-validated kernels)")
@@ -199,6 +202,9 @@ def main():
     else:
         thr = dec.calibrate(args.sparsity, n_tokens=8)
     lib = dec.lib
+    if args.temperature > 0:
+        dec.set_sampling(args.temperature, args.top_k, seed=0)
+        config["sampling"] = f"top_k={args.top_k} temperature={args.temperature} (generate.py:49-66 on device)"
 
     def barrier():
         if world > 1:

@@ -140,6 +140,15 @@ int teal_residual_add_f16(void* x, const void* part, float* ssq_out, int dim, vo
 int teal_tp_allreduce_residual_f16(const void* const* peer_partials, void* const* peer_flags, int rank,
                                    int world, void* x, float* ssq_out, void* epoch_cell, int dim,
                                    void* stream);
+/* Top-k / temperature sampling of the next token -- gpt-fast/generate.py:49-66 (`sample`, `logits_to_probs`,
+ * `multinomial_sample_one_no_sync`): l = fp16(logits / max(T, 1e-5)); values below the top_k-th largest l -> -inf;
+ * p = fp16(softmax_fp32(l)); token = argmax fp16(p / q), q ~ Exponential(1) in fp16.  Runs after teal_dense_gemv_f16
+ * and replaces the greedy arg-max in `argmax_packed` (consumed by teal_advance).  top_k = 0 or >= V: no top-k filter.
+ * noise_f16: optional fp16[V] Exponential(1) draws (tests: the reference's own torch noise => same token as the
+ * reference); NULL = Philox4x32-10 keyed by (seed; vocabulary index, *pos).  probs_out: optional fp16[V] (the `probs`
+ * the reference returns).  One CTA, four passes over the L2-resident logits, graph-capturable. */
+int teal_sample_topk_f16(const void* logits, int V, double temperature, int top_k, const void* noise_f16, uint64_t seed,
+                         const int32_t* pos, void* argmax_packed, void* probs_out, void* stream);
 /* Greedy step bookkeeping: *token = arg-max index, out_tokens[*pos] = *token, ++*pos, reset cell. */
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap,
                  void* stream);

@@ -43,8 +43,41 @@ def seeded(shape, seed, scale=1.0, dist="normal"):
     return (a * scale).astype(np.float32)
 
 
+def gen_sampling():
+    """7. sampling (gpt-fast/generate.py:49-66): the reference's `sample()` on fp16 logits, the Exponential(1) noise
+    it drew (same torch seed replayed), the token it returned and its probs."""
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "gpt-fast"))
+    import generate as G
+    cases = {}
+    specs = [("v4096_k200_t08", 4096, 200, 0.8, 3.0), ("v512_k50_t10", 512, 50, 1.0, 2.0), ("v1000_k5_t05", 1000, 5, 0.5, 1.0),
+             ("v96_none_t08", 96, None, 0.8, 2.0), ("v300_k1000_t13", 300, 1000, 1.3, 4.0), ("v2048_k200_ties", 2048, 200, 0.8, 0.05),
+             ("v640_k64_t0", 640, 64, 0.0, 2.0)]
+    for si, (name, V, k, T, scale) in enumerate(specs):
+        for rep in range(3):
+            logits = torch.from_numpy(seeded((1, 1, V), 900 + 10 * si + rep, scale)).to(torch.float16)
+            if "ties" in name:   # coarse logits: many exact ties around the pivot, +/-0.0 among them
+                logits = (logits * 8).round() / 8
+                logits[0, 0, 5] = -0.0
+            torch.manual_seed(1234 + rep)
+            idx, probs = G.sample(logits, temperature=T, top_k=k)
+            torch.manual_seed(1234 + rep)
+            q = torch.empty_like(probs).exponential_(1)
+            key = f"{name}__{rep}"
+            cases[key + "__logits"] = logits.reshape(-1).numpy()
+            cases[key + "__q"] = q.numpy()
+            cases[key + "__probs"] = probs.numpy()
+            cases[key + "__token"] = np.array(int(idx))
+            cases[key + "__T"] = np.array(T, dtype=np.float64)
+            cases[key + "__k"] = np.array(-1 if k is None else k)
+    np.savez_compressed(os.path.join(OUT, "sampling.npz"), **cases)
+    print("wrote sampling.npz:", len(specs) * 3, "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "sampling":
+        return gen_sampling()
     SparsifyFn, ref_greedy, UDistribution, gdist, gmodel, _mlp_forward = _import_reference()
     torch.manual_seed(0)
 
@@ -207,6 +240,7 @@ def main():
     with open(os.path.join(OUT, "op_schemas.txt"), "w") as f:
         f.write("sparse_gemv" + SparseGEMV.schematize() + "\n")
         f.write("sparse_qkv_gemv" + SparseQKVGEMV.schematize() + "\n")
+    gen_sampling()
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import csv
 import os
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -327,6 +327,48 @@ class OracleDecoder:
 
 
 # --------------------------------------------------------------------------- cpu baseline helper
+# ---------------------------------------------------------------------------------------------
+# Sampling (gpt-fast/generate.py:49-66)
+# ---------------------------------------------------------------------------------------------
+def logits_to_probs(logits: torch.Tensor, temperature: float = 1.0, top_k: Optional[int] = None) -> torch.Tensor:
+    """generate.py:53-61 restated with the arithmetic made explicit for an fp16 logits vector [V]: the division is
+    fp32 (fp16 tensor / Python float) rounded to fp16; values below the top_k-th largest -> -inf; soft-max in fp32
+    rounded once to fp16."""
+    l = (logits.float() / np.float32(max(temperature, 1e-5))).to(logits.dtype)
+    if top_k is not None and top_k > 0:
+        v, _ = torch.topk(l, min(top_k, l.size(-1)))
+        l = torch.where(l < v[..., -1:], torch.full_like(l, -float("inf")), l)
+    return torch.softmax(l.float(), dim=-1).to(logits.dtype)
+
+
+def sample_topk(logits: torch.Tensor, temperature: float, top_k: Optional[int], q: torch.Tensor):
+    """generate.py:49-51,63-66 with the Exponential(1) noise `q` (fp16 [V]) given: token = argmax(probs / q),
+    first index on ties.  Returns (token, probs)."""
+    probs = logits_to_probs(logits, temperature, top_k)
+    r = (probs.float() / q.float()).to(probs.dtype)
+    return int(torch.argmax(r)), probs
+
+
+def philox4x32_10(c0: int, c1: int, c2: int, c3: int, k0: int, k1: int):
+    """Philox4x32-10 (Salmon et al. 2011), the counter-based generator of the library's sampling kernel."""
+    M = 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M, p1 & M, ((p0 >> 32) ^ c3 ^ k1) & M, p0 & M
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return c0, c1, c2, c3
+
+
+def sample_noise(seed: int, V: int, pos: int) -> torch.Tensor:
+    """The library's own Exponential(1) noise: u = ((philox(idx, pos; seed)[0] >> 8) + 1) / 2^24 in (0, 1],
+    q = fp16(-log u), zero replaced by the smallest fp16 subnormal."""
+    r0 = np.array([philox4x32_10(i, pos, 0, 0, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)[0] for i in range(V)], dtype=np.uint64)
+    u = ((r0 >> np.uint64(8)).astype(np.float32) + np.float32(1.0)) * np.float32(1.0 / 16777216.0)
+    q = torch.from_numpy(-np.log(u)).half()
+    q[q == 0] = float(np.float16(2.0 ** -24))
+    return q
+
+
 def time_sparse_linear_cpu(x: torch.Tensor, weight: torch.Tensor, threshold: float, reps: int,
                            warmup: int = 2) -> Tuple[float, torch.Tensor]:
     """Times the reference CPU path (mask then dense F.linear -- it does not skip rows;

@@ -259,6 +259,13 @@ int teal_tp_allreduce_residual_f16(const void* const* peer_partials, void* const
   return launch_tp_allreduce_residual(peer_partials, peer_flags, rank, world, reinterpret_cast<__half*>(x), ssq_out,
                                       reinterpret_cast<unsigned*>(epoch_cell), dim, reinterpret_cast<cudaStream_t>(stream));
 }
+int teal_sample_topk_f16(const void* logits, int V, double temperature, int top_k, const void* noise_f16, uint64_t seed,
+                         const int32_t* pos, void* argmax_packed, void* probs_out, void* stream) {
+  return launch_sample_topk(reinterpret_cast<const __half*>(logits), V, (float)temperature, top_k,
+                            reinterpret_cast<const __half*>(noise_f16), seed, pos,
+                            reinterpret_cast<unsigned long long*>(argmax_packed), reinterpret_cast<__half*>(probs_out),
+                            reinterpret_cast<cudaStream_t>(stream));
+}
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap, void* stream) {
   return launch_advance(reinterpret_cast<unsigned long long*>(argmax_packed), token, pos, out_tokens, out_cap,
                         reinterpret_cast<cudaStream_t>(stream));

@@ -173,6 +173,8 @@ int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, cons
 int launch_residual_add(__half* x, const __half* part, float* ssq_out, int dim, cudaStream_t stream);
 int launch_tp_allreduce_residual(const void* const* bufs, void* const* flags, int rank, int ws, __half* x, float* ssq_out,
                                  unsigned* epoch_cell, int dim, cudaStream_t stream);
+int launch_sample_topk(const __half* logits, int V, float temperature, int top_k, const __half* q_ext, unsigned long long seed,
+                       const int* pos, unsigned long long* argmax_packed, __half* probs_out, cudaStream_t stream);
 int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int* out_tokens, int out_cap,
                    cudaStream_t stream);
 

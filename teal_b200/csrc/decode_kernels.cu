@@ -319,6 +319,135 @@ __global__ void advance_kernel(unsigned long long* argmax_packed, int* token, in
 }
 
 // --------------------------------------------------------------------------------------------
+// Top-k / temperature sampling of the next token (gpt-fast/generate.py:49-66, `sample`):
+//   l = fp16(logits / max(T, 1e-5));  pivot = k-th largest l;  l < pivot -> -inf;  p = fp16(softmax_fp32(l));
+//   q ~ Exponential(1) in fp16;  token = argmax fp16(p / q)   (first index on ties, like torch.argmax)
+// One CTA, four passes over the L2-resident fp16 logits: radix select of the pivot on the order-preserving 16-bit key
+// (high byte, then low byte), online soft-max statistics of the kept values, arg-max of p / q.  The result replaces
+// the greedy arg-max in the packed cell that advance_kernel consumes.  q comes from `q_ext` (tests: the reference's
+// own noise) or from Philox4x32-10 keyed by (seed; vocabulary index, position) -- the reference's torch generator
+// stream cannot be reproduced, the distribution is the same.
+// --------------------------------------------------------------------------------------------
+constexpr int kSampleMaxThreads = 1024;
+
+__host__ __device__ inline unsigned sample_key(unsigned short b) {  // fp16 bits -> unsigned key with the same order
+  if (b == 0x8000u) b = 0;  // -0.0 == +0.0 for torch.topk and for `l < pivot`
+  return (b & 0x8000u) ? (unsigned)(unsigned short)~b : (unsigned)(b | 0x8000u);
+}
+__host__ __device__ inline void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// Exponential(1) noise of vocabulary entry `idx` at decode position `pos`: u in (0, 1], q = fp16(-log u), never zero
+__device__ __forceinline__ __half sample_noise(unsigned long long seed, int idx, int pos) {
+  unsigned r[4];
+  philox4x32_10((unsigned)idx, (unsigned)pos, 0u, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+  const float u = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  const __half q = __float2half_rn(-logf(u));
+  return __half_as_ushort(q) == 0 ? __ushort_as_half((unsigned short)1) : q;
+}
+
+__global__ void __launch_bounds__(kSampleMaxThreads) sample_topk_kernel(const __half* __restrict__ logits, int V, float temperature,
+                                                                       int top_k, const __half* __restrict__ q_ext,
+                                                                       unsigned long long seed, const int* __restrict__ pos,
+                                                                       unsigned long long* __restrict__ argmax_packed,
+                                                                       __half* __restrict__ probs_out) {
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_sel[2];   // selected bin, count still needed inside it
+  __shared__ float s_m[32], s_s[32];
+  __shared__ unsigned long long s_best[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  griddep_wait();
+  const float t = fmaxf(temperature, 1e-5f);
+  auto scaled = [&](int i) { return __float2half_rn(__half2float(logits[i]) / t); };  // fp16 tensor / python float
+  const bool use_topk = top_k > 0 && top_k < V;
+  unsigned pivot_key = 0u;  // keep everything
+  if (use_topk) {
+    unsigned need = (unsigned)top_k, prefix = 0u;
+    for (int pass = 0; pass < 2; ++pass) {  // high byte of the key, then the low byte among keys with that high byte
+      for (int b = tid; b < 256; b += blockDim.x) s_hist[b] = 0u;
+      __syncthreads();
+      for (int i = tid; i < V; i += blockDim.x) {
+        const unsigned key = sample_key(__half_as_ushort(scaled(i)));
+        if (pass == 0) atomicAdd(&s_hist[key >> 8], 1u);
+        else if ((key >> 8) == prefix) atomicAdd(&s_hist[key & 0xffu], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {  // walk down from the largest bin until `need` values are covered
+        unsigned above = 0u;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (above + s_hist[b] >= need) break;
+          above += s_hist[b];
+        }
+        s_sel[0] = (unsigned)b;
+        s_sel[1] = need - above;
+      }
+      __syncthreads();
+      if (pass == 0) prefix = s_sel[0];
+      else pivot_key = (prefix << 8) | s_sel[0];
+      need = s_sel[1];
+      __syncthreads();
+    }
+  }
+  // ---- soft-max statistics of the kept values (online max / sum, fp32) --------------------------------------
+  float m = -CUDART_INF_F, sum = 0.f;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const __half l = scaled(i);
+    if (sample_key(__half_as_ushort(l)) >= pivot_key) {
+      const float f = __half2float(l);
+      if (f > m) { sum = sum * expf(m - f) + 1.f; m = f; }
+      else if (f != -CUDART_INF_F) sum += expf(f - m);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, d), s2 = __shfl_xor_sync(0xffffffffu, sum, d);
+    const float mm = fmaxf(m, m2);
+    sum = (m == -CUDART_INF_F ? 0.f : sum * expf(m - mm)) + (m2 == -CUDART_INF_F ? 0.f : s2 * expf(m2 - mm));
+    m = mm;
+  }
+  if (lane == 0) { s_m[warp] = m; s_s[warp] = sum; }
+  __syncthreads();
+  m = -CUDART_INF_F;
+  for (int w = 0; w < nwarp; ++w) m = fmaxf(m, s_m[w]);
+  sum = 0.f;
+  for (int w = 0; w < nwarp; ++w) sum += (s_m[w] == -CUDART_INF_F) ? 0.f : s_s[w] * expf(s_m[w] - m);
+  // ---- arg-max of fp16(p / q) over the kept values ------------------------------------------------------------
+  const int p0 = pos ? pos[0] : 0;
+  unsigned long long best = 0ull;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const __half l = scaled(i);
+    const bool keep = sample_key(__half_as_ushort(l)) >= pivot_key;
+    const __half p = keep ? __float2half_rn(expf(__half2float(l) - m) / sum) : __ushort_as_half((unsigned short)0);
+    if (probs_out) probs_out[i] = p;
+    if (keep) {
+      const __half q = q_ext ? q_ext[i] : sample_noise(seed, i, p0);
+      const __half r = __float2half_rn(__half2float(p) / __half2float(q));
+      const unsigned long long pk = ((unsigned long long)sample_key(__half_as_ushort(r)) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+      best = pk > best ? pk : best;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+    best = o > best ? o : best;
+  }
+  if (lane == 0) s_best[warp] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < nwarp; ++w) best = s_best[w] > best ? s_best[w] : best;
+    *argmax_packed = best;  // same packing as the greedy arg-max: low word = 0xffffffff - index
+  }
+  griddep_launch_dependents();
+}
+
+// --------------------------------------------------------------------------------------------
 // TP path: x += all-reduced partial (fp16 add, gpt-fast/model.py:160-161 after tp.py:120-121,139-140) and the
 // sum of squares of the new residual stream for the next RMSNorm, in one tiny launch.
 // --------------------------------------------------------------------------------------------
@@ -531,6 +660,16 @@ int launch_advance(unsigned long long* argmax_packed, int* token, int* pos, int*
   if (!argmax_packed || !token || !pos || !out_tokens) return set_error(TEAL_ERR_BAD_ARG, "advance: bad argument");
   return launch_pdl(advance_kernel, dim3(1), dim3(32), 0, stream, "advance launch", argmax_packed, token, pos,
                     out_tokens, out_cap);
+}
+
+int launch_sample_topk(const __half* logits, int V, float temperature, int top_k, const __half* q_ext, unsigned long long seed,
+                       const int* pos, unsigned long long* argmax_packed, __half* probs_out, cudaStream_t stream) {
+  if (!logits || !argmax_packed || V <= 0 || top_k < 0 || !(temperature >= 0.f))
+    return set_error(TEAL_ERR_BAD_ARG, "sample: bad argument");
+  int threads = ((V + 7) / 8 + 31) / 32 * 32;  // ~8 values per thread per pass, one CTA
+  threads = threads < 128 ? 128 : threads > kSampleMaxThreads ? kSampleMaxThreads : threads;
+  return launch_pdl(sample_topk_kernel, dim3(1), dim3(threads), 0, stream, "sample launch", logits, V, temperature, top_k, q_ext,
+                    seed, pos, argmax_packed, probs_out);
 }
 
 }  // namespace teal

@@ -169,6 +169,7 @@ class SparseDecoder:
         self.force_tp_path = False  # tests: take the (plain GEMV -> all-reduce -> residual_add) route at world == 1
         self.ffn_inputs = None  # when a list: per-layer copies of (x, ssq) entering the MLP block (bench roofline)
         self.kernels_per_step = 0
+        self.sampling = None  # None = greedy arg-max; else dict(temperature, top_k, seed): generate.py:49-66 on device
 
     # ------------------------------------------------------------------ TP exchange buffers
     def _setup_peer_exchange(self):
@@ -310,6 +311,15 @@ class SparseDecoder:
         self.set_thresholds(thr)
         return thr
 
+    def set_sampling(self, temperature: float = 0.8, top_k: Optional[int] = 200, seed: int = 0):
+        """Sample the next token like the reference's `sample()` (generate.py:49-66; its benchmark default is
+        temperature 0.8, top_k 200 -- generate.py:353-354) instead of the greedy arg-max.  temperature == 0 / None =
+        greedy (the reference itself divides by 1e-5 there and overflows fp16).  Invalidates the captured graph.
+        The noise is the library's Philox stream keyed by (seed; vocabulary index, position): every TP rank draws the
+        same token from its identical logits without any exchange."""
+        self.sampling = None if not temperature else dict(temperature=float(temperature), top_k=int(top_k or 0), seed=int(seed))
+        self.graph = None
+
     # ------------------------------------------------------------------ one decode step (enqueue only)
     def reset(self, first_token: int = 1):
         self.token.fill_(int(first_token))
@@ -401,6 +411,11 @@ class SparseDecoder:
         chk(lib.teal_dense_gemv_f16(self.x.data_ptr(), self.final_norm.data_ptr(), a.norm_eps, self.lm_head.data_ptr(),
                                     self.logits.data_ptr(), self.argmax.data_ptr(), a.dim, a.vocab_size, a.dim, sp),
             "lm_head")
+        if self.sampling is not None:  # replaces the greedy arg-max in the packed cell that `advance` consumes
+            sm = self.sampling
+            chk(lib.teal_sample_topk_f16(self.logits.data_ptr(), a.vocab_size, sm["temperature"], sm["top_k"], None, sm["seed"],
+                                         self.pos.data_ptr(), self.argmax.data_ptr(), None, sp), "sample")
+            n_launch += 1
         chk(lib.teal_advance(self.argmax.data_ptr(), self.token.data_ptr(), self.pos.data_ptr(),
                              self.out_tokens.data_ptr(), self.out_tokens.numel(), sp), "advance")
         self.kernels_per_step = n_launch + 2
@@ -417,6 +432,8 @@ class SparseDecoder:
             raise ValueError("step program modes: 'sparse', 'dense_own'")
         if mode == "sparse" and not self.sparse:
             raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
+        if self.sampling is not None:
+            raise NotImplementedError("the step program decodes greedily (sampling is not a phase yet): use engine='graph'")
         a = self.args
         d = _lib.StepDesc()
         d.dim, d.n_head, d.n_kv_head, d.head_dim = a.dim, self.n_head_l, self.n_kv_l, self.hd

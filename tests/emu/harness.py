@@ -119,6 +119,7 @@ class EmuDecoder:
         self.ssq = aligned((64,), np.float32, 0)
         self.ws = Workspace()
         self.program = None
+        self.sampling = None   # dict(temperature, top_k, seed) as in SparseDecoder.set_sampling
 
     def reset(self, token):
         self.token[0], self.pos[0], self.argmax[0] = token, 0, 0
@@ -146,6 +147,10 @@ class EmuDecoder:
                                                   t["down"], wsp, wsn, None), "down_proj")
         check(L.teal_dense_gemv_f16(ptr(self.x), ptr(self.final_norm), self.eps, ptr(self.lm_head), ptr(self.logits), ptr(self.argmax),
                                     self.dim, self.vocab, self.dim, None), "lm_head")
+        if self.sampling is not None:
+            sm = self.sampling
+            check(L.teal_sample_topk_f16(ptr(self.logits), self.vocab, sm["temperature"], sm["top_k"], None, sm["seed"], ptr(self.pos),
+                                         ptr(self.argmax), None, None), "sample")
         check(L.teal_advance(ptr(self.argmax), ptr(self.token), ptr(self.pos), ptr(self.out_tokens), self.out_tokens.size, None), "advance")
         ws.assert_clean()
 

@@ -280,3 +280,19 @@ def test_step_program_one_kernel_per_token(knobs):
     dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
     dec.build_program(True, **knobs)
     _run_and_compare(dec, True, dec.step_program)
+
+
+def test_decode_step_with_device_sampling():
+    """lm_head -> sample_topk -> advance (SparseDecoder.set_sampling): the sampled token is the oracle's `sample_topk` of the
+    kernel's own logits under the library's noise stream, and it is what the next step embeds."""
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    dec.sampling = dict(temperature=0.8, top_k=20, seed=77)
+    dec.reset(5)
+    dec.token[0] = 5
+    for i in range(4):
+        fed = int(dec.token[0])
+        dec.step(True)
+        logits = torch.from_numpy(dec.logits.copy())
+        want, _ = O.sample_topk(logits, 0.8, 20, O.sample_noise(77, CFG["vocab_size"], i))
+        assert int(dec.token[0]) == want and int(dec.out_tokens[i]) == want, (i, fed)
+        assert int(dec.pos[0]) == i + 1

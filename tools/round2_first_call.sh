@@ -5,10 +5,11 @@
 # Every step is bounded by its own timeout; results land in gpurun_out/r02_*.
 set -u
 mkdir -p gpurun_out
-export TEAL_PROGRAM_GPU_TESTS=1 TEAL_GEN2_GPU_TESTS=1
+export TEAL_PROGRAM_GPU_TESTS=1 TEAL_GEN2_GPU_TESTS=1 TEAL_SAMPLING_GPU_TESTS=1
 # 1. validated suite first (must stay green), then the opt-in tests of the unvalidated kernels
-timeout 600 python -m pytest tests -m gpu -x -q -k "not gen2 and not unvalidated" > gpurun_out/r02_gpu_tests_validated.log 2>&1; echo "validated suite rc=$?"
+timeout 600 python -m pytest tests -m gpu -x -q -k "not gen2 and not unvalidated and not sampling_gpu" > gpurun_out/r02_gpu_tests_validated.log 2>&1; echo "validated suite rc=$?"
 timeout 900 python -m pytest tests/test_gemv_gen2_gpu.py -q > gpurun_out/r02_gpu_tests_gen2.log 2>&1; echo "gen2/gen3 tests rc=$?"
+timeout 300 python -m pytest tests/test_sampling_gpu.py -q > gpurun_out/r02_gpu_tests_sampling.log 2>&1; echo "sampling tests rc=$?"
 timeout 300 python -m pytest tests/test_step_program_gpu.py -q -k unvalidated > gpurun_out/r02_gpu_tests_program_variants.log 2>&1; echo "step-program variants rc=$?"
 # 2. decode-step A/B on Llama-3-8B @50 %: graph engine under every dispatch setting, then the step-program sweeps
 timeout 420 python tools/bench_engines.py --quick --graph-tunes --out gpurun_out/r02_graph_tunes.jsonl > /dev/null 2>&1; echo "graph tunes rc=$?"
