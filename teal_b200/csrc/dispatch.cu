@@ -24,13 +24,14 @@ static bool g_wave_balance = true;
 bool wave_balance_enabled() { return g_wave_balance; }
 static int g_sub_cols = 0;  // config ids k*1000 + id additionally cap the per-warp sub-tile of gather_gemv at k*256 columns
 int sub_cols_override() { return g_sub_cols; }
-static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1};  // generation 1, no speculation, per-line prefetch
+static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1, 1};  // generation 1, no speculation, per-line prefetch, FHFMA
 int tuning(int knob) { return (knob >= 0 && knob < TEAL_TUNE_COUNT) ? g_tuning[knob] : 0; }
 int set_tuning(int knob, int value) {
   if (knob < 0 || knob >= TEAL_TUNE_COUNT) return set_error(TEAL_ERR_BAD_ARG, "tuning knob out of range");
   if (knob == TEAL_TUNE_GENERATION && (value < 1 || value > 3)) return set_error(TEAL_ERR_BAD_ARG, "generation must be 1, 2 or 3");
   if (knob == TEAL_TUNE_SPEC_ROWS && (value < 0 || value > 32)) return set_error(TEAL_ERR_BAD_ARG, "spec_rows must be 0..32");
   if (knob == TEAL_TUNE_SPEC_MODE && value != 1 && value != 2) return set_error(TEAL_ERR_BAD_ARG, "spec_mode must be 1 or 2");
+  if (knob == TEAL_TUNE_FHFMA && value != 0 && value != 1) return set_error(TEAL_ERR_BAD_ARG, "fhfma must be 0 or 1");
   g_tuning[knob] = value;
   return TEAL_OK;
 }
@@ -65,7 +66,8 @@ int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_
     long long elems = 0;
     for (int s = 0; s < p.nseg; ++s) elems += (long long)p.Z * p.seg[s].ncols;
     variant = (elems >= 40ll * 1000 * 1000) ? 1 : 2;
-    if (g_tuning[TEAL_TUNE_GENERATION] == 2) variant = (variant == 1) ? 13 : 15;  // opt-in, see rowchunk_gemv2_kernel
+    if (g_tuning[TEAL_TUNE_GENERATION] == 2)  // opt-in, see rowchunk_gemv2_kernel
+      variant = g_tuning[TEAL_TUNE_FHFMA] ? ((variant == 1) ? 13 : 15) : ((variant == 1) ? 12 : 14);
     if (g_tuning[TEAL_TUNE_GENERATION] == 3) variant = (variant == 1) ? 20 : 21;  // ... with warp-wise completion
   }
   return launch_rowchunk(p, workspace, ws_bytes, out_cols_total, stream, variant);

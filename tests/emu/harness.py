@@ -73,11 +73,11 @@ def set_config(cfg):
     check(lib().teal_set_config(int(cfg)), "teal_set_config")
 
 
-KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2}
+KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3}
 
 
-def set_tuning(generation=1, spec_rows=0, spec_mode=1):
-    for k, v in (("generation", generation), ("spec_rows", spec_rows), ("spec_mode", spec_mode)):
+def set_tuning(generation=1, spec_rows=0, spec_mode=1, fhfma=1):
+    for k, v in (("generation", generation), ("spec_rows", spec_rows), ("spec_mode", spec_mode), ("fhfma", fhfma)):
         check(lib().teal_set_tuning(KNOBS[k], int(v)), f"teal_set_tuning({k})")
 
 

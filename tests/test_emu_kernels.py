@@ -255,9 +255,12 @@ def _run_and_compare(dec, sparse, step):
         assert int(dec.token[0]) == int(torch.argmax(got))         # fused arg-max == torch.argmax of the fp16 logits
 
 
-@pytest.mark.parametrize("gen,sparse", [(1, False), (1, True), (2, False), (2, True), (3, False), (3, True)])
+@pytest.mark.parametrize("gen,sparse", [(1, False), (1, True), (2, False), (2, True), (3, False), (3, True), (20, True)])
 def test_decode_step_launch_per_projection(gen, sparse):
-    H.set_tuning(generation=gen, spec_rows=4 if gen >= 2 else 0)
+    if gen == 20:   # generation 2 with conversions + FFMA2 instead of FHFMA
+        H.set_tuning(generation=2, fhfma=0)
+    else:
+        H.set_tuning(generation=gen, spec_rows=4 if gen >= 2 else 0)
     dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
     _run_and_compare(dec, sparse, lambda: dec.step(sparse))
 
