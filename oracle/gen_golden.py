@@ -74,10 +74,45 @@ def gen_sampling():
     print("wrote sampling.npz:", len(specs) * 3, "cases")
 
 
+def gen_histogram():
+    """8. calibration histograms (utils/utils.py:125-185): the reference's ActivationModule fed with synthetic prefill
+    activations.  The reference hard-codes `.to('cuda')` for its sort; this container has no GPU, so for the duration
+    of the call `Tensor.to('cuda')` is redirected to the CPU (the arithmetic -- sort, order statistics, linspace,
+    torch.histogram -- is the reference's own, unchanged)."""
+    sys.path.insert(0, REF)
+    from utils.utils import ActivationModule
+    real_to = torch.Tensor.to
+
+    def to_cpu_when_cuda(self, *a, **k):
+        if a and a[0] == "cuda":
+            return self
+        return real_to(self, *a, **k)
+
+    blob = {}
+    for name, dist, scale, ntok, width in [("gauss", "normal", 0.03, 48, 256), ("laplace", "laplace", 0.5, 33, 704)]:
+        am = ActivationModule("/tmp/unused")
+        chunks = [torch.from_numpy(seeded((1, ntok, width), 700 + j, scale, dist)).half() for j in range(3)]
+        for c in chunks:
+            am.grab_activations(c, "h1")
+        am.grab_activations(chunks[0][:, :1], "h1")   # a decode-shaped call: ignored by the reference
+        torch.Tensor.to = to_cpu_when_cuda
+        torch.cuda.empty_cache = lambda: None
+        try:
+            h = am.find_histogram(num_bins=2000 if name == "gauss" else 10000)
+        finally:
+            torch.Tensor.to = real_to
+        blob[f"{name}__acts"] = torch.cat([c.squeeze(0) for c in chunks]).numpy()
+        blob[f"{name}__counts"] = h["h1"].numpy()
+        blob[f"{name}__centers"] = h["h1_centers"].numpy()
+        blob[f"{name}__bins"] = np.array(2000 if name == "gauss" else 10000)
+    np.savez_compressed(os.path.join(OUT, "histogram.npz"), **blob)
+    print("wrote histogram.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "sampling":
-        return gen_sampling()
+    if "--only" in sys.argv:
+        return {"sampling": gen_sampling, "histogram": gen_histogram}[sys.argv[sys.argv.index("--only") + 1]]()
     SparsifyFn, ref_greedy, UDistribution, gdist, gmodel, _mlp_forward = _import_reference()
     torch.manual_seed(0)
 
@@ -241,6 +276,7 @@ def main():
         f.write("sparse_gemv" + SparseGEMV.schematize() + "\n")
         f.write("sparse_qkv_gemv" + SparseQKVGEMV.schematize() + "\n")
     gen_sampling()
+    gen_histogram()
     print("wrote", sorted(os.listdir(OUT)))
 
 

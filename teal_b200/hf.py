@@ -79,9 +79,28 @@ class SparseLinear(nn.Module):
 
 
 def mlp_forward(self, x):
-    """teal/mlp.py:37-57 (non-grabbing branch)."""
+    """teal/mlp.py:37-57: grabbing mode records the two activation sites of a dense forward; otherwise the three
+    projections see their thresholded inputs."""
+    if getattr(self, "grabbing_mode", False):
+        self.activation_module.grab_activations(x, "h1")
+        inter = self.act_fn(self.gate_proj(x)) * self.up_proj(x)
+        self.activation_module.grab_activations(inter, "h2")
+        return self.down_proj(inter)
     inter = self.act_fn(self.sparse_linears["gate"](x)) * self.sparse_linears["up"](x)
     return self.sparse_linears["down"](inter)
+
+
+def patch_mlp_for_calibration(mlp: nn.Module, file_path: str) -> nn.Module:
+    """teal/mlp.py:14-35 with ``grabbing_mode=True``: no thresholds yet, an ``ActivationModule`` collects h1 / h2 of
+    every prefill; ``mlp.activation_module.find_histogram(); .save_histogram()`` then writes the ``histograms.pt``
+    that `patch_mlp` / `Distribution` read (teal/grab_acts.py:86-89)."""
+    from .calibration import ActivationModule
+    mlp.forward_old = mlp.forward
+    mlp.grabbing_mode = True
+    mlp.file_path = file_path
+    mlp.activation_module = ActivationModule(file_path)
+    mlp.forward = types.MethodType(mlp_forward, mlp)
+    return mlp
 
 
 def patch_mlp(mlp: nn.Module, distrs: Dict[str, object]) -> nn.Module:
