@@ -210,7 +210,7 @@ typedef struct teal_step_desc {
   int32_t group_gate_up;   /* column tiles per order group of the gate/up phase (even; default 8) */
   int32_t head_rows;       /* vocabulary rows per lm_head item (default 32) */
   int32_t wide_melems;     /* projections with >= this many million weights use 512-column tiles (default 40) */
-  int32_t reserved;        /* cap on resident CTAs per SM (default: occupancy) */
+  int32_t ctas_per_sm;     /* cap on resident CTAs per SM (0 = default: occupancy) */
   int32_t poll_ns;         /* back-off between two polls of a completion flag, ns (default 32; negative = none) */
   int32_t opts;            /* bit 0: a CTA that has seen a whole-phase dependency satisfied does not poll it again;
                             * bit 1: the RMSNorm scale is computed once per (CTA, phase) instead of per warp and item */

@@ -82,7 +82,7 @@ class StepDesc(_c.Structure):
                 ("layers", _c.POINTER(LayerDesc)),
                 ("out_cap", _c.c_int32), ("rows_small", _c.c_int32), ("rows_large", _c.c_int32),
                 ("group_qkv", _c.c_int32), ("group_gate_up", _c.c_int32), ("head_rows", _c.c_int32),
-                ("wide_melems", _c.c_int32), ("reserved", _c.c_int32), ("poll_ns", _c.c_int32), ("opts", _c.c_int32), ("debug_times", _c.c_void_p), ("warps", _c.c_int32),
+                ("wide_melems", _c.c_int32), ("ctas_per_sm", _c.c_int32), ("poll_ns", _c.c_int32), ("opts", _c.c_int32), ("debug_times", _c.c_void_p), ("warps", _c.c_int32),
                 ("stagger_ns", _c.c_int32), ("rows_kind", _c.c_int32 * 4), ("tiles_per_item", _c.c_int32), ("reserved2", _c.c_int32)]
 
 

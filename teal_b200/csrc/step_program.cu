@@ -1494,7 +1494,7 @@ int build_program(const teal_step_desc* d, const Plan& P, unsigned char* blob) {
   H->nflags = L.nflags;
   H->ndone = L.ndone;
   H->scratch_bytes = L.total;
-  H->ctas_per_sm = d->reserved;
+  H->ctas_per_sm = d->ctas_per_sm;
   H->poll_ns = d->poll_ns == 0 ? 32 : (d->poll_ns < 0 ? 0 : d->poll_ns);
   H->opts = d->opts;
   H->dbg = reinterpret_cast<unsigned long long*>(d->debug_times);

@@ -424,7 +424,7 @@ class SparseDecoder:
     def build_program(self, mode: str = "sparse", **tuning):
         """Plan the whole step (same buffers, same arithmetic as `_enqueue_step`) into a `StepProgram`: one persistent
         data-flow kernel per token instead of 5 launches per layer.  `tuning`: the knobs of teal_step_desc
-        (rows_small, rows_large, group_qkv, group_gate_up, head_rows, wide_melems, reserved = CTAs per SM cap)."""
+        (rows_small, rows_large, group_qkv, group_gate_up, head_rows, wide_melems, ctas_per_sm, ...)."""
         from . import program as _prog
         if self.world != 1:
             raise NotImplementedError("the step program is single-GPU (the TP exchange step is not a phase yet)")

@@ -19,7 +19,7 @@ from ._lib import ItemInfo, LayerDesc, StepDesc
 PROJ_ORDER = ("q", "k", "v", "o", "gate", "up", "down")
 KIND_NAMES = {0: "embed", 1: "gemv", 2: "attn", 3: "lm_head", 4: "advance"}
 DEP_NONE, DEP_ALL, DEP_LANES, DEP_QKV_HEAD = 0, 1, 2, 3
-TUNING_KEYS = ("rows_small", "rows_large", "group_qkv", "group_gate_up", "head_rows", "wide_melems", "reserved", "poll_ns",
+TUNING_KEYS = ("rows_small", "rows_large", "group_qkv", "group_gate_up", "head_rows", "wide_melems", "ctas_per_sm", "poll_ns",
                "opts", "debug_times", "warps", "stagger_ns", "rows_qkv", "rows_o", "rows_gate_up", "rows_down",
                "tiles_per_item")
 ROWS_KIND = {"rows_qkv": 0, "rows_o": 1, "rows_gate_up": 2, "rows_down": 3}

@@ -76,7 +76,7 @@ def test_program_graph_replay_and_epochs():
 
 @pytest.mark.parametrize("tuning", [dict(rows_small=32, rows_large=64), dict(rows_small=128, rows_large=128),
                                     dict(group_qkv=1, group_gate_up=2), dict(group_qkv=64, group_gate_up=64),
-                                    dict(wide_melems=1), dict(head_rows=7), dict(reserved=1), dict(reserved=2)])
+                                    dict(wide_melems=1), dict(head_rows=7), dict(ctas_per_sm=1), dict(ctas_per_sm=2)])
 def test_program_tuning_knobs_do_not_change_results(tuning):
     dec, orc = _mk(THR)
     dec.build_program("sparse", **tuning)

@@ -17,15 +17,15 @@ import torch  # noqa: E402
 from teal_b200.model import ModelArgs, SparseDecoder  # noqa: E402
 
 SWEEP2 = [dict(opts=1), dict(opts=1, poll_ns=200), dict(opts=1, poll_ns=1000), dict(poll_ns=-1), dict(opts=1, poll_ns=-1),
-          dict(opts=1, wide_melems=1), dict(opts=1, wide_melems=1, reserved=6), dict(opts=1, wide_melems=1, rows_large=64),
-          dict(opts=1, wide_melems=1, rows_large=64, reserved=6), dict(opts=1, wide_melems=1, poll_ns=200, reserved=6),
+          dict(opts=1, wide_melems=1), dict(opts=1, wide_melems=1, ctas_per_sm=6), dict(opts=1, wide_melems=1, rows_large=64),
+          dict(opts=1, wide_melems=1, rows_large=64, ctas_per_sm=6), dict(opts=1, wide_melems=1, poll_ns=200, ctas_per_sm=6),
           dict(opts=1, wide_melems=1, rows_large=64, group_gate_up=4), dict(opts=1, wide_melems=1, head_rows=64)]
 # round-2 candidates (variants written after round 1's GPU budget was spent)
 SWEEP3 = [dict(warps=2), dict(warps=2, rows_large=64), dict(warps=2, rows_large=64, wide_melems=1), dict(warps=2, opts=2),
           dict(warps=2, opts=2, stagger_ns=100), dict(warps=2, opts=2, stagger_ns=300), dict(opts=2), dict(opts=2, stagger_ns=100),
           dict(opts=2, stagger_ns=300), dict(warps=2, rows_qkv=32, rows_o=32), dict(warps=2, rows_gate_up=128, rows_down=128),
           dict(warps=2, opts=3, head_rows=64), dict(warps=2, group_gate_up=4), dict(warps=2, group_gate_up=16),
-          dict(warps=2, reserved=12), dict(warps=2, reserved=10)]
+          dict(warps=2, ctas_per_sm=12), dict(warps=2, ctas_per_sm=10)]
 # multi-tile items (x loaded once per K chunk, next tile's first rows prefetched into L2 before the reduction)
 SWEEP4 = [dict(tiles_per_item=2), dict(tiles_per_item=4), dict(tiles_per_item=2, opts=4), dict(tiles_per_item=4, opts=4),
           dict(tiles_per_item=2, warps=2, rows_small=64, rows_large=64), dict(tiles_per_item=4, warps=2, rows_small=64, rows_large=64),
@@ -34,7 +34,7 @@ SWEEP4 = [dict(tiles_per_item=2), dict(tiles_per_item=4), dict(tiles_per_item=2,
 GRAPH_TUNES = [dict(generation=2), dict(generation=2, fhfma=0), dict(generation=2, spec_rows=2), dict(generation=2, spec_rows=4), dict(generation=2, spec_rows=8),
                dict(generation=2, spec_rows=8, spec_mode=2), dict(generation=2, spec_rows=16, spec_mode=2), dict(generation=3),
                dict(generation=3, spec_rows=4), dict(generation=3, spec_rows=8, spec_mode=2)]
-SWEEP = [dict(reserved=6), dict(reserved=5), dict(reserved=4), dict(rows_small=128), dict(rows_small=32),
+SWEEP = [dict(ctas_per_sm=6), dict(ctas_per_sm=5), dict(ctas_per_sm=4), dict(rows_small=128), dict(rows_small=32),
          dict(rows_large=256), dict(rows_large=64), dict(group_gate_up=2), dict(group_gate_up=16), dict(group_gate_up=56),
          dict(group_qkv=1), dict(group_qkv=24), dict(wide_melems=1), dict(wide_melems=1000), dict(head_rows=16),
          dict(head_rows=64), dict(head_rows=128), dict(rows_small=128, rows_large=256), dict(rows_small=32, rows_large=64)]
