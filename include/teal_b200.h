@@ -289,6 +289,14 @@ int teal_set_bytes_probe(void* device_u64x2);
  * (clock64 / globaltimer) to device_buf[blockIdx.x * 16 ...]; pass NULL to switch it off. */
 int teal_set_debug_timestamps(void* device_buf);
 
+/* Profiling hook of the production row-chunk kernel: while set, launch i (i < slots, in launch order, also inside a
+ * CUDA-graph capture) runs a TIMED twin of the default kernel whose CTAs write 16 int64 per CTA into slot i of
+ * device_buf (slot stride = 4096 CTAs x 16 x 8 bytes): globaltimer ns at [0] CTA start, [1] producer done
+ * (griddepcontrol.wait returned), [2] first survivor set known, [3] first rows consumed, [4] gather done, [5] partials
+ * reduced + REDs issued, [6] arrival counted, [7] tile finalised (last arrival only); [8] SM id, [9] survivors of
+ * warp 0, [10] last-arrival flag.  NULL switches it off.  tools/rowchunk_timeline.py reads it. */
+int teal_set_debug_timeline(void* device_buf, int slots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ _SIGS = {
     "teal_set_pdl": (_c.c_int, [_c.c_int]),
     "teal_set_bytes_probe": (_c.c_int, [_c.c_void_p]),
     "teal_set_debug_timestamps": (_c.c_int, [_c.c_void_p]),
+    "teal_set_debug_timeline": (_c.c_int, [_c.c_void_p, _c.c_int]),
 }
 
 

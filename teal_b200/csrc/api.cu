@@ -97,6 +97,12 @@ int teal_set_debug_timestamps(void* device_buf) {
   return TEAL_OK;
 }
 
+int teal_set_debug_timeline(void* device_buf, int slots) {
+  if (device_buf && slots <= 0) return set_error(TEAL_ERR_BAD_ARG, "timeline: slots must be positive");
+  set_debug_timeline(reinterpret_cast<long long*>(device_buf), slots);
+  return TEAL_OK;
+}
+
 int teal_sparse_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, double threshold,
                          void* workspace, size_t workspace_bytes_, void* stream) {
   GemvParams p;

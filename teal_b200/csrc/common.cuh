@@ -127,6 +127,7 @@ struct RcParams {
   int spec_rows;       // speculative L2 prefetch: first rows of every warp's lane range ...
   int spec_ctas;       // ... issued by CTAs [0, spec_ctas) only (the first wave), before griddepcontrol.wait
   int spec_mode;       // 1 = prefetch.global.L2 per 128-byte line, 2 = cp.async.bulk.prefetch.L2 per row segment
+  long long* dbg_time; // TIMED instantiations: [grid][16] globaltimer stamps (teal_set_debug_timestamps)
 };
 constexpr int kRc2MaxPass = 4;  // 32-lane groups one warp of a generation-2 CTA may own
 
@@ -146,6 +147,10 @@ float* workspace_ssq_scratch(void* workspace, size_t ws_bytes);
 int set_config(int id);
 void set_debug_timestamps(long long* buf);
 long long* debug_timestamps();
+constexpr int kTimelineMaxCtas = 4096;                       // CTAs recorded per launch (16 int64 each)
+constexpr size_t kTimelineSlotInts = (size_t)kTimelineMaxCtas * 16;
+void set_debug_timeline(long long* buf, int slots);
+long long* next_debug_timeline_slot();
 int forced_config();
 void set_pdl(bool on);
 bool pdl_enabled();

@@ -14,6 +14,14 @@ static long long* g_dbg_time = nullptr;
 static bool g_pdl = false;
 void set_debug_timestamps(long long* buf) { g_dbg_time = buf; }
 long long* debug_timestamps() { return g_dbg_time; }
+// Per-launch timeline slots for the TIMED row-chunk kernels: launch i of a timed region writes slot i.
+static long long* g_timeline = nullptr;
+static int g_timeline_slots = 0, g_timeline_next = 0;
+void set_debug_timeline(long long* buf, int slots) { g_timeline = buf; g_timeline_slots = buf ? slots : 0; g_timeline_next = 0; }
+long long* next_debug_timeline_slot() {
+  if (!g_timeline || g_timeline_next >= g_timeline_slots) return nullptr;
+  return g_timeline + (size_t)(g_timeline_next++) * kTimelineSlotInts;
+}
 int forced_config() { return g_forced_config; }
 void set_pdl(bool on) { g_pdl = on; }
 bool pdl_enabled() { return g_pdl; }

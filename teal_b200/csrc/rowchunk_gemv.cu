@@ -64,9 +64,19 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p, uint64_t policy) {
 
 // VEC: 16-byte vectors per lane per row (column tile = 256 * VEC); U: rows in flight per lane;
 // WARPS: warps per CTA (each owns 32-lane groups of the CTA's K chunk).
-template <int VEC, int U, int WARPS>
+// TIMED: profiling instantiation (teal_set_debug_timestamps): thread 0 of every CTA records globaltimer stamps of its
+// phases -- tools/rowchunk_timeline.py turns them into the wave / head / tail picture of a launch.  The production
+// instantiation (TIMED = false) is SASS-identical to the build without the stamps (tools/sass_diff.py).
+template <int VEC, int U, int WARPS, bool TIMED = false>
 __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
+  long long* const dbg = TIMED ? p.dbg_time + (size_t)blockIdx.x * 16 : nullptr;
+  auto stamp = [&](int i) {
+    if constexpr (TIMED) {
+      if (threadIdx.x == 0) dbg[i] = globaltimer_ns();
+    }
+  };
+  stamp(0);
   constexpr int kRcWarps = WARPS;
   constexpr int kRcThreads = WARPS * 32;
   __shared__ __align__(16) float s_red[kRcWarps][COLS];
@@ -94,6 +104,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
 
   griddep_wait();                 // PDL: everything above overlapped the previous kernel's tail
   griddep_launch_dependents();    // the next kernel may start launching once all our CTAs are running
+  stamp(1);
 
   // ---- RMSNorm scale from the producer's per-tile sums of squares (gpt-fast/model.py:286-291) --------
   float rs = 1.f;
@@ -132,6 +143,8 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     if (p.keep_out && ct == 0 && k < kend) p.keep_out[k] = keep ? 1 : 0;
     my_nnz += __popc(mask);
     if (p.mode == kModeSurvivors) mask = 0u;  // parity hook: thresholds only, no weights
+    if (k0 == kbeg + warp * 32) stamp(2);     // first survivor set known
+    [[maybe_unused]] bool first_batch = TIMED && k0 == kbeg + warp * 32;
     while (mask) {
       int bit[U];
       uint4 wv[U][VEC];
@@ -162,8 +175,15 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
           }
         }
       }
+      if constexpr (TIMED) {
+        if (first_batch) {  // the first rows have arrived from DRAM and been consumed
+          first_batch = false;
+          if (threadIdx.x == 0) dbg[3] = globaltimer_ns() + (long long)(acc[0][0].x == 1.2345e-30f);
+        }
+      }
     }
   }
+  stamp(4);
   if (p.probe && lane == 0) {  // measurement probe: gathered vs dense weight bytes
     atomicAdd(p.probe, (unsigned long long)my_nnz * (unsigned long long)wcols * 2ull);
     const int rows = max(0, min(kend, kbeg + p.rows_per_cta) - kbeg);
@@ -192,6 +212,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
   // ---- arrival counter: REDs of all threads happen-before the barrier, thread 0's release fence is
   // cumulative over them; the last arrival acquires and finalises the tile ------------------------------
   __syncthreads();
+  stamp(5);
   const int pair = p.mode == kModePairSilu;
   const int cidx = pair ? (ct - sg.ctile0) : ct;
   if (tid == 0) {
@@ -200,6 +221,17 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     const int last = ((int)old + 1 == p.target) ? 1 : 0;
     if (last) fence_acq_rel_gpu();
     s_last = last;
+    if constexpr (TIMED) {
+      unsigned smid = blockIdx.x;
+#ifndef TEAL_EMU
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+#endif
+      dbg[6] = globaltimer_ns();
+      dbg[8] = smid;
+      dbg[9] = my_nnz;
+      dbg[10] = last;
+      dbg[7] = 0;
+    }
   }
   __syncthreads();
   if (!s_last) return;
@@ -253,6 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     }
   }
   if (tid == 0) p.counters[cidx] = 0;
+  stamp(7);  // finaliser done (only the last arrival of a tile gets here)
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -843,6 +876,12 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (grid > 0x7fffffffll) return set_error(TEAL_ERR_UNSUPPORTED, "grid too large");
 
   void (*kern)(const RcParams) = var.kern;
+  if ((variant == 1 || variant == 2) && grid <= kTimelineMaxCtas) {  // profiling: the two default variants have a TIMED twin
+    if (long long* slot = next_debug_timeline_slot()) {           // teal_set_debug_timeline: one slot per launch, in launch order
+      p.dbg_time = slot;
+      kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, true> : rowchunk_gemv_kernel<1, 8, 2, true>;
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(var.warps * 32);

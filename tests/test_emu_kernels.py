@@ -299,3 +299,31 @@ def test_decode_step_with_device_sampling():
         want, _ = O.sample_topk(logits, 0.8, 20, O.sample_noise(77, CFG["vocab_size"], i))
         assert int(dec.token[0]) == want and int(dec.out_tokens[i]) == want, (i, fed)
         assert int(dec.pos[0]) == i + 1
+
+
+def test_timeline_twins_record_every_cta_and_do_not_change_results():
+    """teal_set_debug_timeline: the TIMED twins of the two default kernels write monotone stamps for every CTA into one
+    slot per launch; results are those of the production instantiation."""
+    L = H.lib()
+    slots, slot_ints = 3, 4096 * 16
+    buf = H.aligned((slots * slot_ints,), np.int64, 0)
+    x, W = _mk(512, 1024, 9)
+    ws = H.Workspace()
+    y_plain = _gemv(x, W, 0.6745, ws)
+    H.check(L.teal_set_debug_timeline(H.ptr(buf), slots), "timeline")
+    try:
+        y_timed = _gemv(x, W, 0.6745, ws)          # small launch -> variant 2 twin, slot 0
+        _check_gemv(1000, 776, 0.5, seed=4)         # slot 1
+    finally:
+        H.check(L.teal_set_debug_timeline(None, 0), "timeline off")
+    assert torch.equal(y_plain, y_timed) or float((y_plain.float() - y_timed.float()).abs().max()) < 2e-3
+    t = buf.reshape(slots, 4096, 16)
+    for s, (Z, N) in enumerate([(512, 1024), (1000, 776)]):
+        used = t[s][t[s][:, 0] > 0]
+        ctiles = (N + 255) // 256
+        assert len(used) % ctiles == 0 and len(used) >= ctiles * (Z // 64)     # every CTA of the grid reported
+        for a, b in ((0, 1), (1, 2), (2, 4), (4, 5), (5, 6)):
+            assert (used[:, a] <= used[:, b]).all(), (s, a, b)
+        assert int(used[:, 10].sum()) == ctiles                                 # exactly one last arrival per column tile
+        assert ((used[:, 7] > 0) == (used[:, 10] == 1)).all()                    # only the finaliser stamps [7]
+    assert not t[2].any()                                                        # third slot untouched

@@ -50,8 +50,14 @@ def main():
         subprocess.run(["nvcc", *build.NVCC_FLAGS, "-shared", "-o", old_lib, *srcs], check=True)
         old, new = kernels(old_lib), kernels(new_lib)
     counts = collections.Counter()
+    renamed = set()
     for k, a in old.items():
         if k not in new:
+            twin = next((n for n, b in new.items() if n not in old and n not in renamed and b == a), None)
+            if twin is not None:  # e.g. a template gained a defaulted parameter: same code under a new mangled name
+                renamed.add(twin)
+                counts["identical (renamed)"] += 1
+                continue
             status = "REMOVED"
         elif a == new[k]:
             status = "identical"
@@ -63,7 +69,7 @@ def main():
         if status != "identical":
             print(f"{status:9s} {demangle(k)}  ({len(a)} -> {len(new.get(k, []))} instructions)")
     for k in new:
-        if k not in old:
+        if k not in old and k not in renamed:
             counts["new"] += 1
             print(f"{'new':9s} {demangle(k)}  ({len(new[k])} instructions)")
     print(dict(counts))
