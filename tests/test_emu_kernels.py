@@ -327,3 +327,8 @@ def test_timeline_twins_record_every_cta_and_do_not_change_results():
         assert int(used[:, 10].sum()) == ctiles                                 # exactly one last arrival per column tile
         assert ((used[:, 7] > 0) == (used[:, 10] == 1)).all()                    # only the finaliser stamps [7]
     assert not t[2].any()                                                        # third slot untouched
+    # the analysis of tools/rowchunk_timeline.py digests these stamps
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import rowchunk_timeline as RT
+    r = RT.analyse(t[1])
+    assert r["ctas"] == len(t[1][t[1][:, 0] > 0]) and r["span_us"] >= 0 and r["split_us_p50"]["finalise(last only)"] is not None
