@@ -273,8 +273,11 @@ int teal_set_config(int config_id);
  *   TEAL_TUNE_SPEC_ROWS   generation 2: rows per warp the first-wave CTAs pull into L2 before their producer is done
  *                         (0 = off, default)
  *   TEAL_TUNE_SPEC_MODE   1 = prefetch.global.L2 per 128-byte line (default), 2 = cp.async.bulk.prefetch.L2 per row
- *   TEAL_TUNE_FHFMA       generation 2: 1 = FHFMA arithmetic (default), 0 = conversions + FFMA2 like generation 1 */
-enum { TEAL_TUNE_GENERATION = 0, TEAL_TUNE_SPEC_ROWS = 1, TEAL_TUNE_SPEC_MODE = 2, TEAL_TUNE_FHFMA = 3, TEAL_TUNE_COUNT = 4 };
+ *   TEAL_TUNE_FHFMA       generation 2: 1 = FHFMA arithmetic (default), 0 = conversions + FFMA2 like generation 1
+ *   TEAL_TUNE_ROWS_WIDE / TEAL_TUNE_ROWS_NARROW   input lanes (K chunk) per CTA of the wide-tile (>= 40 M-element
+ *                         launches) / narrow-tile default variant; 0 = the variant's own size with wave balancing */
+enum { TEAL_TUNE_GENERATION = 0, TEAL_TUNE_SPEC_ROWS = 1, TEAL_TUNE_SPEC_MODE = 2, TEAL_TUNE_FHFMA = 3, TEAL_TUNE_ROWS_WIDE = 4,
+       TEAL_TUNE_ROWS_NARROW = 5, TEAL_TUNE_COUNT = 6 };
 int teal_set_tuning(int knob, int value);
 
 /* Launch the GEMV kernels with programmatic dependent launch (prologue overlaps the previous

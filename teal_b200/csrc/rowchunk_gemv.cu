@@ -833,7 +833,11 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (gp.ssq_out && ctile0 > kSsqParts) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out: more column tiles than TEAL_SSQ_PARTS");
   // Wave quantisation: pick the K-chunk so that the grid is (just under) a whole number of full waves of
   // resident CTAs -- 1792 CTAs on 1036 slots ran 1.73 waves, i.e. the second wave left 27 % of the chip idle.
-  if (gp.mode != kModeSurvivors && wave_balance_enabled()) {
+  const int rows_forced = forced_config() ? 0 : tuning(vec == 2 ? TEAL_TUNE_ROWS_WIDE : TEAL_TUNE_ROWS_NARROW);  // experiments only
+  if (rows_forced > 0) {
+    rows = rows_forced;
+    if (var.gen == 2 && rows > 32 * kRc2MaxPass * var.warps) rows = 32 * kRc2MaxPass * var.warps;
+  } else if (gp.mode != kModeSurvivors && wave_balance_enabled()) {
     static int occ_cache[kNumVariants] = {0};  // (was a fixed [16]: variants >= 16 wrote past it -- the exit-time crash of
                                                // profiles/r01_generations_quick_ab.jsonl's run)
     if (!occ_cache[variant]) {

@@ -332,3 +332,13 @@ def test_timeline_twins_record_every_cta_and_do_not_change_results():
     import rowchunk_timeline as RT
     r = RT.analyse(t[1])
     assert r["ctas"] == len(t[1][t[1][:, 0] > 0]) and r["span_us"] >= 0 and r["split_us_p50"]["finalise(last only)"] is not None
+
+
+@pytest.mark.parametrize("gen", [1, 2, 3])
+@pytest.mark.parametrize("rows", [32, 96, 256, 512])
+def test_forced_k_chunk_sizes(gen, rows):
+    """TEAL_TUNE_ROWS_*: any multiple of 32 input lanes per CTA (several lane groups per warp, ragged last chunk)."""
+    H.set_tuning(generation=gen, rows_wide=rows, rows_narrow=rows)
+    _check_gemv(1000, 776, 0.6745, seed=rows)          # narrow variant
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    _run_and_compare(dec, True, lambda: dec.step(True))
