@@ -342,3 +342,54 @@ def test_forced_k_chunk_sizes(gen, rows):
     _check_gemv(1000, 776, 0.6745, seed=rows)          # narrow variant
     dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
     _run_and_compare(dec, True, lambda: dec.step(True))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_peer_memory_allreduce_protocol(world):
+    """The fused one-shot all-reduce + residual + sum-of-squares kernel (gpt-fast/tp.py:120-121,139-140 + model.py:160-161)
+    with `world` emulated ranks running concurrently on shared host memory: every rank publishes its epoch into every
+    peer's flag array, waits for the peers, sums the partials in rank order -- replicas stay bit-identical over many
+    steps on the two alternating buffers."""
+    import threading
+    L = H.lib()
+    dim, steps = 512, 6
+    g = torch.Generator().manual_seed(world)
+    parts = [[H.aligned((dim,), np.float16, 0) for _ in range(world)] for _ in range(2)]      # [parity][rank]
+    flags = [H.aligned((world,), np.uint32, 0) for _ in range(world)]
+    xs = [H.aligned((dim,), np.float16, 0) for _ in range(world)]
+    x0 = (torch.randn(dim, generator=g)).half().numpy()
+    for r in range(world):
+        xs[r][...] = x0
+    ssq = [H.aligned((64,), np.float32, 0) for _ in range(world)]
+    epoch = [H.aligned((1,), np.uint32, 0) for _ in range(world)]
+    vals = [[(torch.randn(dim, generator=g) * 0.5).half().numpy() for _ in range(world)] for _ in range(steps)]
+    import ctypes
+    errors = []
+
+    def rank_main(r):
+        try:
+            for s in range(steps):
+                par = s & 1
+                parts[par][r][...] = vals[s][r]                       # "the row-parallel GEMV wrote its partial"
+                pp = (ctypes.c_void_p * world)(*[parts[par][q].ctypes.data for q in range(world)])
+                pf = (ctypes.c_void_p * world)(*[flags[q].ctypes.data for q in range(world)])
+                H.check(L.teal_tp_allreduce_residual_f16(pp, pf, r, world, H.ptr(xs[r]), H.ptr(ssq[r]), H.ptr(epoch[r]), dim, None), "tp")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors and not any(t.is_alive() for t in threads), errors
+    want = torch.from_numpy(x0.copy())
+    for s in range(steps):
+        tot = torch.zeros(dim)
+        for r in range(world):
+            tot += torch.from_numpy(vals[s][r]).float()              # fp32 sum in rank order, one rounding
+        want = (want + tot.half())                                   # fp16 residual add
+    for r in range(world):
+        assert np.array_equal(xs[r].view(np.uint16), xs[0].view(np.uint16))      # replicas bit-identical
+        assert np.array_equal(xs[r].view(np.uint16), want.numpy().view(np.uint16))
+        assert abs(float(ssq[r].sum()) - float((want.float() ** 2).sum())) <= 1e-3 * float((want.float() ** 2).sum())
