@@ -237,6 +237,32 @@ int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* res
   return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
+                                     double threshold, void* const* peer_partials, void* const* peer_flags, void* epoch_tiles,
+                                     int rank, int world, void* workspace, size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, resid_x, Z)) return rc;
+  if (!wt || !resid_x || !peer_partials || !peer_flags || !epoch_tiles || N <= 0 || ldw < N || world < 1 || world > kMaxTpWorld)
+    return set_error(TEAL_ERR_BAD_ARG, "bad wt / resid_x / peers / N / ldw / world");
+  TpFuse tp;
+  memset(&tp, 0, sizeof(tp));
+  for (int r = 0; r < world; ++r) {
+    tp.part[r] = reinterpret_cast<__half*>(peer_partials[r]);
+    tp.flags[r] = reinterpret_cast<unsigned*>(peer_flags[r]);
+  }
+  tp.epoch = reinterpret_cast<unsigned*>(epoch_tiles);
+  tp.rank = rank;
+  tp.world = world;
+  p.mode = kModePlain;
+  p.out_mode = kOutAddResidual;
+  p.resid = reinterpret_cast<const __half*>(resid_x);
+  p.ssq_out = ssq_out;
+  p.tp = &tp;
+  p.nseg = 1;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ---- the rest of the decode step -------------------------------------------------------------------
 int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, float* ssq_out, int dim, void* stream) {
   return launch_embed(reinterpret_cast<const __half*>(tok_embeddings), token, reinterpret_cast<__half*>(x), ssq_out, dim,

@@ -21,6 +21,7 @@ constexpr int kNumTmaConfigs = 6;                 // tile configurations of the 
 enum { kModePlain = 0, kModePairSilu = 1, kModeSurvivors = 2 };
 enum { kInPlain = 0, kInRmsNorm = 1 };        // how x is produced from the input vector
 enum { kOutPlain = 0, kOutAddResidual = 1 };  // what the finaliser adds before writing fp16
+constexpr int kMaxTpWorld = 16;               // ranks of one tensor-parallel group (one NVSwitch domain)
 
 struct GemvSeg {
   const __half* w;   // fp16 [Z][ldw], first column of the region
@@ -55,6 +56,8 @@ struct GemvParams {
   int tile_n, sub_n, cg, rg;  // gather_gemv tiling (filled by its launcher)
   float thr[kMaxThr];  // fp16-representable thresholds
   GemvSeg seg[kMaxSeg];
+  // appended (the offsets above are those of the hardware-validated build of the kernels that take GemvParams by value)
+  const struct TpFuse* tp;  // optional (host pointer): fuse the TP exchange into the finaliser (row-parallel o / down)
 };
 
 // ---- gather_gemv (cp.async per-warp rings) ------------------------------------------------------
@@ -98,6 +101,16 @@ struct GatherParams {
 // ---- rowchunk_gemv (many small CTAs) --------------------------------------------------------------
 constexpr int kSsqParts = 64;  // fixed length of a sum-of-squares partials buffer (unused tail stays zero)
 
+// Row-parallel GEMV fused with its TP exchange (rowchunk_gemv_kernel<.., TP = true>): the finaliser of a column tile
+// writes the rank's fp16 partial of that tile into its peer-mapped buffer, publishes flags[peer][rank * kSsqParts + tile]
+// = epoch to every peer, waits for the peers' flags of the same tile, sums the partials in rank order, adds the residual.
+struct TpFuse {
+  __half* part[kMaxTpWorld];     // this exchange's partial buffer [N] of every rank (peer-mapped; [rank] is local)
+  unsigned* flags[kMaxTpWorld];  // flag array [world * kSsqParts] of every rank
+  unsigned* epoch;               // local [kSsqParts]: exchanges completed per tile
+  int rank, world;
+};
+
 struct RcSeg {
   const __half* w;
   long long ldw;
@@ -128,6 +141,7 @@ struct RcParams {
   int spec_ctas;       // ... issued by CTAs [0, spec_ctas) only (the first wave), before griddepcontrol.wait
   int spec_mode;       // 1 = prefetch.global.L2 per 128-byte line, 2 = cp.async.bulk.prefetch.L2 per row segment
   long long* dbg_time; // TIMED instantiations: [grid][16] globaltimer stamps (teal_set_debug_timestamps)
+  TpFuse tp;           // TP instantiations only
 };
 constexpr int kRc2MaxPass = 4;  // 32-lane groups one warp of a generation-2 CTA may own
 

@@ -490,7 +490,6 @@ __global__ void residual_add_kernel(__half* __restrict__ x, const __half* __rest
 // The two all-reduces of a layer use alternating buffers (o-proj: 0, down-proj: 1): a rank can only overwrite a
 // buffer two exchanges later, by which time every peer has entered the next exchange and is done reading it.
 // --------------------------------------------------------------------------------------------
-constexpr int kMaxTpWorld = 16;
 struct TpPeers {
   const __half* buf[kMaxTpWorld];  // this parity's partial buffer of every rank (peer-mapped)
   unsigned* flags[kMaxTpWorld];    // flag array of every rank: flags[r][s] = last epoch published by sender s

@@ -64,21 +64,23 @@ int set_config(int id) {
 // implement the sum-of-squares hand-off, so the fused-RMSNorm entry points always use rowchunk_gemv.
 int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream) {
   const int id = g_forced_config;
-  const bool needs_rc = p.in_mode != kInPlain || p.ssq_out || p.keep_out || p.mode == kModeSurvivors;
+  const bool needs_rc = p.in_mode != kInPlain || p.ssq_out || p.keep_out || p.mode == kModeSurvivors || p.tp;
   if (id >= 1 && id <= kNumTmaConfigs && !needs_rc && p.out_mode == kOutPlain && !p.x_out)
     return launch_gemv(p, workspace, ws_bytes, out_cols_total, stream);
   if (id >= 11 && id <= 26 && !needs_rc)
     return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, id - 10);
   int variant;
-  if (id >= 30 && id <= 59) {
+  if (id >= 30 && id <= 59 && (!p.tp || id == 31 || id == 32)) {  // (the fused TP exchange exists for variants 1 and 2)
     variant = id - 30;
   } else {  // measured on B200 (profiles/r01_bench_gemv_history.jsonl): wide tiles pay off once a launch moves >= ~40 MB
     long long elems = 0;
     for (int s = 0; s < p.nseg; ++s) elems += (long long)p.Z * p.seg[s].ncols;
     variant = (elems >= 40ll * 1000 * 1000) ? 1 : 2;
-    if (g_tuning[TEAL_TUNE_GENERATION] == 2)  // opt-in, see rowchunk_gemv2_kernel
+    if (p.tp) {
+      // the fused TP exchange lives in the default generation's finaliser
+    } else if (g_tuning[TEAL_TUNE_GENERATION] == 2)  // opt-in, see rowchunk_gemv2_kernel
       variant = g_tuning[TEAL_TUNE_FHFMA] ? ((variant == 1) ? 13 : 15) : ((variant == 1) ? 12 : 14);
-    if (g_tuning[TEAL_TUNE_GENERATION] == 3) variant = (variant == 1) ? 20 : 21;  // ... with warp-wise completion
+    if (!p.tp && g_tuning[TEAL_TUNE_GENERATION] == 3) variant = (variant == 1) ? 20 : 21;  // ... with warp-wise completion
   }
   return launch_rowchunk(p, workspace, ws_bytes, out_cols_total, stream, variant);
 }

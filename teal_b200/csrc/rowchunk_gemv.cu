@@ -60,6 +60,27 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p, uint64_t policy) {
   return r;
 }
 
+// system-scope flag traffic of the fused TP exchange (TP instantiations)
+#ifdef TEAL_EMU
+__device__ __forceinline__ void rc_st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned rc_ld_acquire_sys(const unsigned* p) { ::emu::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ uint4 rc_ld_volatile_u4(const void* p) { uint4 r; memcpy(&r, p, sizeof r); return r; }
+#else
+__device__ __forceinline__ void rc_st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned rc_ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 rc_ld_volatile_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+#endif
+
 }  // namespace
 
 // VEC: 16-byte vectors per lane per row (column tile = 256 * VEC); U: rows in flight per lane;
@@ -67,7 +88,9 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p, uint64_t policy) {
 // TIMED: profiling instantiation (teal_set_debug_timestamps): thread 0 of every CTA records globaltimer stamps of its
 // phases -- tools/rowchunk_timeline.py turns them into the wave / head / tail picture of a launch.  The production
 // instantiation (TIMED = false) is SASS-identical to the build without the stamps (tools/sass_diff.py).
-template <int VEC, int U, int WARPS, bool TIMED = false>
+// TP: the row-parallel projections under tensor parallelism (o / down, gpt-fast/tp.py:117,130) with the exchange step
+// (tp.py:120-121,139-140) fused into the tile finaliser -- see TpFuse.  Opt-in, not yet run on hardware.
+template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false>
 __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
   long long* const dbg = TIMED ? p.dbg_time + (size_t)blockIdx.x * 16 : nullptr;
@@ -249,6 +272,57 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       o.x = *reinterpret_cast<const uint32_t*>(&h0);
       o.y = *reinterpret_cast<const uint32_t*>(&h1);
       *reinterpret_cast<uint2*>(p.y + col0 + c) = o;
+    }
+  } else if constexpr (TP) {
+    // ---- fused TP exchange of this column tile -----------------------------------------------------------------
+    const int y0 = sg.y_col0 + col0;
+    const TpFuse& tp = p.tp;
+    __half* mine = tp.part[tp.rank];
+    for (int c = tid * 4; c < wcols; c += kRcThreads * 4) {  // 1. my fp16 partial -> my peer-mapped buffer
+      const float4 a = ld_cg_f4(p.acc + acc0 + c);
+      st_cg_f4(p.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(mine + y0 + c) = o;
+    }
+    __syncthreads();  // the partial's stores happen-before the publishing threads' system-scope release
+    if (tid < tp.world) {  // 2. one thread per peer: tell it, then wait for its partial of the same tile
+      const unsigned e = tp.epoch[cidx] + 1u;
+      __threadfence_system();
+      rc_st_release_sys(tp.flags[tid] + tp.rank * kSsqParts + cidx, e);
+      const unsigned* theirs = tp.flags[tp.rank] + tid * kSsqParts + cidx;
+      const long long t0 = clock64();
+      while ((int)(rc_ld_acquire_sys(theirs) - e) < 0) {
+        if (clock64() - t0 > 4000000000ll) __trap();  // a missing peer traps instead of hanging the GPU
+      }
+    }
+    __syncthreads();
+    if (tid == 0) tp.epoch[cidx] += 1u;
+    for (int c = tid * 8; c < wcols; c += kRcThreads * 8) {  // 3. sum in rank order (replicas bit-identical), + residual
+      float a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = 0.f;
+      for (int r = 0; r < tp.world; ++r) {
+        const uint4 v = rc_ld_volatile_u4(tp.part[r] + y0 + c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          a[2 * j] += f.x;
+          a[2 * j + 1] += f.y;
+        }
+      }
+      uint4 xv = *reinterpret_cast<const uint4*>(p.resid + y0 + c);
+      __half2* x2 = reinterpret_cast<__half2*>(&xv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x2[j] = __hadd2(x2[j], __floats2half2_rn(a[2 * j], a[2 * j + 1]));  // y rounds to fp16, then the fp16 residual add
+        const float2 f = __half22float2(x2[j]);
+        ssq = fmaf(f.x, f.x, fmaf(f.y, f.y, ssq));
+      }
+      *reinterpret_cast<uint4*>(p.y + y0 + c) = xv;
     }
   } else {
     const int y0 = sg.y_col0 + col0;
@@ -880,7 +954,20 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (grid > 0x7fffffffll) return set_error(TEAL_ERR_UNSUPPORTED, "grid too large");
 
   void (*kern)(const RcParams) = var.kern;
-  if ((variant == 1 || variant == 2) && grid <= kTimelineMaxCtas) {  // profiling: the two default variants have a TIMED twin
+  if (gp.tp) {  // row-parallel projection with the TP exchange fused into the tile finaliser (TP twins of the defaults)
+    if (variant != 1 && variant != 2) return set_error(TEAL_ERR_UNSUPPORTED, "fused TP exchange: only the default row-chunk variants");
+    if (gp.mode != kModePlain || gp.out_mode != kOutAddResidual || gp.nseg != 1 || (gp.seg[0].ncols & 7) || (reinterpret_cast<uintptr_t>(gp.y) & 15) ||
+        (reinterpret_cast<uintptr_t>(gp.resid) & 15))
+      return set_error(TEAL_ERR_BAD_ARG, "fused TP exchange: one region, residual output, 16-byte aligned vectors");
+    if (gp.tp->world < 1 || gp.tp->world > kMaxTpWorld || gp.tp->rank < 0 || gp.tp->rank >= gp.tp->world || !gp.tp->epoch ||
+        gp.tp->world > var.warps * 32 || ctile0 > kSsqParts)
+      return set_error(TEAL_ERR_BAD_ARG, "fused TP exchange: bad rank / world / tile count");
+    for (int r = 0; r < gp.tp->world; ++r)
+      if (!gp.tp->part[r] || !gp.tp->flags[r] || (reinterpret_cast<uintptr_t>(gp.tp->part[r]) & 15))
+        return set_error(TEAL_ERR_ALIGNMENT, "fused TP exchange: null / unaligned peer pointer");
+    p.tp = *gp.tp;
+    kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, true> : rowchunk_gemv_kernel<1, 8, 2, false, true>;
+  } else if ((variant == 1 || variant == 2) && grid <= kTimelineMaxCtas) {  // profiling: the two default variants have a TIMED twin
     if (long long* slot = next_debug_timeline_slot()) {           // teal_set_debug_timeline: one slot per launch, in launch order
       p.dbg_time = slot;
       kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, true> : rowchunk_gemv_kernel<1, 8, 2, true>;

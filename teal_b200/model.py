@@ -200,6 +200,19 @@ class SparseDecoder:
             self.tp_flags = (ctypes.c_void_p * ws)(*[p + 4 * dim for p in ptrs])
             self.tp_part = [t[par * dim * 2:(par + 1) * dim * 2].view(torch.float16).view(1, 1, dim) for par in (0, 1)]
             self.tp_epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self.tp_gemv = False
+            if os.environ.get("TEAL_TP_ALLREDUCE", "fused") == "gemv":
+                # opt-in (not yet run on hardware): the exchange fused into the row-parallel GEMV's tile finalisers
+                # (teal_sparse_gemv_tp_exchange_f16) -- per parity a flag array [world * 64] per rank, local epochs [64]
+                t2 = symm.empty(2 * ws * 64 * 4, dtype=torch.uint8, device=self.dev)
+                t2.zero_()
+                hdl2 = symm.rendezvous(t2, pg)
+                p2 = [int(p) for p in hdl2.buffer_ptrs]
+                assert len(p2) == ws and all(p2)
+                self._symm2 = (t2, hdl2)
+                self.tp_tile_flags = [(ctypes.c_void_p * ws)(*[p + par * ws * 64 * 4 for p in p2]) for par in (0, 1)]
+                self.tp_tile_epochs = [torch.zeros(64, dtype=torch.int32, device=self.dev) for _ in (0, 1)]
+                self.tp_gemv = True
         except Exception as e:  # noqa: BLE001 - any failure means: use NCCL
             ok = 0
             self._symm_error = repr(e)
@@ -382,6 +395,10 @@ class SparseDecoder:
                 chk(lib.teal_sparse_gemv_residual_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(),
                                                       self.x.data_ptr(), ssq, self.dim_l, a.dim, W["wo"].stride(1), t["o"],
                                                       wsp, wsn, sp), "o_proj")
+            elif self.tp_fused and getattr(self, "tp_gemv", False):  # GEMV + exchange + residual + ssq in one kernel (opt-in)
+                chk(lib.teal_sparse_gemv_tp_exchange_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), ssq, self.dim_l, a.dim,
+                                                         W["wo"].stride(1), t["o"], self.tp_bufs[0], self.tp_tile_flags[0],
+                                                         self.tp_tile_epochs[0].data_ptr(), self.rank, self.world, wsp, wsn, sp), "o_proj+exchange")
             else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
                 dst = self.tp_part[0] if self.tp_fused else self.part
                 chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), dst.data_ptr(), self.dim_l,
@@ -402,6 +419,10 @@ class SparseDecoder:
                 chk(lib.teal_sparse_gemv_residual_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(),
                                                       self.x.data_ptr(), ssq, self.inter_l, a.dim, W["w2"].stride(1),
                                                       t["down"], wsp, wsn, sp), "down_proj")
+            elif self.tp_fused and getattr(self, "tp_gemv", False):
+                chk(lib.teal_sparse_gemv_tp_exchange_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(), ssq, self.inter_l, a.dim,
+                                                         W["w2"].stride(1), t["down"], self.tp_bufs[1], self.tp_tile_flags[1],
+                                                         self.tp_tile_epochs[1].data_ptr(), self.rank, self.world, wsp, wsn, sp), "down_proj+exchange")
             else:
                 dst = self.tp_part[1] if self.tp_fused else self.part
                 chk(lib.teal_sparse_gemv_f16(self.h.data_ptr(), W["w2"].data_ptr(), dst.data_ptr(), self.inter_l,

@@ -393,3 +393,61 @@ def test_tp_peer_memory_allreduce_protocol(world):
         assert np.array_equal(xs[r].view(np.uint16), xs[0].view(np.uint16))      # replicas bit-identical
         assert np.array_equal(xs[r].view(np.uint16), want.numpy().view(np.uint16))
         assert abs(float(ssq[r].sum()) - float((want.float() ** 2).sum())) <= 1e-3 * float((want.float() ** 2).sum())
+
+
+@pytest.mark.parametrize("world,Z,N,cfg", [(2, 256, 512, 0), (4, 512, 776, 0), (2, 2048, 1024, 0), (2, 512, 1032, 31), (4, 1024, 512, 31)])
+def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
+    """teal_sparse_gemv_tp_exchange_f16 with `world` emulated ranks running concurrently: each rank gathers its Z/world
+    lanes, the tile finalisers exchange partials over 'peer' memory -- x ends bit-identical on every rank and equals
+    residual + fp16(sum of the ranks' fp16 partials) of the oracle; two alternating buffer sets over several steps."""
+    import ctypes
+    import threading
+    L = H.lib()
+    L.teal_emu_set_concurrent(1)          # every CTA alive: finalisers wait for peers while the rest of the grid runs
+    H.set_config(cfg)                     # 0: the narrow default variant's TP twin, 31: the wide one's
+    steps, Zs = 4, Z // world
+    g = torch.Generator().manual_seed(world * 1000 + Z)
+    W = (torch.randn(N, Z, generator=g) * 0.05).half()
+    Wc = [H.column_major(W[:, r * Zs:(r + 1) * Zs].numpy()) for r in range(world)]           # row-parallel shards (tp.py:117)
+    x0 = torch.randn(N, generator=g).half()
+    hs = [torch.randn(1, 1, Z, generator=g).half() for _ in range(steps)]                     # replicated input of each step
+    thr = 0.5
+    parts = [[H.aligned((N,), np.float16, 0) for _ in range(world)] for _ in range(2)]
+    flags = [[H.aligned((world * 64,), np.uint32, 0) for _ in range(world)] for _ in range(2)]
+    epochs = [[H.aligned((64,), np.uint32, 0) for _ in range(world)] for _ in range(2)]
+    xs = [H.aligned((N,), np.float16, x0.numpy()) for _ in range(world)]
+    ssq = [H.aligned((64,), np.float32, 0) for _ in range(world)]
+    errors = []
+
+    def rank_main(r):
+        try:
+            ws = H.Workspace()
+            for s in range(steps):
+                par = s & 1
+                xa = H.aligned((Zs,), np.float16, hs[s].reshape(-1)[r * Zs:(r + 1) * Zs].numpy())
+                pp = (ctypes.c_void_p * world)(*[parts[par][q].ctypes.data for q in range(world)])
+                pf = (ctypes.c_void_p * world)(*[flags[par][q].ctypes.data for q in range(world)])
+                H.check(L.teal_sparse_gemv_tp_exchange_f16(H.ptr(xa), H.ptr(Wc[r]), H.ptr(xs[r]), H.ptr(ssq[r]), Zs, N, N, thr, pp, pf,
+                                                           H.ptr(epochs[par][r]), r, world, H.ptr(ws.buf), ws.nbytes, None), "tp gemv")
+                ws.assert_clean()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors and not any(t.is_alive() for t in threads), errors
+    want = x0.clone()
+    for s in range(steps):
+        tot = torch.zeros(N)
+        for r in range(world):
+            sl = slice(r * Zs, (r + 1) * Zs)
+            tot += O.sparse_linear_f32(hs[s][..., sl], W[:, sl], thr).reshape(-1).half().float()   # the rank's fp16 partial
+        want = want + tot.half()
+    for r in range(world):
+        assert np.array_equal(xs[r].view(np.uint16), xs[0].view(np.uint16)), r                     # replicas bit-identical
+    got = torch.from_numpy(xs[0].copy()).float()
+    assert ((got - want.float()).abs() <= want.float().abs() * 2.0 ** -8 + 8e-3).all(), float((got - want.float()).abs().max())
+    assert abs(float(ssq[0].sum()) - float((got ** 2).sum())) <= 1e-3 * float((got ** 2).sum())

@@ -23,3 +23,7 @@ timeout 240 python tools/rowchunk_timeline.py --per-launch --out gpurun_out/r02_
 # 5. is FHFMA (generation 2's arithmetic) slower than conversions + FFMA2?
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fhfma_rate tools/micro/fhfma_rate.cu && timeout 60 /tmp/fhfma_rate > gpurun_out/r02_micro_fhfma_rate.txt 2>&1; echo "fhfma_rate rc=$?"
 tail -n 40 gpurun_out/r02_graph_tunes.jsonl
+# Multi-GPU (separate call, N x the box time): the exchange fused into the GEMV finalisers vs the one-shot kernel
+#   gpurun --gpus 2 --timeout 600 -- 'for m in fused gemv; do TEAL_TP_ALLREDUCE=$m python -m torch.distributed.run --nnodes=1 \
+#     --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 64 --warmup 8 --no-cpu --no-dense \
+#     > gpurun_out/r02_tp2_$m.json; done; python tools/tp_check.py'
