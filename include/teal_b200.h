@@ -288,9 +288,11 @@ int teal_set_config(int config_id);
  *   TEAL_TUNE_SPEC_MODE   1 = prefetch.global.L2 per 128-byte line (default), 2 = cp.async.bulk.prefetch.L2 per row
  *   TEAL_TUNE_FHFMA       generation 2: 1 = FHFMA arithmetic (default), 0 = conversions + FFMA2 like generation 1
  *   TEAL_TUNE_ROWS_WIDE / TEAL_TUNE_ROWS_NARROW   input lanes (K chunk) per CTA of the wide-tile (>= 40 M-element
- *                         launches) / narrow-tile default variant; 0 = the variant's own size with wave balancing */
+ *                         launches) / narrow-tile default variant; 0 = the variant's own size with wave balancing
+ *   TEAL_TUNE_V1_OPTS     generation 1 with ONE change at a time (bit mask): 1 = x / norm weights requested together with
+ *                         the sum-of-squares partials, 2 = FHFMA arithmetic, 4 = 32-bit row offsets */
 enum { TEAL_TUNE_GENERATION = 0, TEAL_TUNE_SPEC_ROWS = 1, TEAL_TUNE_SPEC_MODE = 2, TEAL_TUNE_FHFMA = 3, TEAL_TUNE_ROWS_WIDE = 4,
-       TEAL_TUNE_ROWS_NARROW = 5, TEAL_TUNE_COUNT = 6 };
+       TEAL_TUNE_ROWS_NARROW = 5, TEAL_TUNE_V1_OPTS = 6, TEAL_TUNE_COUNT = 7 };
 int teal_set_tuning(int knob, int value);
 
 /* Launch the GEMV kernels with programmatic dependent launch (prologue overlaps the previous

@@ -32,7 +32,7 @@ static bool g_wave_balance = true;
 bool wave_balance_enabled() { return g_wave_balance; }
 static int g_sub_cols = 0;  // config ids k*1000 + id additionally cap the per-warp sub-tile of gather_gemv at k*256 columns
 int sub_cols_override() { return g_sub_cols; }
-static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1, 1, 0, 0};  // generation 1, no speculation, per-line prefetch, FHFMA, own K chunks
+static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1, 1, 0, 0, 0};  // generation 1, no speculation, per-line prefetch, FHFMA, own K chunks, no opts
 int tuning(int knob) { return (knob >= 0 && knob < TEAL_TUNE_COUNT) ? g_tuning[knob] : 0; }
 int set_tuning(int knob, int value) {
   if (knob < 0 || knob >= TEAL_TUNE_COUNT) return set_error(TEAL_ERR_BAD_ARG, "tuning knob out of range");
@@ -42,6 +42,7 @@ int set_tuning(int knob, int value) {
   if (knob == TEAL_TUNE_FHFMA && value != 0 && value != 1) return set_error(TEAL_ERR_BAD_ARG, "fhfma must be 0 or 1");
   if ((knob == TEAL_TUNE_ROWS_WIDE || knob == TEAL_TUNE_ROWS_NARROW) && (value < 0 || value > 4096 || (value & 31)))
     return set_error(TEAL_ERR_BAD_ARG, "rows per CTA must be a multiple of 32 in [0, 4096]");
+  if (knob == TEAL_TUNE_V1_OPTS && (value < 0 || value > 7)) return set_error(TEAL_ERR_BAD_ARG, "v1_opts is a bit mask 0..7");
   g_tuning[knob] = value;
   return TEAL_OK;
 }

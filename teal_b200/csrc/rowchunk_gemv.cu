@@ -60,6 +60,56 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p, uint64_t policy) {
   return r;
 }
 
+// f32 += f16 * f16 (FHFMA): the product of two fp16 values is exact in fp32, so this is fma(float(w), float(x), acc)
+__device__ __forceinline__ void rc_fhfma2(float2& acc, uint32_t w2, unsigned short xh) {
+#ifdef TEAL_EMU
+  const float x = __half2float(__ushort_as_half(xh));
+  acc.x = fmaf(__half2float(__ushort_as_half((unsigned short)(w2 & 0xffffu))), x, acc.x);
+  acc.y = fmaf(__half2float(__ushort_as_half((unsigned short)(w2 >> 16))), x, acc.y);
+#else
+  asm("{\n"
+      ".reg .b16 lo, hi;\n"
+      "mov.b32 {lo, hi}, %2;\n"
+      "fma.rn.f32.f16 %0, lo, %3, %0;\n"
+      "fma.rn.f32.f16 %1, hi, %3, %1;\n"
+      "}\n"
+      : "+f"(acc.x), "+f"(acc.y)
+      : "r"(w2), "h"(xh));
+#endif
+}
+#ifdef TEAL_EMU
+// the emulation touches every byte a prefetch names, so an out-of-range speculative address is caught by ASan / a fault
+__device__ __forceinline__ void rc_prefetch_l2(const void* p) { (void)*reinterpret_cast<const volatile char*>(p); }
+__device__ __forceinline__ void rc_bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  for (uint32_t i = 0; i < bytes; i += 16) (void)*(reinterpret_cast<const volatile char*>(p) + i);
+}
+__device__ __forceinline__ __half rc_ldcg_half(const __half* p) { return __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(p))); }
+__device__ __forceinline__ uint32_t rc_lds_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, uint32_t row_bytes) { return base + (uint64_t)row * row_bytes; }
+#else
+__device__ __forceinline__ void rc_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void rc_bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ __half rc_ldcg_half(const __half* p) {
+  unsigned short v;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+  return __ushort_as_half(v);
+}
+// volatile asm on purpose: the compiler must neither duplicate the address arithmetic per 16-byte load nor move the
+// list read across the weight loads
+__device__ __forceinline__ uint32_t rc_lds_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, uint32_t row_bytes) {
+  uint64_t a;
+  asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(row), "r"(row_bytes), "l"(base));
+  return a;
+}
+#endif
+
 // system-scope flag traffic of the fused TP exchange (TP instantiations)
 #ifdef TEAL_EMU
 __device__ __forceinline__ void rc_st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
@@ -90,7 +140,11 @@ __device__ __forceinline__ uint4 rc_ld_volatile_u4(const void* p) {
 // instantiation (TIMED = false) is SASS-identical to the build without the stamps (tools/sass_diff.py).
 // TP: the row-parallel projections under tensor parallelism (o / down, gpt-fast/tp.py:117,130) with the exchange step
 // (tp.py:120-121,139-140) fused into the tile finaliser -- see TpFuse.  Opt-in, not yet run on hardware.
-template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false>
+// OPT (bit mask, experiments on the validated structure, one change at a time -- TEAL_TUNE_V1_OPTS):
+//   1 = the first lane group's x and norm weights are requested before / together with the sum-of-squares partials
+//       (one L2 round trip in the head instead of two); 2 = FHFMA arithmetic instead of conversions + FFMA2;
+//   4 = 32-bit row offsets (one IMAD.WIDE.U32 per row instead of 64-bit multiplies per 16-byte load).
+template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false, int OPT = 0>
 __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
   long long* const dbg = TIMED ? p.dbg_time + (size_t)blockIdx.x * 16 : nullptr;
@@ -125,9 +179,19 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
   const long long ldw = sg.ldw;
   const uint64_t policy = make_evict_first_policy();
 
+  [[maybe_unused]] __half early_nw = __ushort_as_half((unsigned short)0), early_x = __ushort_as_half((unsigned short)0);
+  [[maybe_unused]] const int early_k = kc * p.rows_per_cta + warp * 32 + lane;
+  [[maybe_unused]] const bool early_ok = early_k < min(p.Z, (kc + 1) * p.rows_per_cta);
+  if constexpr ((OPT & 1) != 0) {
+    if (early_ok && p.in_mode == kInRmsNorm) early_nw = p.norm_w[early_k];  // a constant: before the producer is done
+  }
+
   griddep_wait();                 // PDL: everything above overlapped the previous kernel's tail
   griddep_launch_dependents();    // the next kernel may start launching once all our CTAs are running
   stamp(1);
+  if constexpr ((OPT & 1) != 0) {
+    if (early_ok) early_x = rc_ldcg_half(p.x + early_k);  // in flight together with the sum-of-squares partials below
+  }
 
   // ---- RMSNorm scale from the producer's per-tile sums of squares (gpt-fast/model.py:286-291) --------
   float rs = 1.f;
@@ -152,10 +216,11 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     const int k = k0 + lane;
     float xf = 0.f;
     if (k < kend) {
-      const __half xh = p.x[k];
+      const bool early = (OPT & 1) != 0 && k0 == kbeg + warp * 32;
+      const __half xh = early ? early_x : p.x[k];
       if (p.in_mode == kInRmsNorm) {
         // fp32 norm, cast to fp16, multiply by the fp16 weight in fp16
-        xf = __half2float(__hmul(__float2half_rn(__half2float(xh) * rs), p.norm_w[k]));
+        xf = __half2float(__hmul(__float2half_rn(__half2float(xh) * rs), early ? early_nw : p.norm_w[k]));
         if (p.x_out && ct == 0) p.x_out[k] = __float2half_rn(xf);
       } else {
         xf = __half2float(xh);
@@ -176,7 +241,11 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
         bit[u] = mask ? (__ffs(mask) - 1) : -1;
         mask &= mask - 1;  // no-op when mask == 0
         if (bit[u] >= 0) {
-          const __half* src = wbase + (long long)(k0 + bit[u]) * ldw;
+          const __half* src;
+          if constexpr ((OPT & 4) != 0)
+            src = reinterpret_cast<const __half*>(rc_row_address(reinterpret_cast<uint64_t>(wbase), (uint32_t)(k0 + bit[u]), (uint32_t)ldw * 2u));
+          else
+            src = wbase + (long long)(k0 + bit[u]) * ldw;
 #pragma unroll
           for (int v = 0; v < VEC; ++v)
             if (vact[v]) wv[u][v] = ld_stream_u4(src + 256 * v, policy);
@@ -187,9 +256,17 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
         if (bit[u] >= 0) {
           const float xs = __shfl_sync(0xffffffffu, xf, bit[u]);
           const float2 x2 = make_float2(xs, xs);
+          [[maybe_unused]] const unsigned short xb = __half_as_ushort(__float2half_rn(xs));  // exact: xs is an fp16 value
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
-            if (vact[v]) {
+            if constexpr ((OPT & 2) != 0) {
+              if (vact[v]) {
+                rc_fhfma2(acc[v][0], wv[u][v].x, xb);
+                rc_fhfma2(acc[v][1], wv[u][v].y, xb);
+                rc_fhfma2(acc[v][2], wv[u][v].z, xb);
+                rc_fhfma2(acc[v][3], wv[u][v].w, xb);
+              }
+            } else if (vact[v]) {
               rc_ffma2(acc[v][0], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].x)), x2);
               rc_ffma2(acc[v][1], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].y)), x2);
               rc_ffma2(acc[v][2], __half22float2(*reinterpret_cast<const __half2*>(&wv[u][v].z)), x2);
@@ -541,57 +618,6 @@ __device__ __forceinline__ void rc2_finish_warp(const RcParams& p, const RcSeg& 
   (void)COLS;
 }
 
-namespace {
-// f32 += f16 * f16 (FHFMA): the product of two fp16 values is exact in fp32, so this is fma(float(w), float(x), acc)
-__device__ __forceinline__ void rc_fhfma2(float2& acc, uint32_t w2, unsigned short xh) {
-#ifdef TEAL_EMU
-  const float x = __half2float(__ushort_as_half(xh));
-  acc.x = fmaf(__half2float(__ushort_as_half((unsigned short)(w2 & 0xffffu))), x, acc.x);
-  acc.y = fmaf(__half2float(__ushort_as_half((unsigned short)(w2 >> 16))), x, acc.y);
-#else
-  asm("{\n"
-      ".reg .b16 lo, hi;\n"
-      "mov.b32 {lo, hi}, %2;\n"
-      "fma.rn.f32.f16 %0, lo, %3, %0;\n"
-      "fma.rn.f32.f16 %1, hi, %3, %1;\n"
-      "}\n"
-      : "+f"(acc.x), "+f"(acc.y)
-      : "r"(w2), "h"(xh));
-#endif
-}
-#ifdef TEAL_EMU
-// the emulation touches every byte a prefetch names, so an out-of-range speculative address is caught by ASan / a fault
-__device__ __forceinline__ void rc_prefetch_l2(const void* p) { (void)*reinterpret_cast<const volatile char*>(p); }
-__device__ __forceinline__ void rc_bulk_prefetch_l2(const void* p, uint32_t bytes) {
-  for (uint32_t i = 0; i < bytes; i += 16) (void)*(reinterpret_cast<const volatile char*>(p) + i);
-}
-__device__ __forceinline__ __half rc_ldcg_half(const __half* p) { return __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(p))); }
-__device__ __forceinline__ uint32_t rc_lds_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
-__device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, uint32_t row_bytes) { return base + (uint64_t)row * row_bytes; }
-#else
-__device__ __forceinline__ void rc_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void rc_bulk_prefetch_l2(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ __half rc_ldcg_half(const __half* p) {
-  unsigned short v;
-  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
-  return __ushort_as_half(v);
-}
-// volatile asm on purpose: the compiler must neither duplicate the address arithmetic per 16-byte load nor move the
-// list read across the weight loads
-__device__ __forceinline__ uint32_t rc_lds_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, uint32_t row_bytes) {
-  uint64_t a;
-  asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(row), "r"(row_bytes), "l"(base));
-  return a;
-}
-#endif
-}  // namespace
 
 // The gather loop of generation 2.  `list` (shared-space address) holds n entries {fp16 bits of x | lane offset << 16};
 // row i+U is requested as soon as row i has been consumed (ring slot i % U, statically indexed by the unrolled u).
@@ -967,6 +993,19 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
         return set_error(TEAL_ERR_ALIGNMENT, "fused TP exchange: null / unaligned peer pointer");
     p.tp = *gp.tp;
     kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, true> : rowchunk_gemv_kernel<1, 8, 2, false, true>;
+  } else if (const int opts = forced_config() ? 0 : tuning(TEAL_TUNE_V1_OPTS); opts && (variant == 1 || variant == 2)) {
+    // one experimental change at a time on the validated structure (see the OPT template parameter)
+    using K = void (*)(const RcParams);
+#define TEAL_OPT_ROW(V, UU, W) {nullptr, rowchunk_gemv_kernel<V, UU, W, false, false, 1>, rowchunk_gemv_kernel<V, UU, W, false, false, 2>, \
+                                rowchunk_gemv_kernel<V, UU, W, false, false, 3>, rowchunk_gemv_kernel<V, UU, W, false, false, 4>,          \
+                                rowchunk_gemv_kernel<V, UU, W, false, false, 5>, rowchunk_gemv_kernel<V, UU, W, false, false, 6>,          \
+                                rowchunk_gemv_kernel<V, UU, W, false, false, 7>}
+    static const K kOpt[2][8] = {TEAL_OPT_ROW(2, 4, 4), TEAL_OPT_ROW(1, 8, 2)};
+#undef TEAL_OPT_ROW
+    if (opts & 4)
+      for (int s = 0; s < p.nseg && gp.mode != kModeSurvivors; ++s)
+        if (p.seg[s].ldw <= 0 || p.seg[s].ldw >= (1ll << 30)) return set_error(TEAL_ERR_UNSUPPORTED, "32-bit row offsets: ldw out of range");
+    kern = kOpt[variant - 1][opts & 7];
   } else if ((variant == 1 || variant == 2) && grid <= kTimelineMaxCtas) {  // profiling: the two default variants have a TIMED twin
     if (long long* slot = next_debug_timeline_slot()) {           // teal_set_debug_timeline: one slot per launch, in launch order
       p.dbg_time = slot;

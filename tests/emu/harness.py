@@ -73,12 +73,12 @@ def set_config(cfg):
     check(lib().teal_set_config(int(cfg)), "teal_set_config")
 
 
-KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5}
+KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5, "v1_opts": 6}
 
 
-def set_tuning(generation=1, spec_rows=0, spec_mode=1, fhfma=1, rows_wide=0, rows_narrow=0):
+def set_tuning(generation=1, spec_rows=0, spec_mode=1, fhfma=1, rows_wide=0, rows_narrow=0, v1_opts=0):
     for k, v in (("generation", generation), ("spec_rows", spec_rows), ("spec_mode", spec_mode), ("fhfma", fhfma),
-                 ("rows_wide", rows_wide), ("rows_narrow", rows_narrow)):
+                 ("rows_wide", rows_wide), ("rows_narrow", rows_narrow), ("v1_opts", v1_opts)):
         check(lib().teal_set_tuning(KNOBS[k], int(v)), f"teal_set_tuning({k})")
 
 

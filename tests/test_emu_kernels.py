@@ -451,3 +451,13 @@ def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
     got = torch.from_numpy(xs[0].copy()).float()
     assert ((got - want.float()).abs() <= want.float().abs() * 2.0 ** -8 + 8e-3).all(), float((got - want.float()).abs().max())
     assert abs(float(ssq[0].sum()) - float((got ** 2).sum())) <= 1e-3 * float((got ** 2).sum())
+
+
+@pytest.mark.parametrize("opts", [1, 2, 3, 4, 5, 6, 7])
+def test_generation1_one_change_at_a_time(opts):
+    """TEAL_TUNE_V1_OPTS: early x / norm-weight requests, FHFMA, 32-bit row offsets on the validated kernel structure."""
+    H.set_tuning(v1_opts=opts, rows_narrow=96 if opts & 1 else 0)     # (96: a warp owns a ragged second lane group)
+    for Z, N in SHAPES[:4]:
+        _check_gemv(Z, N, 0.6745, seed=opts)
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    _run_and_compare(dec, True, lambda: dec.step(True))

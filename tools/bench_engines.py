@@ -31,7 +31,7 @@ SWEEP4 = [dict(tiles_per_item=2), dict(tiles_per_item=4), dict(tiles_per_item=2,
           dict(tiles_per_item=2, warps=2, rows_small=64, rows_large=64), dict(tiles_per_item=4, warps=2, rows_small=64, rows_large=64),
           dict(tiles_per_item=4, wide_melems=1), dict(tiles_per_item=2, wide_melems=1, opts=4),
           dict(tiles_per_item=4, group_gate_up=16, group_qkv=8)]
-GRAPH_TUNES = [dict(rows_wide=256), dict(rows_wide=96), dict(rows_narrow=128), dict(rows_narrow=32), dict(rows_wide=256, rows_narrow=128),
+GRAPH_TUNES = [dict(v1_opts=1), dict(v1_opts=2), dict(v1_opts=4), dict(v1_opts=5), dict(v1_opts=7), dict(rows_wide=256), dict(rows_wide=96), dict(rows_narrow=128), dict(rows_narrow=32), dict(rows_wide=256, rows_narrow=128),
                dict(generation=2), dict(generation=2, fhfma=0), dict(generation=2, fhfma=0, rows_wide=256), dict(generation=2, rows_wide=256, rows_narrow=128),
                dict(generation=2, spec_rows=2), dict(generation=2, spec_rows=4), dict(generation=2, spec_rows=8),
                dict(generation=2, spec_rows=8, spec_mode=2), dict(generation=2, spec_rows=16, spec_mode=2), dict(generation=3),

@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import teal_b200.ops as ops  # noqa: E402
 from teal_b200.model import ModelArgs, SparseDecoder  # noqa: E402
 
-TUNES = [dict(generation=2), dict(generation=2, fhfma=0), dict(generation=3), dict(generation=2, spec_rows=4), dict(generation=3, spec_rows=8, spec_mode=2),
+TUNES = [dict(v1_opts=1), dict(v1_opts=2), dict(v1_opts=4), dict(v1_opts=7), dict(generation=2, fhfma=0), dict(rows_wide=256), dict(generation=2), dict(generation=3), dict(generation=2, spec_rows=4), dict(generation=3, spec_rows=8, spec_mode=2),
          dict(generation=2, spec_rows=8), dict(generation=3, spec_rows=4)]
 
 
