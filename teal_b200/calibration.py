@@ -17,20 +17,24 @@ import torch
 
 
 def find_histogram(acts: torch.Tensor, num_bins: int = 10000, outlier_threshold: float = 0.01):
-    """counts, bin_centers exactly as utils/utils.py:145-173: sort; the 1 % / 99 % order statistics bound
-    ``num_bins - 2`` uniform bins (``linspace(lower, upper, num_bins - 1)`` edges), one bin on either side catches the
-    outliers out to the extreme values; centres are edge mid-points.  Both fp32."""
-    acts = acts.flatten().detach().float()
-    acts = torch.sort(acts)[0]
-    n = len(acts)
-    lower_bound = acts[int(outlier_threshold * n)]
-    upper_bound = acts[-int(outlier_threshold * n)]
-    acts = acts.cpu()
-    main_bins = torch.linspace(lower_bound.cpu(), upper_bound.cpu(), num_bins - 1)
-    bins = torch.cat([torch.tensor([acts[0]]), main_bins, torch.tensor([acts[-1]])])
-    counts, _ = torch.histogram(acts, bins=bins)
-    bin_centers = (bins[:-1] + bins[1:]) / 2
-    return counts.float(), bin_centers.float()
+    """(counts, bin_centers), both fp32, in the format `Distribution` reads -- the numbers of utils/utils.py:145-173:
+    ``num_bins - 2`` uniform bins between the 1 % and 99 % order statistics plus one catch-all bin on either side out
+    to the extreme values; centres are the edge mid-points.
+
+    The values are sorted once (needed for the order statistics anyway), so the counts are differences of the edges'
+    insertion points in the sorted array instead of a second pass (`torch.histogram` semantics: bins are
+    [e_i, e_{i+1}), the last one closed)."""
+    v = torch.sort(acts.detach().flatten().float())[0]
+    n = v.numel()
+    cut = int(outlier_threshold * n)
+    lo, hi = v[cut], v[n - cut] if cut else v[0]   # v[-0] is v[0] in the reference's indexing, too
+    edges = torch.cat([v[:1].cpu(), torch.linspace(lo.cpu(), hi.cpu(), num_bins - 1), v[-1:].cpu()])
+    at = torch.searchsorted(v, edges.to(v.device), right=False)   # values < edge
+    at[-1] = n                                                     # last bin is closed on the right
+    at[0] = 0
+    counts = (at[1:] - at[:-1]).clamp_(min=0).to(torch.float32).cpu()
+    centers = ((edges[:-1] + edges[1:]) / 2).to(torch.float32)
+    return counts, centers
 
 
 class ActivationModule:
