@@ -205,6 +205,8 @@ def main():
     if world > 1:
         config["tp_exchange"] = ("fused into the row-parallel GEMV finalisers" if getattr(dec, "tp_gemv", False) else
                                  "one-shot peer-memory kernel" if dec.tp_fused else "nccl all-reduce")
+    if getattr(dec, "chain_mlp", False):
+        config["chain_mlp"] = "flag-chained gate/up -> down (TEAL_CHAIN_MLP=1)"
     if args.temperature > 0:
         dec.set_sampling(args.temperature, args.top_k, seed=0)
         config["sampling"] = f"top_k={args.top_k} temperature={args.temperature} (generate.py:49-66 on device)"

@@ -149,6 +149,18 @@ int teal_tp_allreduce_residual_f16(const void* const* peer_partials, void* const
  * the reference returns).  One CTA, four passes over the L2-resident logits, graph-capturable. */
 int teal_sample_topk_f16(const void* logits, int V, double temperature, int top_k, const void* noise_f16, uint64_t seed,
                          const int32_t* pos, void* argmax_packed, void* probs_out, void* stream);
+/* Flag-chained MLP pair (opt-in; checked on the CPU emulation with the two launches running concurrently, not yet run
+ * on hardware).  Same arithmetic as teal_norm_sparse_gate_up_f16 followed by teal_sparse_gemv_residual_f16 on the same
+ * workspace and stream, but the second launch does not wait for the first grid to finish: the gate/up finalisers
+ * release h tile by tile (CTAs run group-major so that the first tiles are final early) and every down-projection
+ * CTA waits only for the h tiles that cover its K chunk.  Both calls must use the library's default dispatch, be
+ * issued back to back (PDL enabled) with Z = dim, I = intermediate size, N = dim; ssq_in is required. */
+int teal_norm_sparse_gate_up_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
+                                       const void* w3t, void* h, int Z, int I, int64_t ldw1, int64_t ldw3, double threshold_gate,
+                                       double threshold_up, void* workspace, size_t workspace_bytes, void* stream);
+int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const void* resid, void* y, float* ssq_out, int I, int N,
+                                        int64_t ldw, double threshold, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Row-parallel projection (o / down under tensor parallelism, gpt-fast/tp.py:117,130) with its exchange step
  * (tp.py:120-121,139-140) and the residual add (model.py:160-161) in ONE kernel: resid_x[N] += sum over ranks of the
  * rank's partial y = W_shard * mask(x_shard), in place, plus the per-tile sums of squares for the next RMSNorm.  The
@@ -290,9 +302,11 @@ int teal_set_config(int config_id);
  *   TEAL_TUNE_ROWS_WIDE / TEAL_TUNE_ROWS_NARROW   input lanes (K chunk) per CTA of the wide-tile (>= 40 M-element
  *                         launches) / narrow-tile default variant; 0 = the variant's own size with wave balancing
  *   TEAL_TUNE_V1_OPTS     generation 1 with ONE change at a time (bit mask): 1 = x / norm weights requested together with
- *                         the sum-of-squares partials, 2 = FHFMA arithmetic, 4 = 32-bit row offsets */
+ *                         the sum-of-squares partials, 2 = FHFMA arithmetic, 4 = 32-bit row offsets
+ *   TEAL_TUNE_WIDE_KELEMS  launches of at least this many thousand weight elements use the wide-tile (512-column) variant
+ *                         (0 = the measured default, 40 000) */
 enum { TEAL_TUNE_GENERATION = 0, TEAL_TUNE_SPEC_ROWS = 1, TEAL_TUNE_SPEC_MODE = 2, TEAL_TUNE_FHFMA = 3, TEAL_TUNE_ROWS_WIDE = 4,
-       TEAL_TUNE_ROWS_NARROW = 5, TEAL_TUNE_V1_OPTS = 6, TEAL_TUNE_COUNT = 7 };
+       TEAL_TUNE_ROWS_NARROW = 5, TEAL_TUNE_V1_OPTS = 6, TEAL_TUNE_WIDE_KELEMS = 7, TEAL_TUNE_COUNT = 8 };
 int teal_set_tuning(int knob, int value);
 
 /* Launch the GEMV kernels with programmatic dependent launch (prologue overlaps the previous

@@ -49,6 +49,11 @@ _SIGS = {
                                                  _c.c_void_p, _c.c_int, _c.c_void_p]),
     "teal_sample_topk_f16": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_int, _c.c_void_p, _c.c_uint64, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p]),
+    "teal_norm_sparse_gate_up_chain_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                      _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _c.c_double, _c.c_double,
+                                                      _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "teal_sparse_gemv_residual_chain_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                                       _c.c_int, _c.c_int64, _c.c_double, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "teal_sparse_gemv_tp_exchange_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
                                                     _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                                     _c.c_size_t, _c.c_void_p]),

@@ -237,6 +237,42 @@ int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* res
   return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- flag-chained MLP pair (opt-in): gate/up releases h tile by tile, down starts on the tiles it needs ------------
+int teal_norm_sparse_gate_up_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
+                                       const void* w3t, void* h, int Z, int I, int64_t ldw1, int64_t ldw3, double threshold_gate,
+                                       double threshold_up, void* workspace, size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, h, Z)) return rc;
+  if (!w1t || !w3t || !h || !norm_w || !ssq_in || I <= 0 || ldw1 < I || ldw3 < I)
+    return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / h / norm_w / ssq_in / I / ldw");
+  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
+  p.mode = kModePairSilu;
+  if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
+  p.nseg = 2;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
+  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, slot_for(p, round_threshold_fp16(threshold_up)), 0, 0, 0};
+  p.chain = 1;
+  chain_describe(Z, I, &p.chain_rows, &p.chain_ctiles, &p.chain_cols);
+  return dispatch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const void* resid, void* y, float* ssq_out, int I, int N,
+                                        int64_t ldw, double threshold, void* workspace, size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, h, y, I)) return rc;
+  if (!wt || !y || !resid || N <= 0 || ldw < N) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw");
+  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
+  p.mode = kModePlain;
+  p.out_mode = kOutAddResidual;
+  p.resid = reinterpret_cast<const __half*>(resid);
+  p.ssq_out = ssq_out;
+  p.nseg = 1;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
+  p.chain = 2;
+  chain_describe(N, I, &p.chain_rows, &p.chain_ctiles, &p.chain_cols);
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
                                      double threshold, void* const* peer_partials, void* const* peer_flags, void* epoch_tiles,
                                      int rank, int world, void* workspace, size_t workspace_bytes_, void* stream) {

@@ -58,6 +58,8 @@ struct GemvParams {
   GemvSeg seg[kMaxSeg];
   // appended (the offsets above are those of the hardware-validated build of the kernels that take GemvParams by value)
   const struct TpFuse* tp;  // optional (host pointer): fuse the TP exchange into the finaliser (row-parallel o / down)
+  int chain;                // 0 | 1 = producer of a flag-chained pair (gate/up) | 2 = its consumer (down): see RcParams
+  int chain_rows, chain_ctiles, chain_cols;  // consumer K chunk, consumer column tiles, producer tile width (lanes of h)
 };
 
 // ---- gather_gemv (cp.async per-warp rings) ------------------------------------------------------
@@ -142,6 +144,10 @@ struct RcParams {
   int spec_mode;       // 1 = prefetch.global.L2 per 128-byte line, 2 = cp.async.bulk.prefetch.L2 per row segment
   long long* dbg_time; // TIMED instantiations: [grid][16] globaltimer stamps (teal_set_debug_timestamps)
   TpFuse tp;           // TP instantiations only
+  // CHAIN instantiations (flag-chained launches: the consumer grid never executes griddepcontrol.wait, it waits for the
+  // producer's tiles): ready[j] = number of consumer CTAs that still have to read h tile j (0 = not produced yet)
+  unsigned* chain_ready;
+  int chain_rows, chain_ctiles, chain_cols, chain_group;
 };
 constexpr int kRc2MaxPass = 4;  // 32-lane groups one warp of a generation-2 CTA may own
 
@@ -170,6 +176,7 @@ void set_pdl(bool on);
 bool pdl_enabled();
 int sub_cols_override();
 bool wave_balance_enabled();
+void chain_describe(int dim, int inter, int* rows_c, int* ctiles_c, int* cols_p);
 int set_tuning(int knob, int value);
 int tuning(int knob);
 void set_bytes_probe(unsigned long long* p);

@@ -32,7 +32,7 @@ static bool g_wave_balance = true;
 bool wave_balance_enabled() { return g_wave_balance; }
 static int g_sub_cols = 0;  // config ids k*1000 + id additionally cap the per-warp sub-tile of gather_gemv at k*256 columns
 int sub_cols_override() { return g_sub_cols; }
-static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1, 1, 0, 0, 0};  // generation 1, no speculation, per-line prefetch, FHFMA, own K chunks, no opts
+static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1, 1, 0, 0, 0, 0};  // generation 1, no speculation, per-line prefetch, FHFMA, own K chunks, no opts
 int tuning(int knob) { return (knob >= 0 && knob < TEAL_TUNE_COUNT) ? g_tuning[knob] : 0; }
 int set_tuning(int knob, int value) {
   if (knob < 0 || knob >= TEAL_TUNE_COUNT) return set_error(TEAL_ERR_BAD_ARG, "tuning knob out of range");
@@ -42,10 +42,13 @@ int set_tuning(int knob, int value) {
   if (knob == TEAL_TUNE_FHFMA && value != 0 && value != 1) return set_error(TEAL_ERR_BAD_ARG, "fhfma must be 0 or 1");
   if ((knob == TEAL_TUNE_ROWS_WIDE || knob == TEAL_TUNE_ROWS_NARROW) && (value < 0 || value > 4096 || (value & 31)))
     return set_error(TEAL_ERR_BAD_ARG, "rows per CTA must be a multiple of 32 in [0, 4096]");
+  if (knob == TEAL_TUNE_WIDE_KELEMS && value < 0) return set_error(TEAL_ERR_BAD_ARG, "wide_kelems must be >= 0");
   if (knob == TEAL_TUNE_V1_OPTS && (value < 0 || value > 7)) return set_error(TEAL_ERR_BAD_ARG, "v1_opts is a bit mask 0..7");
   g_tuning[knob] = value;
   return TEAL_OK;
 }
+
+static long long wide_min_elems() { return g_tuning[TEAL_TUNE_WIDE_KELEMS] > 0 ? 1000ll * g_tuning[TEAL_TUNE_WIDE_KELEMS] : 40ll * 1000 * 1000; }
 
 int set_config(int id) {
   g_wave_balance = true;
@@ -65,25 +68,34 @@ int set_config(int id) {
 // implement the sum-of-squares hand-off, so the fused-RMSNorm entry points always use rowchunk_gemv.
 int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_total, cudaStream_t stream) {
   const int id = g_forced_config;
-  const bool needs_rc = p.in_mode != kInPlain || p.ssq_out || p.keep_out || p.mode == kModeSurvivors || p.tp;
+  const bool needs_rc = p.in_mode != kInPlain || p.ssq_out || p.keep_out || p.mode == kModeSurvivors || p.tp || p.chain;
   if (id >= 1 && id <= kNumTmaConfigs && !needs_rc && p.out_mode == kOutPlain && !p.x_out)
     return launch_gemv(p, workspace, ws_bytes, out_cols_total, stream);
   if (id >= 11 && id <= 26 && !needs_rc)
     return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, id - 10);
   int variant;
-  if (id >= 30 && id <= 59 && (!p.tp || id == 31 || id == 32)) {  // (the fused TP exchange exists for variants 1 and 2)
+  if (id >= 30 && id <= 59 && ((!p.tp && !p.chain) || id == 31 || id == 32)) {  // (the fused TP exchange exists for variants 1 and 2)
     variant = id - 30;
   } else {  // measured on B200 (profiles/r01_bench_gemv_history.jsonl): wide tiles pay off once a launch moves >= ~40 MB
     long long elems = 0;
     for (int s = 0; s < p.nseg; ++s) elems += (long long)p.Z * p.seg[s].ncols;
-    variant = (elems >= 40ll * 1000 * 1000) ? 1 : 2;
-    if (p.tp) {
-      // the fused TP exchange lives in the default generation's finaliser
+    variant = (elems >= wide_min_elems()) ? 1 : 2;
+    if (p.tp || p.chain) {
+      // the fused TP exchange and the flag-chained pair live in the default generation
     } else if (g_tuning[TEAL_TUNE_GENERATION] == 2)  // opt-in, see rowchunk_gemv2_kernel
       variant = g_tuning[TEAL_TUNE_FHFMA] ? ((variant == 1) ? 13 : 15) : ((variant == 1) ? 12 : 14);
-    if (!p.tp && g_tuning[TEAL_TUNE_GENERATION] == 3) variant = (variant == 1) ? 20 : 21;  // ... with warp-wise completion
+    if (!p.tp && !p.chain && g_tuning[TEAL_TUNE_GENERATION] == 3) variant = (variant == 1) ? 20 : 21;  // ... with warp-wise completion
   }
   return launch_rowchunk(p, workspace, ws_bytes, out_cols_total, stream, variant);
+}
+
+// Tiling of a flag-chained MLP pair, derived once for both launches with the default dispatch's size rule: the producer
+// (gate/up, Z = dim, 2 x inter columns) must know the consumer's (down, Z = inter, dim columns) K chunk and tile count.
+void chain_describe(int dim, int inter, int* rows_c, int* ctiles_c, int* cols_p) {
+  const bool wide_p = (long long)dim * 2 * inter >= wide_min_elems(), wide_c = (long long)inter * dim >= wide_min_elems();
+  *cols_p = wide_p ? 512 : 256;
+  *rows_c = wide_c ? 128 : 64;
+  *ctiles_c = (dim + (wide_c ? 512 : 256) - 1) / (wide_c ? 512 : 256);
 }
 
 size_t workspace_bytes(int max_out_cols) {

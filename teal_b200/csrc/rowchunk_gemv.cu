@@ -110,6 +110,20 @@ __device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, 
 }
 #endif
 
+// gpu-scope flag traffic of the flag-chained launches (CHAIN instantiations)
+#ifdef TEAL_EMU
+__device__ __forceinline__ void rc_st_release_gpu(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned rc_ld_acquire_gpu(const unsigned* p) { ::emu::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+#else
+__device__ __forceinline__ void rc_st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned rc_ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#endif
 // system-scope flag traffic of the fused TP exchange (TP instantiations)
 #ifdef TEAL_EMU
 __device__ __forceinline__ void rc_st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
@@ -144,7 +158,14 @@ __device__ __forceinline__ uint4 rc_ld_volatile_u4(const void* p) {
 //   1 = the first lane group's x and norm weights are requested before / together with the sum-of-squares partials
 //       (one L2 round trip in the head instead of two); 2 = FHFMA arithmetic instead of conversions + FFMA2;
 //   4 = 32-bit row offsets (one IMAD.WIDE.U32 per row instead of 64-bit multiplies per 16-byte load).
-template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false, int OPT = 0>
+// CHAIN (flag-chained launches; opt-in, not yet run on hardware): 1 = producer of the MLP pair
+//   (gate/up): CTAs run group-major (a group of tile pairs x all K chunks, so tiles complete early) and the finaliser of
+//   pair tile j releases ready[j] = #consumer CTAs; 2 = consumer (down): launched with the PDL attribute but WITHOUT
+//   griddepcontrol.wait -- every CTA waits for the h tiles that cover its K chunk, reads them at L2 and counts
+//   ready[j] down again (the cell is back to 0 when the step is over: nothing to reset, graph-replayable).  Safe
+//   because every producer CTA issued launch_dependents when it started: by the time a consumer CTA exists, all
+//   producer CTAs are resident or done, and everything older than the producer is complete.
+template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false, int OPT = 0, int CHAIN = 0>
 __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
   long long* const dbg = TIMED ? p.dbg_time + (size_t)blockIdx.x * 16 : nullptr;
@@ -163,8 +184,16 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // ---- which (column tile, K chunk) is mine: column tile varies fastest so that concurrently running
   // CTAs read neighbouring pieces of the same weight rows ---------------------------------------------
-  const int ct = (int)(blockIdx.x % (unsigned)p.total_ctiles);
-  const int kc = (int)(blockIdx.x / (unsigned)p.total_ctiles);
+  int ct = (int)(blockIdx.x % (unsigned)p.total_ctiles);
+  int kc = (int)(blockIdx.x / (unsigned)p.total_ctiles);
+  if constexpr (CHAIN == 1) {  // group-major: order position -> (gate tile j, up tile j neighbours), K chunk slow inside a group
+    const int T = p.total_ctiles, G = p.chain_group, per = G * p.nkchunks;
+    const int g = (int)blockIdx.x / per, r = (int)blockIdx.x - g * per;
+    const int gsz = min(G, T - g * G);
+    kc = r / gsz;
+    const int pos = g * G + (r - kc * gsz);
+    ct = (pos & 1) ? (T >> 1) + (pos >> 1) : (pos >> 1);
+  }
   int s = 0;
 #pragma unroll
   for (int j = 1; j < kMaxSeg; ++j) s += (j < p.nseg && ct >= p.seg[j].ctile0) ? 1 : 0;
@@ -186,8 +215,23 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     if (early_ok && p.in_mode == kInRmsNorm) early_nw = p.norm_w[early_k];  // a constant: before the producer is done
   }
 
-  griddep_wait();                 // PDL: everything above overlapped the previous kernel's tail
-  griddep_launch_dependents();    // the next kernel may start launching once all our CTAs are running
+  if constexpr (CHAIN == 2) {
+    griddep_launch_dependents();
+    // the h tiles covering my K chunk: one polling thread per tile
+    const int cb = kc * p.rows_per_cta, ce = min(p.Z, cb + p.rows_per_cta);
+    const int t0 = cb / p.chain_cols, t1 = (ce - 1) / p.chain_cols;
+    if (tid <= t1 - t0) {
+      const unsigned* cell = p.chain_ready + t0 + tid;
+      const long long w0 = clock64();
+      while (rc_ld_acquire_gpu(cell) == 0u) {
+        if (clock64() - w0 > 4000000000ll) __trap();  // a protocol bug traps instead of hanging the GPU
+      }
+    }
+    __syncthreads();
+  } else {
+    griddep_wait();                 // PDL: everything above overlapped the previous kernel's tail
+    griddep_launch_dependents();    // the next kernel may start launching once all our CTAs are running
+  }
   stamp(1);
   if constexpr ((OPT & 1) != 0) {
     if (early_ok) early_x = rc_ldcg_half(p.x + early_k);  // in flight together with the sum-of-squares partials below
@@ -217,7 +261,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     float xf = 0.f;
     if (k < kend) {
       const bool early = (OPT & 1) != 0 && k0 == kbeg + warp * 32;
-      const __half xh = early ? early_x : p.x[k];
+      const __half xh = early ? early_x : (CHAIN == 2 ? rc_ldcg_half(p.x + k) : p.x[k]);  // (chained: written by a grid that is still running -> L2)
       if (p.in_mode == kInRmsNorm) {
         // fp32 norm, cast to fp16, multiply by the fp16 weight in fp16
         xf = __half2float(__hmul(__float2half_rn(__half2float(xh) * rs), early ? early_nw : p.norm_w[k]));
@@ -299,6 +343,11 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     *reinterpret_cast<float4*>(d + 4) = make_float4(acc[v][2].x, acc[v][2].y, acc[v][3].x, acc[v][3].y);
   }
   __syncthreads();
+  if constexpr (CHAIN == 2) {  // every warp has consumed its lanes of h: this CTA is done with the tiles it waited for
+    const int cb = kc * p.rows_per_cta, ce = min(p.Z, cb + p.rows_per_cta);
+    const int t0 = cb / p.chain_cols, t1 = (ce - 1) / p.chain_cols;
+    if (tid <= t1 - t0) atomicSub(p.chain_ready + t0 + tid, 1u);
+  }
   const int acc0 = sg.acc_col0 + col0;
   for (int c = tid * 4; c < wcols; c += kRcThreads * 4) {
     float4 a = *reinterpret_cast<const float4*>(&s_red[0][c]);
@@ -349,6 +398,15 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       o.x = *reinterpret_cast<const uint32_t*>(&h0);
       o.y = *reinterpret_cast<const uint32_t*>(&h1);
       *reinterpret_cast<uint2*>(p.y + col0 + c) = o;
+    }
+    if constexpr (CHAIN == 1) {  // h tile `cidx` is final: release it to the consumer CTAs whose K chunks overlap it
+      __syncthreads();
+      if (tid == 0) {
+        const int lo = cidx * COLS, hi = min(sg.ncols, lo + COLS) - 1;
+        const unsigned readers = (unsigned)((hi / p.chain_rows - lo / p.chain_rows + 1) * p.chain_ctiles);
+        __threadfence();
+        rc_st_release_gpu(p.chain_ready + cidx, readers);
+      }
     }
   } else if constexpr (TP) {
     // ---- fused TP exchange of this column tile -----------------------------------------------------------------
@@ -933,7 +991,8 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (gp.ssq_out && ctile0 > kSsqParts) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out: more column tiles than TEAL_SSQ_PARTS");
   // Wave quantisation: pick the K-chunk so that the grid is (just under) a whole number of full waves of
   // resident CTAs -- 1792 CTAs on 1036 slots ran 1.73 waves, i.e. the second wave left 27 % of the chip idle.
-  const int rows_forced = forced_config() ? 0 : tuning(vec == 2 ? TEAL_TUNE_ROWS_WIDE : TEAL_TUNE_ROWS_NARROW);  // experiments only
+  int rows_forced = forced_config() ? 0 : tuning(vec == 2 ? TEAL_TUNE_ROWS_WIDE : TEAL_TUNE_ROWS_NARROW);  // experiments only
+  if (gp.chain == 2) rows_forced = gp.chain_rows;  // the producer was told this K chunk (ready[] counts depend on it)
   if (rows_forced > 0) {
     rows = rows_forced;
     if (var.gen == 2 && rows > 32 * kRc2MaxPass * var.warps) rows = 32 * kRc2MaxPass * var.warps;
@@ -980,7 +1039,28 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (grid > 0x7fffffffll) return set_error(TEAL_ERR_UNSUPPORTED, "grid too large");
 
   void (*kern)(const RcParams) = var.kern;
-  if (gp.tp) {  // row-parallel projection with the TP exchange fused into the tile finaliser (TP twins of the defaults)
+  if (gp.chain) {  // flag-chained MLP pair (gate/up -> down): CHAIN twins of the two default variants
+    constexpr int kChainCounter0 = 2048, kChainReady0 = 3072, kChainAcc0 = 65536;  // consumer's own regions of the workspace
+    if (variant != 1 && variant != 2) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches: only the default row-chunk variants");
+    if (gp.chain_rows < 32 || gp.chain_ctiles < 1 || gp.chain_cols < 256 || gp.tp)
+      return set_error(TEAL_ERR_BAD_ARG, "chained launches: bad consumer description");
+    p.chain_ready = reinterpret_cast<unsigned*>(workspace) + kChainReady0;
+    p.chain_rows = gp.chain_rows; p.chain_ctiles = gp.chain_ctiles; p.chain_cols = gp.chain_cols;
+    if (gp.chain == 1) {
+      if (!pair || cols != gp.chain_cols || ncounters > kMaxCounters - kChainReady0 || ncounters > kChainCounter0)
+        return set_error(TEAL_ERR_BAD_ARG, "chained producer: gate/up pair whose tile width is the announced one");
+      p.chain_group = 8;  // order positions per group = 4 tile pairs: the first h tiles are final after 1/7th of an 8B launch
+      kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 1> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 1>;
+    } else {
+      const int ntiles_in = (gp.Z + gp.chain_cols - 1) / gp.chain_cols;
+      if (gp.mode != kModePlain || gp.in_mode != kInPlain || ntiles_in > kMaxCounters - kChainReady0 || ctile0 > kChainReady0 - kChainCounter0 ||
+          ws_bytes < (size_t)kMaxCounters * 4 + ((size_t)kChainAcc0 + out_cols_total) * 4 + (size_t)kSsqParts * 4 || gp.chain_ctiles != ctile0)
+        return set_error(TEAL_ERR_BAD_ARG, "chained consumer: plain-input projection, announced tiling, workspace for a second accumulator region");
+      p.counters += kChainCounter0;  // the producer grid is still running: its counters / accumulators are not ours
+      p.acc += kChainAcc0;
+      kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 2> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 2>;
+    }
+  } else if (gp.tp) {  // row-parallel projection with the TP exchange fused into the tile finaliser (TP twins of the defaults)
     if (variant != 1 && variant != 2) return set_error(TEAL_ERR_UNSUPPORTED, "fused TP exchange: only the default row-chunk variants");
     if (gp.mode != kModePlain || gp.out_mode != kOutAddResidual || gp.nseg != 1 || (gp.seg[0].ncols & 7) || (reinterpret_cast<uintptr_t>(gp.y) & 15) ||
         (reinterpret_cast<uintptr_t>(gp.resid) & 15))

@@ -16,6 +16,8 @@ PyTorch here is plumbing: device memory, the CUDA-graph capture and torch.distri
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -170,6 +172,9 @@ class SparseDecoder:
         self.ffn_inputs = None  # when a list: per-layer copies of (x, ssq) entering the MLP block (bench roofline)
         self.kernels_per_step = 0
         self.sampling = None  # None = greedy arg-max; else dict(temperature, top_k, seed): generate.py:49-66 on device
+        # opt-in (not yet run on hardware): flag-chained MLP pair -- down starts on the h tiles it needs instead of waiting
+        # for the whole gate/up grid (teal_*_chain_f16)
+        self.chain_mlp = os.environ.get("TEAL_CHAIN_MLP") == "1" and world == 1
 
     # ------------------------------------------------------------------ TP exchange buffers
     def _setup_peer_exchange(self):
@@ -406,6 +411,14 @@ class SparseDecoder:
                 n_launch += self._exchange(0, sp)
             if self.ffn_inputs is not None:
                 self.ffn_inputs.append((self.x.clone(), self.ssq.clone()))
+            if self.chain_mlp and tap is None and self.world == 1 and not self.force_tp_path:
+                chk(lib.teal_norm_sparse_gate_up_chain_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq, W["w1"].data_ptr(),
+                                                           W["w3"].data_ptr(), self.h.data_ptr(), a.dim, self.inter_l, W["w1"].stride(1),
+                                                           W["w3"].stride(1), t["gate"], t["up"], wsp, wsn, sp), "gate_up_chain")
+                chk(lib.teal_sparse_gemv_residual_chain_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(), self.x.data_ptr(), ssq,
+                                                            self.inter_l, a.dim, W["w2"].stride(1), t["down"], wsp, wsn, sp), "down_chain")
+                n_launch += 3
+                continue
             xn_out = torch.empty_like(self.x) if tap is not None else None
             chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq,
                                                  W["w1"].data_ptr(), W["w3"].data_ptr(), self.h.data_ptr(),

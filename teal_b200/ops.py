@@ -276,8 +276,8 @@ def set_config(config_id: int) -> None:
     _lib.check(_lib.load().teal_set_config(int(config_id)), "teal_set_config")
 
 
-TUNING_KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5, "v1_opts": 6}  # TEAL_TUNE_* of include/teal_b200.h
-TUNING_DEFAULTS = {"generation": 1, "spec_rows": 0, "spec_mode": 1, "fhfma": 1, "rows_wide": 0, "rows_narrow": 0, "v1_opts": 0}
+TUNING_KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5, "v1_opts": 6, "wide_kelems": 7}  # TEAL_TUNE_* of include/teal_b200.h
+TUNING_DEFAULTS = {"generation": 1, "spec_rows": 0, "spec_mode": 1, "fhfma": 1, "rows_wide": 0, "rows_narrow": 0, "v1_opts": 0, "wide_kelems": 0}
 
 
 def set_tuning(**knobs: int) -> None:

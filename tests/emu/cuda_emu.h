@@ -265,6 +265,7 @@ inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v)
   }
   return old;
 }
+inline unsigned atomicSub(unsigned* p, unsigned v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) {
   __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED);

@@ -73,12 +73,12 @@ def set_config(cfg):
     check(lib().teal_set_config(int(cfg)), "teal_set_config")
 
 
-KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5, "v1_opts": 6}
+KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5, "v1_opts": 6, "wide_kelems": 7}
 
 
-def set_tuning(generation=1, spec_rows=0, spec_mode=1, fhfma=1, rows_wide=0, rows_narrow=0, v1_opts=0):
+def set_tuning(generation=1, spec_rows=0, spec_mode=1, fhfma=1, rows_wide=0, rows_narrow=0, v1_opts=0, wide_kelems=0):
     for k, v in (("generation", generation), ("spec_rows", spec_rows), ("spec_mode", spec_mode), ("fhfma", fhfma),
-                 ("rows_wide", rows_wide), ("rows_narrow", rows_narrow), ("v1_opts", v1_opts)):
+                 ("rows_wide", rows_wide), ("rows_narrow", rows_narrow), ("v1_opts", v1_opts), ("wide_kelems", wide_kelems)):
         check(lib().teal_set_tuning(KNOBS[k], int(v)), f"teal_set_tuning({k})")
 
 
@@ -118,9 +118,10 @@ class EmuDecoder:
         self.x, self.qkv, self.att = aligned((self.dim,), f16, 0), aligned((self.nqkv,), f16, 0), aligned((self.dim,), f16, 0)
         self.h, self.logits = aligned((self.inter,), f16, 0), aligned((self.vocab,), f16, 0)
         self.ssq = aligned((64,), np.float32, 0)
-        self.ws = Workspace()
+        self.ws = Workspace(1 << 17)   # the product's size (teal_b200/ops.py)
         self.program = None
         self.sampling = None   # dict(temperature, top_k, seed) as in SparseDecoder.set_sampling
+        self.chain_mlp = False  # SparseDecoder.chain_mlp: the flag-chained gate/up -> down pair
 
     def reset(self, token):
         self.token[0], self.pos[0], self.argmax[0] = token, 0, 0
@@ -142,6 +143,12 @@ class EmuDecoder:
                                          self.n_head, self.n_kv, self.hd, self.max_seq, None), "attn")
             check(L.teal_sparse_gemv_residual_f16(ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim,
                                                   t["o"], wsp, wsn, None), "o_proj")
+            if self.chain_mlp:
+                check(L.teal_norm_sparse_gate_up_chain_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), ptr(self.h),
+                                                           self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], wsp, wsn, None), "gate_up_chain")
+                check(L.teal_sparse_gemv_residual_chain_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter, self.dim, self.dim,
+                                                            t["down"], wsp, wsn, None), "down_chain")
+                continue
             check(L.teal_norm_sparse_gate_up_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), ptr(self.h), None,
                                                  self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], wsp, wsn, None), "gate_up")
             check(L.teal_sparse_gemv_residual_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter, self.dim, self.dim,

@@ -461,3 +461,86 @@ def test_generation1_one_change_at_a_time(opts):
         _check_gemv(Z, N, 0.6745, seed=opts)
     dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
     _run_and_compare(dec, True, lambda: dec.step(True))
+
+
+def _chain_case(dim, inter, seed):
+    g = torch.Generator().manual_seed(seed)
+    resid = torch.randn(1, 1, dim, generator=g).half()
+    nw = (1 + 0.1 * torch.randn(dim, generator=g)).half()
+    W1, W3 = [(torch.randn(inter, dim, generator=g) * 0.05).half() for _ in range(2)]
+    W2 = (torch.randn(dim, inter, generator=g) * 0.05).half()
+    return resid, nw, W1, W3, W2
+
+
+@pytest.mark.parametrize("dim,inter,wide_kelems,concurrent", [(256, 704, 0, False), (256, 704, 0, True), (256, 1000, 0, True),
+                                                               (512, 1536, 100, True), (512, 1400, 100, False), (256, 704, 300, True)])
+def test_flag_chained_mlp_pair(dim, inter, wide_kelems, concurrent):
+    """teal_norm_sparse_gate_up_chain_f16 -> teal_sparse_gemv_residual_chain_f16: the down projection waits for h tile by
+    tile instead of for the whole gate/up grid.  `concurrent`: the two launches really overlap (two host threads; the
+    consumer is started FIRST and spins until the producer's finalisers release its tiles).  wide_kelems lowers the
+    wide-variant threshold so that the 512-column twins and mixed tile widths are exercised at emulation sizes.
+    Result == the unchained pair's (oracle tolerance), ready cells back to zero, workspace clean."""
+    import threading
+    L = H.lib()
+    L.teal_emu_set_concurrent(1)
+    H.set_tuning(wide_kelems=wide_kelems)
+    resid, nw, W1, W3, W2 = _chain_case(dim, inter, dim + inter)
+    tg, tu, td, eps = 0.4, 0.6, 0.02, 1e-5
+    ws = H.Workspace(1 << 17)                             # the product's size (teal_b200/ops.py): room for the second accumulator region
+    xa = H.aligned((dim,), np.float16, resid.reshape(-1).numpy())
+    nwa = H.aligned((dim,), np.float16, nw.numpy())
+    W1c, W3c, W2c = H.column_major(W1.numpy()), H.column_major(W3.numpy()), H.column_major(W2.numpy())
+    ssq = H.aligned((64,), np.float32, 0)
+    ssq[0] = float((resid.float() ** 2).sum())
+    for rep in range(2):                                  # twice on the same workspace: the cells reset themselves
+        h = H.aligned((inter,), np.float16, 0)
+        y = H.aligned((dim,), np.float16, 0)
+        ssq_out = H.aligned((64,), np.float32, 5.0)
+        errors = []
+
+        def produce():
+            try:
+                H.check(L.teal_norm_sparse_gate_up_chain_f16(H.ptr(xa), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(W1c), H.ptr(W3c), H.ptr(h), dim, inter,
+                                                             inter, inter, tg, tu, H.ptr(ws.buf), ws.nbytes, None), "gate_up_chain")
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        def consume():
+            try:
+                H.check(L.teal_sparse_gemv_residual_chain_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim, dim, td,
+                                                              H.ptr(ws.buf), ws.nbytes, None), "down_chain")
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        if concurrent:
+            tc, tp = threading.Thread(target=consume), threading.Thread(target=produce)
+            tc.start()
+            import time
+            time.sleep(0.05)                              # the consumer grid is alive and polling before any h tile exists
+            tp.start()
+            tp.join(timeout=120)
+            tc.join(timeout=120)
+            assert not tc.is_alive() and not tp.is_alive()
+        else:
+            produce()
+            consume()
+        assert not errors, errors
+        ws.assert_clean()                                 # counters, both accumulator regions and the ready cells are zero again
+        xn = O.rms_norm(resid, nw, eps)
+        g32, u32 = O.sparse_linear_f32(xn, W1, tg), O.sparse_linear_f32(xn, W3, tu)
+        h_ref = (torch.nn.functional.silu(g32.half()) * u32.half()).reshape(-1)
+        h_t = torch.from_numpy(h.copy())
+        assert ((h_t.float() - h_ref.float()).abs() <= h_ref.float().abs() * 2.0 ** -8 + 2e-3).all()
+        d32 = O.sparse_linear_f32(h_t.reshape(1, 1, -1), W2, td).reshape(-1)
+        want = (resid.reshape(-1) + d32.half()).float()
+        y_t = torch.from_numpy(y.copy()).float()
+        assert ((y_t - want).abs() <= want.abs() * 2.0 ** -9 + 2e-3).all(), (rep, float((y_t - want).abs().max()))
+        assert abs(float(ssq_out.sum()) - float((y_t ** 2).sum())) <= 1e-4 * float((y_t ** 2).sum())
+
+
+@pytest.mark.parametrize("wide_kelems", [0, 150])
+def test_decode_step_with_the_flag_chained_mlp_pair(wide_kelems):
+    H.set_tuning(wide_kelems=wide_kelems)
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    dec.chain_mlp = True
+    _run_and_compare(dec, True, lambda: dec.step(True))

@@ -73,3 +73,25 @@ def test_decode_step(gen2):
     for mode, thr in [("dense_own", None), ("sparse", D.THR)]:
         D.test_decode_logits_match_oracle(mode, thr)
     D.test_graph_replay_equals_eager_and_is_deterministic_in_tokens()
+
+
+def test_flag_chained_mlp_pair_in_the_decode_step():
+    """TEAL_CHAIN_MLP: down starts on the h tiles it needs (no griddepcontrol.wait on the gate/up grid); logits == oracle,
+    graph replay == eager, tokens deterministic."""
+    dec, orc = D._mk(D.THR)
+    dec.chain_mlp = True
+    import torch
+    toks = [3, 17, 42, 8, 77, 300, 5, 11]
+    dec.capture("sparse")
+    dec.reset(toks[0])
+    for i, t in enumerate(toks):
+        dec.token.fill_(t)
+        dec.graph.replay()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
+        got = dec.logits.float().cpu().reshape(-1)
+        assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2, i
+    a = dec.generate(1, 24, mode="sparse").cpu().tolist()
+    b = dec.generate(1, 24, mode="sparse").cpu().tolist()
+    assert a == b

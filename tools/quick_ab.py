@@ -69,9 +69,21 @@ def main():
             ops.set_tuning()
         return rec
 
+    def run_chain():
+        dec.chain_mlp = True
+        try:
+            return dict(run({}), tuning={"chain_mlp": 1})
+        finally:
+            dec.chain_mlp = False
+
     base = run({})
     base_logits = base.pop("dense_logits", None)
     emit(base)
+    rec = run_chain()
+    lg = rec.pop("dense_logits", None)
+    if lg is not None and base_logits is not None:
+        rec["dense_logits_max_abs_diff_vs_default"] = round(float((lg - base_logits).abs().max()), 4)
+    emit(rec)
     for tune in TUNES:
         if time.time() - T0 > args.deadline:
             emit({"skipped": tune})
