@@ -207,6 +207,8 @@ def main():
                                  "one-shot peer-memory kernel" if dec.tp_fused else "nccl all-reduce")
     if getattr(dec, "chain_mlp", False):
         config["chain_mlp"] = "flag-chained gate/up -> down (TEAL_CHAIN_MLP=1)"
+    if getattr(dec, "chain_attn", False):
+        config["chain_attn"] = "flag-chained QKV -> attention -> o-proj (TEAL_CHAIN_ATTN=1)"
     if args.temperature > 0:
         dec.set_sampling(args.temperature, args.top_k, seed=0)
         config["sampling"] = f"top_k={args.top_k} temperature={args.temperature} (generate.py:49-66 on device)"

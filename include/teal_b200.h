@@ -161,6 +161,22 @@ int teal_norm_sparse_gate_up_chain_f16(const void* x, const void* norm_w, double
 int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const void* resid, void* y, float* ssq_out, int I, int N,
                                         int64_t ldw, double threshold, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Flag-chained attention block (opt-in, same status as the MLP pair): teal_norm_sparse_qkv_gemv_f16 -> teal_attn_decode_f16
+ * -> teal_sparse_gemv_residual_f16 (o-proj), issued back to back on one workspace and stream, without a grid-wide wait
+ * between them: the QKV finalisers release their column tiles (k / v tiles first), the attention CTA of a head waits for the
+ * tiles holding its q / k / v slices, the o-proj CTAs for the heads covering their K chunk.  Z = dim, N = (n_head + 2 n_kv)
+ * head_dim; the three calls must agree on n_head / n_kv_head / head_dim and on the QKV thresholds (they select the tiling). */
+int teal_norm_sparse_qkv_gemv_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt, void* y,
+                                        int Z, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
+                                        double threshold_v, int n_head, int n_kv_head, int head_dim, void* workspace,
+                                        size_t workspace_bytes, void* stream);
+int teal_attn_decode_chain_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos, void* out,
+                               int n_head, int n_kv_head, int head_dim, int max_seq, int dim, double threshold_q, double threshold_k,
+                               double threshold_v, void* workspace, size_t workspace_bytes, void* stream);
+int teal_sparse_o_proj_chain_f16(const void* att, const void* wt, const void* resid, void* y, float* ssq_out, int Z, int N, int64_t ldw,
+                                 double threshold, int n_head, int n_kv_head, int head_dim, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* Row-parallel projection (o / down under tensor parallelism, gpt-fast/tp.py:117,130) with its exchange step
  * (tp.py:120-121,139-140) and the residual add (model.py:160-161) in ONE kernel: resid_x[N] += sum over ranks of the
  * rank's partial y = W_shard * mask(x_shard), in place, plus the per-tile sums of squares for the next RMSNorm.  The

@@ -273,6 +273,63 @@ int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const voi
   return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- flag-chained attention block (opt-in): QKV releases tile by tile, attention starts per head, o-proj per K chunk ----
+int teal_norm_sparse_qkv_gemv_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt, void* y,
+                                        int Z, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
+                                        double threshold_v, int n_head, int n_kv_head, int head_dim, void* workspace,
+                                        size_t workspace_bytes_, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, y, Z)) return rc;
+  if (!wt || !y || !norm_w || !ssq_in || N != (n_head + 2 * n_kv_head) * head_dim || ldw < N || kv_size != n_kv_head * head_dim)
+    return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / norm_w / ssq_in / N / ldw / kv_size");
+  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
+  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k), tv = round_threshold_fp16(threshold_v);
+  ChainAttn ca;
+  if (int rc = chain_attn_describe(&ca, workspace, workspace_bytes_, Z, n_head, n_kv_head, head_dim, tq == tk && tk == tv)) return rc;
+  p.mode = kModePlain;
+  if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
+  const __half* w = reinterpret_cast<const __half*>(wt);
+  const float thr[3] = {tq, tk, tv};
+  for (int s = 0; s < ca.nseg; ++s)
+    p.seg[p.nseg++] = GemvSeg{w + ca.seg_col0[s], ldw, ca.seg_ncols[s], ca.seg_col0[s], slot_for(p, thr[s]), 0, 0, 0};
+  p.chain = 3;
+  p.ca = &ca;
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_attn_decode_chain_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos, void* out,
+                               int n_head, int n_kv_head, int head_dim, int max_seq, int dim, double threshold_q, double threshold_k,
+                               double threshold_v, void* workspace, size_t workspace_bytes_, void* stream) {
+  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k), tv = round_threshold_fp16(threshold_v);
+  ChainAttn ca;
+  if (int rc = chain_attn_describe(&ca, workspace, workspace_bytes_, dim, n_head, n_kv_head, head_dim, tq == tk && tk == tv)) return rc;
+  return launch_attn_decode_chain(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(freqs_cis),
+                                  reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), pos,
+                                  reinterpret_cast<__half*>(out), max_seq, ca, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_sparse_o_proj_chain_f16(const void* att, const void* wt, const void* resid, void* y, float* ssq_out, int Z, int N, int64_t ldw,
+                                 double threshold, int n_head, int n_kv_head, int head_dim, void* workspace, size_t workspace_bytes_,
+                                 void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, att, y, Z)) return rc;
+  if (!wt || !y || !resid || N <= 0 || ldw < N || Z != n_head * head_dim) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw / Z");
+  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
+  ChainAttn ca;
+  if (int rc = chain_attn_describe(&ca, workspace, workspace_bytes_, N, n_head, n_kv_head, head_dim, true)) return rc;
+  p.mode = kModePlain;
+  p.out_mode = kOutAddResidual;
+  p.resid = reinterpret_cast<const __half*>(resid);
+  p.ssq_out = ssq_out;
+  p.nseg = 1;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
+  p.chain = 4;
+  p.chain_rows = ca.rows_o;
+  p.chain_ctiles = ca.ctiles_o;
+  p.chain_cols = head_dim;
+  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
                                      double threshold, void* const* peer_partials, void* const* peer_flags, void* epoch_tiles,
                                      int rank, int world, void* workspace, size_t workspace_bytes_, void* stream) {

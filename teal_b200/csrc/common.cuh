@@ -58,7 +58,9 @@ struct GemvParams {
   GemvSeg seg[kMaxSeg];
   // appended (the offsets above are those of the hardware-validated build of the kernels that take GemvParams by value)
   const struct TpFuse* tp;  // optional (host pointer): fuse the TP exchange into the finaliser (row-parallel o / down)
-  int chain;                // 0 | 1 = producer of a flag-chained pair (gate/up) | 2 = its consumer (down): see RcParams
+  int chain;                // 0 | 1 = producer of a flag-chained pair (gate/up) | 2 = its consumer (down) | 3 = QKV producer of a
+                            // chained attention block | 4 = its o-proj consumer: see RcParams
+  const struct ChainAttn* ca;  // chain 3 / 4 (host pointer)
   int chain_rows, chain_ctiles, chain_cols;  // consumer K chunk, consumer column tiles, producer tile width (lanes of h)
 };
 
@@ -113,6 +115,42 @@ struct TpFuse {
   int rank, world;
 };
 
+// Geometry of a flag-chained attention block (QKV -> attention -> o-proj), shared by the three launches: which QKV column
+// tiles a head's q / k / v slices live in, and how many o-proj CTAs read a head.
+struct ChainAttn {
+  unsigned* ready_qkv;  // [QKV column tiles]: attention CTAs that still have to read the tile (0 = not produced yet)
+  unsigned* ready_att;  // [n_head]: o-proj CTAs that still have to read the head's output
+  int n_head, n_kv, hd;
+  int cols;             // QKV tile width
+  int nseg, seg_col0[3], seg_ncols[3], seg_tile0[3];  // QKV column regions (1 = uniform thresholds, 3 = q | k | v) and their first tiles
+  int rows_o, ctiles_o; // o-proj: K chunk per CTA, column tiles
+};
+__host__ __device__ inline int chain_tile_of(const ChainAttn& c, int col) {  // QKV column -> column tile
+  int s = 0;
+  for (int j = 1; j < c.nseg; ++j) s += (col >= c.seg_col0[j]) ? 1 : 0;
+  return c.seg_tile0[s] + (col - c.seg_col0[s]) / c.cols;
+}
+// column range [a, b) of slice `which` (0 q, 1 k, 2 v) of query head h
+__host__ __device__ inline void chain_slice(const ChainAttn& c, int h, int which, int* a, int* b) {
+  const int kvh = h / (c.n_head / c.n_kv);
+  *a = which == 0 ? h * c.hd : which == 1 ? (c.n_head + kvh) * c.hd : (c.n_head + c.n_kv + kvh) * c.hd;
+  *b = *a + c.hd;
+}
+// attention CTAs that read QKV tile `tile` (one count per (head, slice) whose columns touch it; a slice spans <= 2 tiles)
+__host__ __device__ inline unsigned chain_qkv_readers(const ChainAttn& c, int tile) {
+  unsigned n = 0;
+  for (int h = 0; h < c.n_head; ++h)
+    for (int w = 0; w < 3; ++w) {
+      int a, b;
+      chain_slice(c, h, w, &a, &b);
+      n += (chain_tile_of(c, a) <= tile && tile <= chain_tile_of(c, b - 1)) ? 1u : 0u;
+    }
+  return n;
+}
+__host__ __device__ inline unsigned chain_att_readers(const ChainAttn& c, int h) {  // o-proj CTAs whose K chunk overlaps head h
+  return (unsigned)((((h + 1) * c.hd - 1) / c.rows_o - (h * c.hd) / c.rows_o + 1) * c.ctiles_o);
+}
+
 struct RcSeg {
   const __half* w;
   long long ldw;
@@ -147,7 +185,8 @@ struct RcParams {
   // CHAIN instantiations (flag-chained launches: the consumer grid never executes griddepcontrol.wait, it waits for the
   // producer's tiles): ready[j] = number of consumer CTAs that still have to read h tile j (0 = not produced yet)
   unsigned* chain_ready;
-  int chain_rows, chain_ctiles, chain_cols, chain_group;
+  int chain_rows, chain_ctiles, chain_cols, chain_group, chain_rot;
+  ChainAttn ca;        // CHAIN == 3 (QKV producer of a chained attention block)
 };
 constexpr int kRc2MaxPass = 4;  // 32-lane groups one warp of a generation-2 CTA may own
 
@@ -177,6 +216,7 @@ bool pdl_enabled();
 int sub_cols_override();
 bool wave_balance_enabled();
 void chain_describe(int dim, int inter, int* rows_c, int* ctiles_c, int* cols_p);
+int chain_attn_describe(ChainAttn* ca, void* workspace, size_t ws_bytes, int dim, int n_head, int n_kv, int head_dim, bool uniform);
 int set_tuning(int knob, int value);
 int tuning(int knob);
 void set_bytes_probe(unsigned long long* p);
@@ -194,6 +234,8 @@ int launch_simple(const __half* x, const __half* wt, __half* y, int Z, int N, lo
 int launch_embed(const __half* emb, const int* token, __half* x, float* ssq_out, int dim, cudaStream_t stream);
 int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,
                        __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream);
+int launch_attn_decode_chain(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos, __half* out,
+                             int max_seq, const ChainAttn& ca, cudaStream_t stream);
 int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,
                           unsigned long long* argmax_packed, int Z, int V, long long ldw, cudaStream_t stream);
 int launch_residual_add(__half* x, const __half* part, float* ssq_out, int dim, cudaStream_t stream);

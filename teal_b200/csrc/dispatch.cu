@@ -98,6 +98,34 @@ void chain_describe(int dim, int inter, int* rows_c, int* ctiles_c, int* cols_p)
   *ctiles_c = (dim + (wide_c ? 512 : 256) - 1) / (wide_c ? 512 : 256);
 }
 
+// Geometry of a flag-chained attention block, derived once for its three launches (same size rule as the dispatch).
+int chain_attn_describe(ChainAttn* ca, void* workspace, size_t ws_bytes, int dim, int n_head, int n_kv, int head_dim, bool uniform) {
+  if (!workspace || ws_bytes < workspace_bytes(8)) return set_error(TEAL_ERR_WORKSPACE, "workspace too small");
+  if (n_head <= 0 || n_kv <= 0 || n_head % n_kv || n_head > 128 || (head_dim != 64 && head_dim != 128))
+    return set_error(TEAL_ERR_UNSUPPORTED, "chained attention block: heads / head_dim");
+  const int N = (n_head + 2 * n_kv) * head_dim;
+  ca->n_head = n_head; ca->n_kv = n_kv; ca->hd = head_dim;
+  ca->cols = ((long long)dim * N >= wide_min_elems()) ? 512 : 256;
+  const int widths[3] = {n_head * head_dim, n_kv * head_dim, n_kv * head_dim};
+  ca->nseg = uniform ? 1 : 3;
+  int col = 0, tile = 0;
+  for (int s = 0; s < 3; ++s) ca->seg_col0[s] = ca->seg_ncols[s] = ca->seg_tile0[s] = 0;
+  for (int s = 0; s < ca->nseg; ++s) {
+    const int w = uniform ? N : widths[s];
+    ca->seg_col0[s] = col; ca->seg_ncols[s] = w; ca->seg_tile0[s] = tile;
+    col += w;
+    tile += (w + ca->cols - 1) / ca->cols;
+  }
+  if (tile > 64) return set_error(TEAL_ERR_UNSUPPORTED, "chained attention block: more than 64 QKV tiles");
+  const bool wide_o = (long long)n_head * head_dim * dim >= wide_min_elems();
+  ca->rows_o = wide_o ? 128 : 64;
+  ca->ctiles_o = (dim + (wide_o ? 512 : 256) - 1) / (wide_o ? 512 : 256);
+  unsigned* cells = reinterpret_cast<unsigned*>(workspace) + 3072;  // the ready cells live in the unused tail of the counter region
+  ca->ready_qkv = cells + 128;
+  ca->ready_att = cells + 256;
+  return TEAL_OK;
+}
+
 size_t workspace_bytes(int max_out_cols) {
   size_t acc = ((size_t)max_out_cols * 4 + 255) & ~(size_t)255;
   return (size_t)kMaxCounters * 4 + acc + (size_t)kSsqParts * 4;  // [counters][acc][ssq scratch]

@@ -194,6 +194,14 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     const int pos = g * G + (r - kc * gsz);
     ct = (pos & 1) ? (T >> 1) + (pos >> 1) : (pos >> 1);
   }
+  if constexpr (CHAIN == 3) {  // group-major, k / v tiles first (every head needs its kv head's tiles), then the q tiles
+    const int T = p.total_ctiles, G = p.chain_group, per = G * p.nkchunks;
+    const int g = (int)blockIdx.x / per, r = (int)blockIdx.x - g * per;
+    const int gsz = min(G, T - g * G);
+    kc = r / gsz;
+    ct = g * G + (r - kc * gsz) + p.chain_rot;
+    if (ct >= T) ct -= T;
+  }
   int s = 0;
 #pragma unroll
   for (int j = 1; j < kMaxSeg; ++j) s += (j < p.nseg && ct >= p.seg[j].ctile0) ? 1 : 0;
@@ -476,6 +484,14 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       *reinterpret_cast<uint2*>(p.y + y0 + c) = o;
       const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
       ssq = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, ssq))));
+    }
+    if constexpr (CHAIN == 3) {  // QKV tile `cidx` is final: release it to the attention CTAs whose q / k / v slices touch it
+      __syncthreads();
+      if (tid == 0) {
+        const unsigned readers = chain_qkv_readers(p.ca, cidx);
+        __threadfence();
+        rc_st_release_gpu(p.ca.ready_qkv + cidx, readers);
+      }
     }
   }
   if (p.ssq_out) {  // this tile's contribution to the next RMSNorm (fixed reduction order: deterministic)
@@ -992,7 +1008,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   // Wave quantisation: pick the K-chunk so that the grid is (just under) a whole number of full waves of
   // resident CTAs -- 1792 CTAs on 1036 slots ran 1.73 waves, i.e. the second wave left 27 % of the chip idle.
   int rows_forced = forced_config() ? 0 : tuning(vec == 2 ? TEAL_TUNE_ROWS_WIDE : TEAL_TUNE_ROWS_NARROW);  // experiments only
-  if (gp.chain == 2) rows_forced = gp.chain_rows;  // the producer was told this K chunk (ready[] counts depend on it)
+  if (gp.chain == 2 || gp.chain == 4) rows_forced = gp.chain_rows;  // the producer was told this K chunk (ready[] counts depend on it)
   if (rows_forced > 0) {
     rows = rows_forced;
     if (var.gen == 2 && rows > 32 * kRc2MaxPass * var.warps) rows = 32 * kRc2MaxPass * var.warps;
@@ -1042,16 +1058,26 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (gp.chain) {  // flag-chained MLP pair (gate/up -> down): CHAIN twins of the two default variants
     constexpr int kChainCounter0 = 2048, kChainReady0 = 3072, kChainAcc0 = 65536;  // consumer's own regions of the workspace
     if (variant != 1 && variant != 2) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches: only the default row-chunk variants");
-    if (gp.chain_rows < 32 || gp.chain_ctiles < 1 || gp.chain_cols < 256 || gp.tp)
+    if (gp.chain != 3 && (gp.chain_rows < 32 || gp.chain_ctiles < 1 || gp.chain_cols < 64 || gp.tp))
       return set_error(TEAL_ERR_BAD_ARG, "chained launches: bad consumer description");
     p.chain_ready = reinterpret_cast<unsigned*>(workspace) + kChainReady0;
     p.chain_rows = gp.chain_rows; p.chain_ctiles = gp.chain_ctiles; p.chain_cols = gp.chain_cols;
-    if (gp.chain == 1) {
+    if (gp.chain == 3) {  // QKV producer of a chained attention block
+      if (!gp.ca || pair || gp.mode != kModePlain || cols != gp.ca->cols || ctile0 > 64 || gp.nseg != gp.ca->nseg)
+        return set_error(TEAL_ERR_BAD_ARG, "chained QKV: announced tiling");
+      p.ca = *gp.ca;
+      p.ca.ready_qkv = reinterpret_cast<unsigned*>(workspace) + kChainReady0 + 128;
+      p.ca.ready_att = reinterpret_cast<unsigned*>(workspace) + kChainReady0 + 256;
+      p.chain_group = 4;
+      p.chain_rot = chain_tile_of(p.ca, p.ca.n_head * p.ca.hd);  // first k tile
+      kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 3> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 3>;
+    } else if (gp.chain == 1) {
       if (!pair || cols != gp.chain_cols || ncounters > kMaxCounters - kChainReady0 || ncounters > kChainCounter0)
         return set_error(TEAL_ERR_BAD_ARG, "chained producer: gate/up pair whose tile width is the announced one");
       p.chain_group = 8;  // order positions per group = 4 tile pairs: the first h tiles are final after 1/7th of an 8B launch
       kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 1> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 1>;
     } else {
+      if (gp.chain == 4) p.chain_ready = reinterpret_cast<unsigned*>(workspace) + kChainReady0 + 256;  // ready_att: one cell per head
       const int ntiles_in = (gp.Z + gp.chain_cols - 1) / gp.chain_cols;
       if (gp.mode != kModePlain || gp.in_mode != kInPlain || ntiles_in > kMaxCounters - kChainReady0 || ctile0 > kChainReady0 - kChainCounter0 ||
           ws_bytes < (size_t)kMaxCounters * 4 + ((size_t)kChainAcc0 + out_cols_total) * 4 + (size_t)kSsqParts * 4 || gp.chain_ctiles != ctile0)

@@ -175,6 +175,8 @@ class SparseDecoder:
         # opt-in (not yet run on hardware): flag-chained MLP pair -- down starts on the h tiles it needs instead of waiting
         # for the whole gate/up grid (teal_*_chain_f16)
         self.chain_mlp = os.environ.get("TEAL_CHAIN_MLP") == "1" and world == 1
+        # ... and the flag-chained attention block: QKV releases its tiles, attention starts per head, o-proj per K chunk
+        self.chain_attn = os.environ.get("TEAL_CHAIN_ATTN") == "1" and world == 1
 
     # ------------------------------------------------------------------ TP exchange buffers
     def _setup_peer_exchange(self):
@@ -366,7 +368,19 @@ class SparseDecoder:
             W = L[li]
             t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else dense_t
             tap = self.taps[li] if self.taps is not None else None
-            if mode == "dense_cublas":
+            chain_attn = self.chain_attn and tap is None and mode != "dense_cublas" and self.world == 1 and not self.force_tp_path
+            if chain_attn:
+                chk(lib.teal_norm_sparse_qkv_gemv_chain_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps, ssq, W["wqkv"].data_ptr(),
+                                                            self.qkv.data_ptr(), a.dim, self.nqkv_l, W["wqkv"].stride(1), self.kv_l, t["q"], t["k"],
+                                                            t["v"], self.n_head_l, self.n_kv_l, self.hd, wsp, wsn, sp), "qkv_chain")
+                chk(lib.teal_attn_decode_chain_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
+                                                   self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(), self.n_head_l,
+                                                   self.n_kv_l, self.hd, self.max_seq, a.dim, t["q"], t["k"], t["v"], wsp, wsn, sp), "attn_chain")
+                chk(lib.teal_sparse_o_proj_chain_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), self.x.data_ptr(), ssq,
+                                                     self.dim_l, a.dim, W["wo"].stride(1), t["o"], self.n_head_l, self.n_kv_l, self.hd,
+                                                     wsp, wsn, sp), "o_chain")
+                n_launch += 2  # (the o projection is counted with the MLP launches below)
+            elif mode == "dense_cublas":
                 xn = _rms_norm(self.x, W["attn_norm"], a.norm_eps)
                 torch.matmul(xn, W["wqkv"].T, out=self.qkv)
             else:
@@ -378,37 +392,38 @@ class SparseDecoder:
                     "norm_qkv")
                 if tap is not None:
                     tap["attn_h1"].append(xn_out.flatten().float().cpu())
-            chk(lib.teal_attn_decode_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
-                                         self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
-                                         self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
-            if tap is not None:
-                tap["attn_h2"].append(self.att.flatten().float().cpu())
-            n_launch += 2
-            if mode == "dense_cublas":
-                torch.matmul(self.att, W["wo"].T, out=self.part)
-                self._allreduce(self.part)
-                self.x.add_(self.part)
-                xn = _rms_norm(self.x, W["ffn_norm"], a.norm_eps)
-                g1 = torch.matmul(xn, W["w1"].T)
-                u1 = torch.matmul(xn, W["w3"].T)
-                torch.mul(torch.nn.functional.silu(g1), u1, out=self.h)
-                torch.matmul(self.h, W["w2"].T, out=self.part)
-                self._allreduce(self.part)
-                self.x.add_(self.part)
-                continue
-            if self.world == 1 and not self.force_tp_path:
-                chk(lib.teal_sparse_gemv_residual_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(),
-                                                      self.x.data_ptr(), ssq, self.dim_l, a.dim, W["wo"].stride(1), t["o"],
-                                                      wsp, wsn, sp), "o_proj")
-            elif self.tp_fused and getattr(self, "tp_gemv", False):  # GEMV + exchange + residual + ssq in one kernel (opt-in)
-                chk(lib.teal_sparse_gemv_tp_exchange_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), ssq, self.dim_l, a.dim,
-                                                         W["wo"].stride(1), t["o"], self.tp_bufs[0], self.tp_tile_flags[0],
-                                                         self.tp_tile_epochs[0].data_ptr(), self.rank, self.world, wsp, wsn, sp), "o_proj+exchange")
-            else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
-                dst = self.tp_part[0] if self.tp_fused else self.part
-                chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), dst.data_ptr(), self.dim_l,
-                                             a.dim, W["wo"].stride(1), t["o"], wsp, wsn, sp), "o_proj")
-                n_launch += self._exchange(0, sp)
+            if not chain_attn:  # (the chained block above already ran attention and the o projection)
+                chk(lib.teal_attn_decode_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
+                                             self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
+                                             self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
+                if tap is not None:
+                    tap["attn_h2"].append(self.att.flatten().float().cpu())
+                n_launch += 2
+                if mode == "dense_cublas":
+                    torch.matmul(self.att, W["wo"].T, out=self.part)
+                    self._allreduce(self.part)
+                    self.x.add_(self.part)
+                    xn = _rms_norm(self.x, W["ffn_norm"], a.norm_eps)
+                    g1 = torch.matmul(xn, W["w1"].T)
+                    u1 = torch.matmul(xn, W["w3"].T)
+                    torch.mul(torch.nn.functional.silu(g1), u1, out=self.h)
+                    torch.matmul(self.h, W["w2"].T, out=self.part)
+                    self._allreduce(self.part)
+                    self.x.add_(self.part)
+                    continue
+                if self.world == 1 and not self.force_tp_path:
+                    chk(lib.teal_sparse_gemv_residual_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(),
+                                                          self.x.data_ptr(), ssq, self.dim_l, a.dim, W["wo"].stride(1), t["o"],
+                                                          wsp, wsn, sp), "o_proj")
+                elif self.tp_fused and getattr(self, "tp_gemv", False):  # GEMV + exchange + residual + ssq in one kernel (opt-in)
+                    chk(lib.teal_sparse_gemv_tp_exchange_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), ssq, self.dim_l, a.dim,
+                                                             W["wo"].stride(1), t["o"], self.tp_bufs[0], self.tp_tile_flags[0],
+                                                             self.tp_tile_epochs[0].data_ptr(), self.rank, self.world, wsp, wsn, sp), "o_proj+exchange")
+                else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
+                    dst = self.tp_part[0] if self.tp_fused else self.part
+                    chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), dst.data_ptr(), self.dim_l,
+                                                 a.dim, W["wo"].stride(1), t["o"], wsp, wsn, sp), "o_proj")
+                    n_launch += self._exchange(0, sp)
             if self.ffn_inputs is not None:
                 self.ffn_inputs.append((self.x.clone(), self.ssq.clone()))
             if self.chain_mlp and tap is None and self.world == 1 and not self.force_tp_path:

@@ -122,6 +122,8 @@ class EmuDecoder:
         self.program = None
         self.sampling = None   # dict(temperature, top_k, seed) as in SparseDecoder.set_sampling
         self.chain_mlp = False  # SparseDecoder.chain_mlp: the flag-chained gate/up -> down pair
+        self.chain_attn = False  # SparseDecoder.chain_attn: the flag-chained QKV -> attention -> o-proj block
+        self.concurrent_chain = False  # launch the kernels of a chained block from concurrent host threads, consumers first
 
     def reset(self, token):
         self.token[0], self.pos[0], self.argmax[0] = token, 0, 0
@@ -137,17 +139,31 @@ class EmuDecoder:
         check(L.teal_embed_f16(ptr(self.tok_emb), ptr(self.token), ptr(self.x), ssq, self.dim, None), "embed")
         for li, W in enumerate(self.layers):
             t = self.thresholds[li] if (sparse and self.thresholds[li] is not None) else {p: -1.0 for p in self.PROJS}
-            check(L.teal_norm_sparse_qkv_gemv_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), None,
-                                                  self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], wsp, wsn, None), "norm_qkv")
-            check(L.teal_attn_decode_f16(ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att),
-                                         self.n_head, self.n_kv, self.hd, self.max_seq, None), "attn")
-            check(L.teal_sparse_gemv_residual_f16(ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim,
-                                                  t["o"], wsp, wsn, None), "o_proj")
+            if self.chain_attn:
+                self._run_chain([
+                    lambda: check(L.teal_norm_sparse_qkv_gemv_chain_f16(
+                        ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), self.dim, self.nqkv, self.nqkv, self.kv,
+                        t["q"], t["k"], t["v"], self.n_head, self.n_kv, self.hd, wsp, wsn, None), "qkv_chain"),
+                    lambda: check(L.teal_attn_decode_chain_f16(
+                        ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att), self.n_head, self.n_kv,
+                        self.hd, self.max_seq, self.dim, t["q"], t["k"], t["v"], wsp, wsn, None), "attn_chain"),
+                    lambda: check(L.teal_sparse_o_proj_chain_f16(
+                        ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim, t["o"], self.n_head, self.n_kv,
+                        self.hd, wsp, wsn, None), "o_chain")])
+            else:
+                check(L.teal_norm_sparse_qkv_gemv_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), None,
+                                                      self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], wsp, wsn, None), "norm_qkv")
+                check(L.teal_attn_decode_f16(ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att),
+                                             self.n_head, self.n_kv, self.hd, self.max_seq, None), "attn")
+                check(L.teal_sparse_gemv_residual_f16(ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim,
+                                                      t["o"], wsp, wsn, None), "o_proj")
             if self.chain_mlp:
-                check(L.teal_norm_sparse_gate_up_chain_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), ptr(self.h),
-                                                           self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], wsp, wsn, None), "gate_up_chain")
-                check(L.teal_sparse_gemv_residual_chain_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter, self.dim, self.dim,
-                                                            t["down"], wsp, wsn, None), "down_chain")
+                self._run_chain([
+                    lambda: check(L.teal_norm_sparse_gate_up_chain_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]),
+                                                                       ptr(self.h), self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"],
+                                                                       wsp, wsn, None), "gate_up_chain"),
+                    lambda: check(L.teal_sparse_gemv_residual_chain_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter,
+                                                                        self.dim, self.dim, t["down"], wsp, wsn, None), "down_chain")])
                 continue
             check(L.teal_norm_sparse_gate_up_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), ptr(self.h), None,
                                                  self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], wsp, wsn, None), "gate_up")
@@ -161,6 +177,32 @@ class EmuDecoder:
                                          ptr(self.argmax), None, None), "sample")
         check(L.teal_advance(ptr(self.argmax), ptr(self.token), ptr(self.pos), ptr(self.out_tokens), self.out_tokens.size, None), "advance")
         ws.assert_clean()
+
+    def _run_chain(self, calls):
+        """The launches of one flag-chained block, in stream order -- or, with `concurrent_chain`, from concurrent host threads
+        with the LAST launch started first (every consumer grid is alive and polling before its producer runs)."""
+        if not self.concurrent_chain:
+            for c in calls:
+                c()
+            return
+        import threading
+        import time
+        errors = []
+
+        def guarded(c):
+            try:
+                c()
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=guarded, args=(c,)) for c in reversed(calls)]
+        for th in threads:
+            th.start()
+            time.sleep(0.02)
+        for th in threads:
+            th.join(timeout=300)
+        if errors or any(th.is_alive() for th in threads):
+            raise RuntimeError(f"chained block failed: {errors}")
 
     def build_program(self, sparse=True, **tuning):
         """SparseDecoder.build_program against the emulation library (host blob == "device" blob)."""

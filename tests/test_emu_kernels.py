@@ -544,3 +544,30 @@ def test_decode_step_with_the_flag_chained_mlp_pair(wide_kelems):
     dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
     dec.chain_mlp = True
     _run_and_compare(dec, True, lambda: dec.step(True))
+
+
+@pytest.mark.parametrize("uniform_qkv,concurrent,wide_kelems", [(True, False, 0), (False, False, 0), (True, True, 0), (False, True, 0),
+                                                                (False, True, 60), (True, True, 200)])
+def test_decode_step_with_flag_chained_blocks(uniform_qkv, concurrent, wide_kelems):
+    """Both blocks of every layer flag-chained: QKV -> attention -> o-proj (tiles / heads) and gate/up -> down (h tiles).
+    `concurrent`: the launches of a block run in concurrent host threads, last launch first, so every consumer grid is
+    polling before its producer starts.  3-threshold QKV (tiles per q | k | v region) and uniform QKV (one region, slices
+    share tiles); wide_kelems moves the narrow / wide variant boundary so that 512-column tiles hold several heads."""
+    H.set_tuning(wide_kelems=wide_kelems)
+    H.lib().teal_emu_set_concurrent(1 if concurrent else 0)
+    thr = [dict(t, k=t["q"], v=t["q"]) for t in THR] if uniform_qkv else THR
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), thr)
+    dec.chain_attn = dec.chain_mlp = True
+    dec.concurrent_chain = concurrent
+    if uniform_qkv:
+        orc = O.OracleDecoder(CFG, _state_dict(CFG), thr, max_seq=64)
+        dec.reset(TOKS[0])
+        for i, t in enumerate(TOKS):
+            dec.token[0] = t
+            dec.step(True)
+            with torch.no_grad():
+                want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
+            got = torch.from_numpy(dec.logits.astype(np.float32))
+            assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2, i
+    else:
+        _run_and_compare(dec, True, lambda: dec.step(True))

@@ -1,0 +1,103 @@
+"""teal_b200.model.SparseDecoder's own Python control flow on the CPU: the class is instantiated on CPU tensors with the
+CUDA plumbing (streams, availability check, workspace) stubbed and the library replaced by the CPU emulation of the kernels
+(tests/emu), so `_enqueue_step` -- the exact sequence of C-ABI calls the captured graph contains, including the opt-in
+chained / sampling branches -- runs for real and is checked against OracleDecoder.  CUDA-graph capture itself is not
+exercised here (that is what the -m gpu tests do)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import teal_oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import harness as H  # noqa: E402
+from test_emu_kernels import CFG, THR, TOKS, _state_dict  # noqa: E402
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
+@pytest.fixture
+def cpu_decoder(monkeypatch):
+    from teal_b200 import _lib, model, ops
+    emu = H.lib()
+    H.set_config(0)
+    H.set_tuning()
+    emu.teal_emu_set_concurrent(0)
+    monkeypatch.setattr(_lib, "load", lambda: emu)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+    ws = torch.zeros(emu.teal_workspace_bytes(1 << 17), dtype=torch.uint8)
+    monkeypatch.setattr(ops, "workspace", lambda dev, sp: ws)
+
+    def make(thresholds, **env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        dec = model.SparseDecoder(model.ModelArgs(**CFG), device="cpu", max_seq=64, state_dict=_state_dict(CFG))
+        dec.set_thresholds(thresholds)
+        return dec
+
+    yield make
+    H.set_tuning()
+
+
+def _check(dec, mode, thresholds):
+    orc = O.OracleDecoder(CFG, _state_dict(CFG), thresholds, max_seq=64)
+    dec.reset(TOKS[0])
+    for i, t in enumerate(TOKS):
+        dec.token.fill_(t)
+        dec._enqueue_step(mode)
+        with torch.no_grad():
+            want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
+        got = dec.logits.float().reshape(-1)
+        tol = (6e-2 if mode == "sparse" else 2e-2) * float(want.abs().max()) + 2e-2
+        assert float((got - want).abs().max()) <= tol, (mode, i)
+        assert int(dec.pos) == i + 1 and int(dec.token) == int(torch.argmax(got))
+
+
+@pytest.mark.parametrize("mode", ["sparse", "dense_own"])
+def test_default_step_sequence(cpu_decoder, mode):
+    dec = cpu_decoder(THR)
+    _check(dec, mode, THR if mode == "sparse" else [None] * CFG["n_layer"])
+    assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2
+
+
+def test_opt_in_branches(cpu_decoder):
+    dec = cpu_decoder(THR, TEAL_CHAIN_MLP="1", TEAL_CHAIN_ATTN="1")
+    assert dec.chain_mlp and dec.chain_attn
+    _check(dec, "sparse", THR)
+    assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2
+    dec.chain_attn = False
+    _check(dec, "sparse", THR)
+    dec.chain_mlp, dec.chain_attn = False, True
+    _check(dec, "dense_own", [None] * CFG["n_layer"])
+
+
+def test_sampling_branch(cpu_decoder):
+    dec = cpu_decoder(THR)
+    dec.set_sampling(0.8, 20, seed=5)
+    dec.reset(3)
+    for i in range(3):
+        dec._enqueue_step("sparse")
+        want, _ = O.sample_topk(dec.logits.reshape(-1).clone(), 0.8, 20, O.sample_noise(5, CFG["vocab_size"], i))
+        assert int(dec.token) == want
+    assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 3
+    with pytest.raises(NotImplementedError):
+        dec.build_program("sparse")
+    dec.set_sampling(0.0)
+    assert dec.sampling is None
+
+
+def test_calibration_runs_through_the_taps(cpu_decoder):
+    dec = cpu_decoder([None] * CFG["n_layer"], TEAL_CHAIN_MLP="1", TEAL_CHAIN_ATTN="1")
+    thr = dec.calibrate(0.5, n_tokens=3)       # taps force the unchained entry points (they return the normalised x)
+    assert len(thr) == CFG["n_layer"] and all(v > 0 for t in thr for v in t.values())

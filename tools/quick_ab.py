@@ -69,21 +69,22 @@ def main():
             ops.set_tuning()
         return rec
 
-    def run_chain():
-        dec.chain_mlp = True
+    def run_chain(mlp, attn):
+        dec.chain_mlp, dec.chain_attn = mlp, attn
         try:
-            return dict(run({}), tuning={"chain_mlp": 1})
+            return dict(run({}), tuning={"chain_mlp": int(mlp), "chain_attn": int(attn)})
         finally:
-            dec.chain_mlp = False
+            dec.chain_mlp = dec.chain_attn = False
 
     base = run({})
     base_logits = base.pop("dense_logits", None)
     emit(base)
-    rec = run_chain()
-    lg = rec.pop("dense_logits", None)
-    if lg is not None and base_logits is not None:
-        rec["dense_logits_max_abs_diff_vs_default"] = round(float((lg - base_logits).abs().max()), 4)
-    emit(rec)
+    for mlp, attn in ((True, False), (False, True), (True, True)):
+        rec = run_chain(mlp, attn)
+        lg = rec.pop("dense_logits", None)
+        if lg is not None and base_logits is not None:
+            rec["dense_logits_max_abs_diff_vs_default"] = round(float((lg - base_logits).abs().max()), 4)
+        emit(rec)
     for tune in TUNES:
         if time.time() - T0 > args.deadline:
             emit({"skipped": tune})
