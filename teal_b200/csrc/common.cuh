@@ -124,6 +124,7 @@ struct ChainAttn {
   int cols;             // QKV tile width
   int nseg, seg_col0[3], seg_ncols[3], seg_tile0[3];  // QKV column regions (1 = uniform thresholds, 3 = q | k | v) and their first tiles
   int rows_o, ctiles_o; // o-proj: K chunk per CTA, column tiles
+  unsigned char readers[64];  // per QKV tile: attention CTAs that read it (chain_qkv_readers, filled on the host)
 };
 __host__ __device__ inline int chain_tile_of(const ChainAttn& c, int col) {  // QKV column -> column tile
   int s = 0;

@@ -117,6 +117,11 @@ int chain_attn_describe(ChainAttn* ca, void* workspace, size_t ws_bytes, int dim
     tile += (w + ca->cols - 1) / ca->cols;
   }
   if (tile > 64) return set_error(TEAL_ERR_UNSUPPORTED, "chained attention block: more than 64 QKV tiles");
+  for (int t = 0; t < 64; ++t) {
+    const unsigned r = t < tile ? chain_qkv_readers(*ca, t) : 0u;
+    if (r > 255u) return set_error(TEAL_ERR_UNSUPPORTED, "chained attention block: more than 255 readers of one QKV tile");
+    ca->readers[t] = (unsigned char)r;
+  }
   const bool wide_o = (long long)n_head * head_dim * dim >= wide_min_elems();
   ca->rows_o = wide_o ? 128 : 64;
   ca->ctiles_o = (dim + (wide_o ? 512 : 256) - 1) / (wide_o ? 512 : 256);

@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     if constexpr (CHAIN == 3) {  // QKV tile `cidx` is final: release it to the attention CTAs whose q / k / v slices touch it
       __syncthreads();
       if (tid == 0) {
-        const unsigned readers = chain_qkv_readers(p.ca, cidx);
+        const unsigned readers = p.ca.readers[cidx];  // (head, slice) pairs touching this tile: chain_qkv_readers, from the host
         __threadfence();
         rc_st_release_gpu(p.ca.ready_qkv + cidx, readers);
       }
@@ -645,6 +645,7 @@ __device__ __forceinline__ void rc2_finish_warp(const RcParams& p, const RcSeg& 
     if (last) fence_acq_rel_gpu();
   }
   last = __shfl_sync(0xffffffffu, last, 0);
+  __syncwarp();  // lane 0's acquire fence happens-before the other lanes' accumulator reads
   if (!last) return;
 
   float ssq = 0.f;
