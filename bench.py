@@ -207,6 +207,8 @@ def main():
                                  "one-shot peer-memory kernel" if dec.tp_fused else "nccl all-reduce")
     if getattr(dec, "chain_mlp", False):
         config["chain_mlp"] = "flag-chained gate/up -> down (TEAL_CHAIN_MLP=1)"
+    if getattr(dec, "chain_norms", False) and dec.chain_mlp and dec.chain_attn:
+        config["chain_norms"] = "hand-off cells at the RMSNorm points (TEAL_CHAIN_NORMS=1)"
     if getattr(dec, "chain_attn", False):
         config["chain_attn"] = "flag-chained QKV -> attention -> o-proj (TEAL_CHAIN_ATTN=1)"
     if args.temperature > 0:

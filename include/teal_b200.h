@@ -157,9 +157,17 @@ int teal_sample_topk_f16(const void* logits, int V, double temperature, int top_
  * issued back to back (PDL enabled) with Z = dim, I = intermediate size, N = dim; ssq_in is required. */
 int teal_norm_sparse_gate_up_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
                                        const void* w3t, void* h, int Z, int I, int64_t ldw1, int64_t ldw3, double threshold_gate,
-                                       double threshold_up, void* workspace, size_t workspace_bytes, void* stream);
+                                       double threshold_up, int wait_all, void* workspace, size_t workspace_bytes, void* stream);
 int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const void* resid, void* y, float* ssq_out, int I, int N,
-                                        int64_t ldw, double threshold, void* workspace, size_t workspace_bytes, void* stream);
+                                        int64_t ldw, double threshold, int release_all_ctas, void* workspace, size_t workspace_bytes,
+                                        void* stream);
+/* Block-to-block hand-off of the chained step (the two RMSNorm points): the last block of a chain (o-proj, down) called with
+ * release_all_ctas = teal_chain_consumer_ctas(...) of the NEXT launch counts its final tiles and releases the whole residual
+ * stream + sum-of-squares partials; that next launch (gate/up, the next layer's QKV) called with wait_all = 1 skips
+ * griddepcontrol.wait and waits for the release instead.  wait_all = 0 / release_all_ctas = 0: an ordinary grid-wide wait
+ * (first layer after the embedding, last layer before the lm_head).  kind 0 = QKV (a = n_head, b = n_kv_head, c = head_dim,
+ * thresholds select the tiling), kind 1 = gate/up (a = intermediate size). */
+int teal_chain_consumer_ctas(int kind, int dim, int a, int b, int c, double threshold_q, double threshold_k, double threshold_v);
 
 /* Flag-chained attention block (opt-in, same status as the MLP pair): teal_norm_sparse_qkv_gemv_f16 -> teal_attn_decode_f16
  * -> teal_sparse_gemv_residual_f16 (o-proj), issued back to back on one workspace and stream, without a grid-wide wait
@@ -168,14 +176,14 @@ int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const voi
  * head_dim; the three calls must agree on n_head / n_kv_head / head_dim and on the QKV thresholds (they select the tiling). */
 int teal_norm_sparse_qkv_gemv_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt, void* y,
                                         int Z, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
-                                        double threshold_v, int n_head, int n_kv_head, int head_dim, void* workspace,
+                                        double threshold_v, int n_head, int n_kv_head, int head_dim, int wait_all, void* workspace,
                                         size_t workspace_bytes, void* stream);
 int teal_attn_decode_chain_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos, void* out,
                                int n_head, int n_kv_head, int head_dim, int max_seq, int dim, double threshold_q, double threshold_k,
                                double threshold_v, void* workspace, size_t workspace_bytes, void* stream);
 int teal_sparse_o_proj_chain_f16(const void* att, const void* wt, const void* resid, void* y, float* ssq_out, int Z, int N, int64_t ldw,
-                                 double threshold, int n_head, int n_kv_head, int head_dim, void* workspace, size_t workspace_bytes,
-                                 void* stream);
+                                 double threshold, int n_head, int n_kv_head, int head_dim, int release_all_ctas, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 
 /* Row-parallel projection (o / down under tensor parallelism, gpt-fast/tp.py:117,130) with its exchange step
  * (tp.py:120-121,139-140) and the residual add (model.py:160-161) in ONE kernel: resid_x[N] += sum over ranks of the

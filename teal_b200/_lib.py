@@ -51,17 +51,18 @@ _SIGS = {
                                         _c.c_void_p, _c.c_void_p]),
     "teal_norm_sparse_gate_up_chain_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                       _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _c.c_double, _c.c_double,
-                                                      _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                                      _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "teal_sparse_gemv_residual_chain_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
-                                                       _c.c_int, _c.c_int64, _c.c_double, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                                       _c.c_int, _c.c_int64, _c.c_double, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "teal_chain_consumer_ctas": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_double, _c.c_double]),
     "teal_norm_sparse_qkv_gemv_chain_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                                        _c.c_int, _c.c_int64, _c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_int,
-                                                       _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                                       _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "teal_attn_decode_chain_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                               _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_double, _c.c_double,
                                               _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "teal_sparse_o_proj_chain_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
-                                                _c.c_int64, _c.c_double, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t,
+                                                _c.c_int64, _c.c_double, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t,
                                                 _c.c_void_p]),
     "teal_sparse_gemv_tp_exchange_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
                                                     _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,

@@ -240,11 +240,12 @@ int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* res
 // ---- flag-chained MLP pair (opt-in): gate/up releases h tile by tile, down starts on the tiles it needs ------------
 int teal_norm_sparse_gate_up_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
                                        const void* w3t, void* h, int Z, int I, int64_t ldw1, int64_t ldw3, double threshold_gate,
-                                       double threshold_up, void* workspace, size_t workspace_bytes_, void* stream) {
+                                       double threshold_up, int wait_all, void* workspace, size_t workspace_bytes_, void* stream) {
   GemvParams p;
   if (int rc = fill_common(p, x, h, Z)) return rc;
   if (!w1t || !w3t || !h || !norm_w || !ssq_in || I <= 0 || ldw1 < I || ldw3 < I)
     return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / h / norm_w / ssq_in / I / ldw");
+  p.chain_wait_all = wait_all;
   if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
   p.mode = kModePairSilu;
   if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
@@ -257,9 +258,11 @@ int teal_norm_sparse_gate_up_chain_f16(const void* x, const void* norm_w, double
 }
 
 int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const void* resid, void* y, float* ssq_out, int I, int N,
-                                        int64_t ldw, double threshold, void* workspace, size_t workspace_bytes_, void* stream) {
+                                        int64_t ldw, double threshold, int release_all_ctas, void* workspace, size_t workspace_bytes_,
+                                        void* stream) {
   GemvParams p;
   if (int rc = fill_common(p, h, y, I)) return rc;
+  p.chain_release_all = release_all_ctas;
   if (!wt || !y || !resid || N <= 0 || ldw < N) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw");
   if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
   p.mode = kModePlain;
@@ -276,10 +279,11 @@ int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const voi
 // ---- flag-chained attention block (opt-in): QKV releases tile by tile, attention starts per head, o-proj per K chunk ----
 int teal_norm_sparse_qkv_gemv_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt, void* y,
                                         int Z, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
-                                        double threshold_v, int n_head, int n_kv_head, int head_dim, void* workspace,
+                                        double threshold_v, int n_head, int n_kv_head, int head_dim, int wait_all, void* workspace,
                                         size_t workspace_bytes_, void* stream) {
   GemvParams p;
   if (int rc = fill_common(p, x, y, Z)) return rc;
+  p.chain_wait_all = wait_all;
   if (!wt || !y || !norm_w || !ssq_in || N != (n_head + 2 * n_kv_head) * head_dim || ldw < N || kv_size != n_kv_head * head_dim)
     return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / norm_w / ssq_in / N / ldw / kv_size");
   if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
@@ -309,10 +313,11 @@ int teal_attn_decode_chain_f16(const void* qkv, const void* freqs_cis, void* k_c
 }
 
 int teal_sparse_o_proj_chain_f16(const void* att, const void* wt, const void* resid, void* y, float* ssq_out, int Z, int N, int64_t ldw,
-                                 double threshold, int n_head, int n_kv_head, int head_dim, void* workspace, size_t workspace_bytes_,
-                                 void* stream) {
+                                 double threshold, int n_head, int n_kv_head, int head_dim, int release_all_ctas, void* workspace,
+                                 size_t workspace_bytes_, void* stream) {
   GemvParams p;
   if (int rc = fill_common(p, att, y, Z)) return rc;
+  p.chain_release_all = release_all_ctas;
   if (!wt || !y || !resid || N <= 0 || ldw < N || Z != n_head * head_dim) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw / Z");
   if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
   ChainAttn ca;
@@ -328,6 +333,11 @@ int teal_sparse_o_proj_chain_f16(const void* att, const void* wt, const void* re
   p.chain_ctiles = ca.ctiles_o;
   p.chain_cols = head_dim;
   return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_chain_consumer_ctas(int kind, int dim, int a, int b, int c, double threshold_q, double threshold_k, double threshold_v) {
+  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k), tv = round_threshold_fp16(threshold_v);
+  return chain_consumer_ctas(kind, dim, a, b, c, tq == tk && tk == tv);
 }
 
 int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,

@@ -61,6 +61,8 @@ struct GemvParams {
   int chain;                // 0 | 1 = producer of a flag-chained pair (gate/up) | 2 = its consumer (down) | 3 = QKV producer of a
                             // chained attention block | 4 = its o-proj consumer: see RcParams
   const struct ChainAttn* ca;  // chain 3 / 4 (host pointer)
+  int chain_wait_all;          // chain 1 / 3: do not griddepcontrol.wait, wait for the previous block's whole output instead
+  int chain_release_all;       // chain 2 / 4: grid size of the next RMSNorm consumer to release the whole output to (0 = none)
   int chain_rows, chain_ctiles, chain_cols;  // consumer K chunk, consumer column tiles, producer tile width (lanes of h)
 };
 
@@ -187,6 +189,10 @@ struct RcParams {
   // producer's tiles): ready[j] = number of consumer CTAs that still have to read h tile j (0 = not produced yet)
   unsigned* chain_ready;
   int chain_rows, chain_ctiles, chain_cols, chain_group, chain_rot;
+  unsigned* chain_all_in;   // CIN == 2: consumer CTAs that still have to read the producer's whole output (0 = not final yet)
+  unsigned* chain_all_out;  // COUT == 4: the cell of the NEXT RMSNorm consumer, ...
+  unsigned* chain_done;     // ... the count of final tiles of this launch, ...
+  int chain_all_readers;    // ... and that consumer's grid size
   ChainAttn ca;        // CHAIN == 3 (QKV producer of a chained attention block)
 };
 constexpr int kRc2MaxPass = 4;  // 32-lane groups one warp of a generation-2 CTA may own
@@ -217,6 +223,7 @@ bool pdl_enabled();
 int sub_cols_override();
 bool wave_balance_enabled();
 void chain_describe(int dim, int inter, int* rows_c, int* ctiles_c, int* cols_p);
+int chain_consumer_ctas(int kind, int dim, int a, int b, int c, bool uniform);
 int chain_attn_describe(ChainAttn* ca, void* workspace, size_t ws_bytes, int dim, int n_head, int n_kv, int head_dim, bool uniform);
 int set_tuning(int knob, int value);
 int tuning(int knob);

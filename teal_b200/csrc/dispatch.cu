@@ -131,6 +131,25 @@ int chain_attn_describe(ChainAttn* ca, void* workspace, size_t ws_bytes, int dim
   return TEAL_OK;
 }
 
+// Grid size of an RMSNorm consumer launched with chain_wait_all (nominal K chunk, no wave balancing): what the previous
+// block's last finaliser writes into the hand-off cell.  kind 0 = QKV (a = n_head, b = n_kv, c = head_dim, uniform),
+// kind 1 = gate/up (a = inter).
+int chain_consumer_ctas(int kind, int dim, int a, int b, int c, bool uniform) {
+  if (kind == 1) {
+    const bool wide = (long long)dim * 2 * a >= wide_min_elems();
+    const int cols = wide ? 512 : 256, rows = wide ? 128 : 64;
+    return 2 * ((a + cols - 1) / cols) * ((dim + rows - 1) / rows);
+  }
+  const int N = (a + 2 * b) * c;
+  const bool wide = (long long)dim * N >= wide_min_elems();
+  const int cols = wide ? 512 : 256, rows = wide ? 128 : 64;
+  const int widths[3] = {a * c, b * c, b * c};
+  int tiles = 0;
+  if (uniform) tiles = (N + cols - 1) / cols;
+  else for (int s = 0; s < 3; ++s) tiles += (widths[s] + cols - 1) / cols;
+  return tiles * ((dim + rows - 1) / rows);
+}
+
 size_t workspace_bytes(int max_out_cols) {
   size_t acc = ((size_t)max_out_cols * 4 + 255) & ~(size_t)255;
   return (size_t)kMaxCounters * 4 + acc + (size_t)kSsqParts * 4;  // [counters][acc][ssq scratch]

@@ -165,9 +165,14 @@ __device__ __forceinline__ uint4 rc_ld_volatile_u4(const void* p) {
 //   ready[j] down again (the cell is back to 0 when the step is over: nothing to reset, graph-replayable).  Safe
 //   because every producer CTA issued launch_dependents when it started: by the time a consumer CTA exists, all
 //   producer CTAs are resident or done, and everything older than the producer is complete.
+//   CHAIN = 10 * CIN + COUT.  CIN: 0 = griddepcontrol.wait, 1 = wait for the producer's tiles covering my K chunk (o-proj, down),
+//   2 = wait for the producer's WHOLE output (the RMSNorm consumers QKV and gate/up: `chain_all_in` holds the number of consumer
+//   CTAs once every tile of the producer is final).  COUT: 0 = none, 1 = release h tile pairs (gate/up), 3 = release QKV tiles,
+//   4 = count final tiles and release the whole output to the next RMSNorm consumer (o-proj, down).
 template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false, int OPT = 0, int CHAIN = 0>
 __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
+  constexpr int CIN = CHAIN / 10, COUT = CHAIN % 10;
   long long* const dbg = TIMED ? p.dbg_time + (size_t)blockIdx.x * 16 : nullptr;
   auto stamp = [&](int i) {
     if constexpr (TIMED) {
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
   // CTAs read neighbouring pieces of the same weight rows ---------------------------------------------
   int ct = (int)(blockIdx.x % (unsigned)p.total_ctiles);
   int kc = (int)(blockIdx.x / (unsigned)p.total_ctiles);
-  if constexpr (CHAIN == 1) {  // group-major: order position -> (gate tile j, up tile j neighbours), K chunk slow inside a group
+  if constexpr (COUT == 1) {  // group-major: order position -> (gate tile j, up tile j neighbours), K chunk slow inside a group
     const int T = p.total_ctiles, G = p.chain_group, per = G * p.nkchunks;
     const int g = (int)blockIdx.x / per, r = (int)blockIdx.x - g * per;
     const int gsz = min(G, T - g * G);
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     const int pos = g * G + (r - kc * gsz);
     ct = (pos & 1) ? (T >> 1) + (pos >> 1) : (pos >> 1);
   }
-  if constexpr (CHAIN == 3) {  // group-major, k / v tiles first (every head needs its kv head's tiles), then the q tiles
+  if constexpr (COUT == 3) {  // group-major, k / v tiles first (every head needs its kv head's tiles), then the q tiles
     const int T = p.total_ctiles, G = p.chain_group, per = G * p.nkchunks;
     const int g = (int)blockIdx.x / per, r = (int)blockIdx.x - g * per;
     const int gsz = min(G, T - g * G);
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     if (early_ok && p.in_mode == kInRmsNorm) early_nw = p.norm_w[early_k];  // a constant: before the producer is done
   }
 
-  if constexpr (CHAIN == 2) {
+  if constexpr (CIN == 1) {
     griddep_launch_dependents();
     // the h tiles covering my K chunk: one polling thread per tile
     const int cb = kc * p.rows_per_cta, ce = min(p.Z, cb + p.rows_per_cta);
@@ -233,6 +238,15 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       const long long w0 = clock64();
       while (rc_ld_acquire_gpu(cell) == 0u) {
         if (clock64() - w0 > 4000000000ll) __trap();  // a protocol bug traps instead of hanging the GPU
+      }
+    }
+    __syncthreads();
+  } else if constexpr (CIN == 2) {
+    griddep_launch_dependents();
+    if (tid == 0) {  // the producer's whole output (residual stream + sum-of-squares partials)
+      const long long w0 = clock64();
+      while (rc_ld_acquire_gpu(p.chain_all_in) == 0u) {
+        if (clock64() - w0 > 4000000000ll) __trap();
       }
     }
     __syncthreads();
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     float xf = 0.f;
     if (k < kend) {
       const bool early = (OPT & 1) != 0 && k0 == kbeg + warp * 32;
-      const __half xh = early ? early_x : (CHAIN == 2 ? rc_ldcg_half(p.x + k) : p.x[k]);  // (chained: written by a grid that is still running -> L2)
+      const __half xh = early ? early_x : (CIN != 0 ? rc_ldcg_half(p.x + k) : p.x[k]);  // (chained: written by a grid that is still running -> L2)
       if (p.in_mode == kInRmsNorm) {
         // fp32 norm, cast to fp16, multiply by the fp16 weight in fp16
         xf = __half2float(__hmul(__float2half_rn(__half2float(xh) * rs), early ? early_nw : p.norm_w[k]));
@@ -351,10 +365,13 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     *reinterpret_cast<float4*>(d + 4) = make_float4(acc[v][2].x, acc[v][2].y, acc[v][3].x, acc[v][3].y);
   }
   __syncthreads();
-  if constexpr (CHAIN == 2) {  // every warp has consumed its lanes of h: this CTA is done with the tiles it waited for
+  if constexpr (CIN == 1) {  // every warp has consumed its lanes of h: this CTA is done with the tiles it waited for
     const int cb = kc * p.rows_per_cta, ce = min(p.Z, cb + p.rows_per_cta);
     const int t0 = cb / p.chain_cols, t1 = (ce - 1) / p.chain_cols;
     if (tid <= t1 - t0) atomicSub(p.chain_ready + t0 + tid, 1u);
+  }
+  if constexpr (CIN == 2) {  // ... with its lanes of the residual stream and the partials
+    if (tid == 0) atomicSub(p.chain_all_in, 1u);
   }
   const int acc0 = sg.acc_col0 + col0;
   for (int c = tid * 4; c < wcols; c += kRcThreads * 4) {
@@ -407,7 +424,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       o.y = *reinterpret_cast<const uint32_t*>(&h1);
       *reinterpret_cast<uint2*>(p.y + col0 + c) = o;
     }
-    if constexpr (CHAIN == 1) {  // h tile `cidx` is final: release it to the consumer CTAs whose K chunks overlap it
+    if constexpr (COUT == 1) {  // h tile `cidx` is final: release it to the consumer CTAs whose K chunks overlap it
       __syncthreads();
       if (tid == 0) {
         const int lo = cidx * COLS, hi = min(sg.ncols, lo + COLS) - 1;
@@ -485,7 +502,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
       ssq = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, ssq))));
     }
-    if constexpr (CHAIN == 3) {  // QKV tile `cidx` is final: release it to the attention CTAs whose q / k / v slices touch it
+    if constexpr (COUT == 3) {  // QKV tile `cidx` is final: release it to the attention CTAs whose q / k / v slices touch it
       __syncthreads();
       if (tid == 0) {
         const unsigned readers = p.ca.readers[cidx];  // (head, slice) pairs touching this tile: chain_qkv_readers, from the host
@@ -507,6 +524,18 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       // every slot of the kSsqParts-long buffer is (re)defined by exactly one tile on every call: slot i by tile i,
       // the unused tail i + T, i + 2T, ... is zeroed -- a previous producer with more tiles leaves nothing stale
       for (int sidx = cidx + p.total_ctiles; sidx < kSsqParts; sidx += p.total_ctiles) p.ssq_out[sidx] = 0.f;
+    }
+  }
+  if constexpr (COUT == 4) {  // this tile of the residual stream (and its sum of squares) is final: count it; the last one
+    __syncthreads();          // releases the whole vector to the CTAs of the next RMSNorm consumer
+    if (tid == 0) {
+      __threadfence();
+      const unsigned done = atomicAdd(p.chain_done, 1u) + 1u;
+      if ((int)done == p.total_ctiles) {
+        *p.chain_done = 0u;
+        __threadfence();
+        rc_st_release_gpu(p.chain_all_out, (unsigned)p.chain_all_readers);
+      }
     }
   }
   if (tid == 0) p.counters[cidx] = 0;
@@ -1010,6 +1039,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   // resident CTAs -- 1792 CTAs on 1036 slots ran 1.73 waves, i.e. the second wave left 27 % of the chip idle.
   int rows_forced = forced_config() ? 0 : tuning(vec == 2 ? TEAL_TUNE_ROWS_WIDE : TEAL_TUNE_ROWS_NARROW);  // experiments only
   if (gp.chain == 2 || gp.chain == 4) rows_forced = gp.chain_rows;  // the producer was told this K chunk (ready[] counts depend on it)
+  if ((gp.chain == 1 || gp.chain == 3) && gp.chain_wait_all) rows_forced = var.rows;  // ... and the previous block this grid size
   if (rows_forced > 0) {
     rows = rows_forced;
     if (var.gen == 2 && rows > 32 * kRc2MaxPass * var.warps) rows = 32 * kRc2MaxPass * var.warps;
@@ -1063,6 +1093,16 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       return set_error(TEAL_ERR_BAD_ARG, "chained launches: bad consumer description");
     p.chain_ready = reinterpret_cast<unsigned*>(workspace) + kChainReady0;
     p.chain_rows = gp.chain_rows; p.chain_ctiles = gp.chain_ctiles; p.chain_cols = gp.chain_cols;
+    // whole-output hand-offs between the blocks: cell A = o-proj -> gate/up, cell B = down -> the next layer's QKV
+    unsigned* const all_cells = reinterpret_cast<unsigned*>(workspace) + kChainReady0 + 384;
+    if (gp.chain == 1 || gp.chain == 3) {
+      p.chain_all_in = gp.chain_wait_all ? all_cells + (gp.chain == 1 ? 0 : 1) : nullptr;
+    } else if (gp.chain_release_all > 0) {
+      p.chain_all_out = all_cells + (gp.chain == 4 ? 0 : 1);
+      p.chain_done = all_cells + (gp.chain == 4 ? 2 : 3);
+      p.chain_all_readers = gp.chain_release_all;
+    }
+    const bool wa = gp.chain_wait_all != 0, ra = gp.chain_release_all > 0;
     if (gp.chain == 3) {  // QKV producer of a chained attention block
       if (!gp.ca || pair || gp.mode != kModePlain || cols != gp.ca->cols || ctile0 > 64 || gp.nseg != gp.ca->nseg)
         return set_error(TEAL_ERR_BAD_ARG, "chained QKV: announced tiling");
@@ -1071,12 +1111,14 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       p.ca.ready_att = reinterpret_cast<unsigned*>(workspace) + kChainReady0 + 256;
       p.chain_group = 4;
       p.chain_rot = chain_tile_of(p.ca, p.ca.n_head * p.ca.hd);  // first k tile
-      kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 3> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 3>;
+      kern = variant == 1 ? (wa ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 23> : rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 3>)
+                          : (wa ? rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 23> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 3>);
     } else if (gp.chain == 1) {
       if (!pair || cols != gp.chain_cols || ncounters > kMaxCounters - kChainReady0 || ncounters > kChainCounter0)
         return set_error(TEAL_ERR_BAD_ARG, "chained producer: gate/up pair whose tile width is the announced one");
       p.chain_group = 8;  // order positions per group = 4 tile pairs: the first h tiles are final after 1/7th of an 8B launch
-      kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 1> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 1>;
+      kern = variant == 1 ? (wa ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 21> : rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 1>)
+                          : (wa ? rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 21> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 1>);
     } else {
       if (gp.chain == 4) p.chain_ready = reinterpret_cast<unsigned*>(workspace) + kChainReady0 + 256;  // ready_att: one cell per head
       const int ntiles_in = (gp.Z + gp.chain_cols - 1) / gp.chain_cols;
@@ -1085,7 +1127,8 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
         return set_error(TEAL_ERR_BAD_ARG, "chained consumer: plain-input projection, announced tiling, workspace for a second accumulator region");
       p.counters += kChainCounter0;  // the producer grid is still running: its counters / accumulators are not ours
       p.acc += kChainAcc0;
-      kern = variant == 1 ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 2> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 2>;
+      kern = variant == 1 ? (ra ? rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 14> : rowchunk_gemv_kernel<2, 4, 4, false, false, 0, 10>)
+                          : (ra ? rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 14> : rowchunk_gemv_kernel<1, 8, 2, false, false, 0, 10>);
     }
   } else if (gp.tp) {  // row-parallel projection with the TP exchange fused into the tile finaliser (TP twins of the defaults)
     if (variant != 1 && variant != 2) return set_error(TEAL_ERR_UNSUPPORTED, "fused TP exchange: only the default row-chunk variants");

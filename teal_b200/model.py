@@ -177,6 +177,8 @@ class SparseDecoder:
         self.chain_mlp = os.environ.get("TEAL_CHAIN_MLP") == "1" and world == 1
         # ... and the flag-chained attention block: QKV releases its tiles, attention starts per head, o-proj per K chunk
         self.chain_attn = os.environ.get("TEAL_CHAIN_ATTN") == "1" and world == 1
+        # ... and the two RMSNorm points between the blocks as hand-off cells instead of grid-wide waits (needs both blocks chained)
+        self.chain_norms = os.environ.get("TEAL_CHAIN_NORMS") == "1" and world == 1
 
     # ------------------------------------------------------------------ TP exchange buffers
     def _setup_peer_exchange(self):
@@ -369,15 +371,23 @@ class SparseDecoder:
             t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else dense_t
             tap = self.taps[li] if self.taps is not None else None
             chain_attn = self.chain_attn and tap is None and mode != "dense_cublas" and self.world == 1 and not self.force_tp_path
+            chain_norms = chain_attn and self.chain_mlp and self.chain_norms
+            rel_o = rel_d = 0  # grid sizes of the next RMSNorm consumers (the hand-off cells are released to that many CTAs)
+            if chain_norms:
+                rel_o = lib.teal_chain_consumer_ctas(1, a.dim, self.inter_l, 0, 0, 0.0, 0.0, 0.0)
+                if li + 1 < a.n_layer:
+                    tn = self.thresholds[li + 1] if (mode == "sparse" and self.thresholds[li + 1] is not None) else dense_t
+                    rel_d = lib.teal_chain_consumer_ctas(0, a.dim, self.n_head_l, self.n_kv_l, self.hd, tn["q"], tn["k"], tn["v"])
             if chain_attn:
                 chk(lib.teal_norm_sparse_qkv_gemv_chain_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps, ssq, W["wqkv"].data_ptr(),
                                                             self.qkv.data_ptr(), a.dim, self.nqkv_l, W["wqkv"].stride(1), self.kv_l, t["q"], t["k"],
-                                                            t["v"], self.n_head_l, self.n_kv_l, self.hd, wsp, wsn, sp), "qkv_chain")
+                                                            t["v"], self.n_head_l, self.n_kv_l, self.hd, 1 if (chain_norms and li > 0) else 0,
+                                                            wsp, wsn, sp), "qkv_chain")
                 chk(lib.teal_attn_decode_chain_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
                                                    self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(), self.n_head_l,
                                                    self.n_kv_l, self.hd, self.max_seq, a.dim, t["q"], t["k"], t["v"], wsp, wsn, sp), "attn_chain")
                 chk(lib.teal_sparse_o_proj_chain_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), self.x.data_ptr(), ssq,
-                                                     self.dim_l, a.dim, W["wo"].stride(1), t["o"], self.n_head_l, self.n_kv_l, self.hd,
+                                                     self.dim_l, a.dim, W["wo"].stride(1), t["o"], self.n_head_l, self.n_kv_l, self.hd, rel_o,
                                                      wsp, wsn, sp), "o_chain")
                 n_launch += 2  # (the o projection is counted with the MLP launches below)
             elif mode == "dense_cublas":
@@ -429,9 +439,10 @@ class SparseDecoder:
             if self.chain_mlp and tap is None and self.world == 1 and not self.force_tp_path:
                 chk(lib.teal_norm_sparse_gate_up_chain_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq, W["w1"].data_ptr(),
                                                            W["w3"].data_ptr(), self.h.data_ptr(), a.dim, self.inter_l, W["w1"].stride(1),
-                                                           W["w3"].stride(1), t["gate"], t["up"], wsp, wsn, sp), "gate_up_chain")
+                                                           W["w3"].stride(1), t["gate"], t["up"], 1 if chain_norms else 0, wsp, wsn, sp),
+                    "gate_up_chain")
                 chk(lib.teal_sparse_gemv_residual_chain_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(), self.x.data_ptr(), ssq,
-                                                            self.inter_l, a.dim, W["w2"].stride(1), t["down"], wsp, wsn, sp), "down_chain")
+                                                            self.inter_l, a.dim, W["w2"].stride(1), t["down"], rel_d, wsp, wsn, sp), "down_chain")
                 n_launch += 3
                 continue
             xn_out = torch.empty_like(self.x) if tap is not None else None

@@ -124,6 +124,7 @@ class EmuDecoder:
         self.chain_mlp = False  # SparseDecoder.chain_mlp: the flag-chained gate/up -> down pair
         self.chain_attn = False  # SparseDecoder.chain_attn: the flag-chained QKV -> attention -> o-proj block
         self.concurrent_chain = False  # launch the kernels of a chained block from concurrent host threads, consumers first
+        self.chain_norms = False  # SparseDecoder.chain_norms: hand-off cells instead of grid-wide waits at the two RMSNorm points
 
     def reset(self, token):
         self.token[0], self.pos[0], self.argmax[0] = token, 0, 0
@@ -139,17 +140,34 @@ class EmuDecoder:
         check(L.teal_embed_f16(ptr(self.tok_emb), ptr(self.token), ptr(self.x), ssq, self.dim, None), "embed")
         for li, W in enumerate(self.layers):
             t = self.thresholds[li] if (sparse and self.thresholds[li] is not None) else {p: -1.0 for p in self.PROJS}
+            norms = self.chain_attn and self.chain_mlp and self.chain_norms
+            rel_o = rel_d = 0
+            if norms:
+                rel_o = L.teal_chain_consumer_ctas(1, self.dim, self.inter, 0, 0, 0.0, 0.0, 0.0)
+                if li + 1 < len(self.layers):
+                    tn = self.thresholds[li + 1] if (sparse and self.thresholds[li + 1] is not None) else {p: -1.0 for p in self.PROJS}
+                    rel_d = L.teal_chain_consumer_ctas(0, self.dim, self.n_head, self.n_kv, self.hd, tn["q"], tn["k"], tn["v"])
+            attn_calls = [
+                lambda: check(L.teal_norm_sparse_qkv_gemv_chain_f16(
+                    ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), self.dim, self.nqkv, self.nqkv, self.kv,
+                    t["q"], t["k"], t["v"], self.n_head, self.n_kv, self.hd, 1 if (norms and li > 0) else 0, wsp, wsn, None), "qkv_chain"),
+                lambda: check(L.teal_attn_decode_chain_f16(
+                    ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att), self.n_head, self.n_kv,
+                    self.hd, self.max_seq, self.dim, t["q"], t["k"], t["v"], wsp, wsn, None), "attn_chain"),
+                lambda: check(L.teal_sparse_o_proj_chain_f16(
+                    ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim, t["o"], self.n_head, self.n_kv,
+                    self.hd, rel_o, wsp, wsn, None), "o_chain")]
+            mlp_calls = [
+                lambda: check(L.teal_norm_sparse_gate_up_chain_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]),
+                                                                   ptr(self.h), self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"],
+                                                                   1 if norms else 0, wsp, wsn, None), "gate_up_chain"),
+                lambda: check(L.teal_sparse_gemv_residual_chain_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter,
+                                                                    self.dim, self.dim, t["down"], rel_d, wsp, wsn, None), "down_chain")]
+            if norms:  # the five launches of the layer form one chain (the o-proj -> gate/up hand-off is a cell, not a grid-wide wait)
+                self._run_chain(attn_calls + mlp_calls)
+                continue
             if self.chain_attn:
-                self._run_chain([
-                    lambda: check(L.teal_norm_sparse_qkv_gemv_chain_f16(
-                        ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), self.dim, self.nqkv, self.nqkv, self.kv,
-                        t["q"], t["k"], t["v"], self.n_head, self.n_kv, self.hd, wsp, wsn, None), "qkv_chain"),
-                    lambda: check(L.teal_attn_decode_chain_f16(
-                        ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att), self.n_head, self.n_kv,
-                        self.hd, self.max_seq, self.dim, t["q"], t["k"], t["v"], wsp, wsn, None), "attn_chain"),
-                    lambda: check(L.teal_sparse_o_proj_chain_f16(
-                        ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim, t["o"], self.n_head, self.n_kv,
-                        self.hd, wsp, wsn, None), "o_chain")])
+                self._run_chain(attn_calls)
             else:
                 check(L.teal_norm_sparse_qkv_gemv_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), None,
                                                       self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], wsp, wsn, None), "norm_qkv")
@@ -158,12 +176,7 @@ class EmuDecoder:
                 check(L.teal_sparse_gemv_residual_f16(ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim,
                                                       t["o"], wsp, wsn, None), "o_proj")
             if self.chain_mlp:
-                self._run_chain([
-                    lambda: check(L.teal_norm_sparse_gate_up_chain_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]),
-                                                                       ptr(self.h), self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"],
-                                                                       wsp, wsn, None), "gate_up_chain"),
-                    lambda: check(L.teal_sparse_gemv_residual_chain_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter,
-                                                                        self.dim, self.dim, t["down"], wsp, wsn, None), "down_chain")])
+                self._run_chain(mlp_calls)
                 continue
             check(L.teal_norm_sparse_gate_up_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), ptr(self.h), None,
                                                  self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], wsp, wsn, None), "gate_up")

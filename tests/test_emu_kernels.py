@@ -501,13 +501,13 @@ def test_flag_chained_mlp_pair(dim, inter, wide_kelems, concurrent):
         def produce():
             try:
                 H.check(L.teal_norm_sparse_gate_up_chain_f16(H.ptr(xa), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(W1c), H.ptr(W3c), H.ptr(h), dim, inter,
-                                                             inter, inter, tg, tu, H.ptr(ws.buf), ws.nbytes, None), "gate_up_chain")
+                                                             inter, inter, tg, tu, 0, H.ptr(ws.buf), ws.nbytes, None), "gate_up_chain")
             except Exception as e:  # noqa: BLE001
                 errors.append(e)
 
         def consume():
             try:
-                H.check(L.teal_sparse_gemv_residual_chain_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim, dim, td,
+                H.check(L.teal_sparse_gemv_residual_chain_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim, dim, td, 0,
                                                               H.ptr(ws.buf), ws.nbytes, None), "down_chain")
             except Exception as e:  # noqa: BLE001
                 errors.append(e)
@@ -571,3 +571,25 @@ def test_decode_step_with_flag_chained_blocks(uniform_qkv, concurrent, wide_kele
             assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2, i
     else:
         _run_and_compare(dec, True, lambda: dec.step(True))
+
+
+@pytest.mark.parametrize("uniform_qkv,concurrent,wide_kelems", [(False, False, 0), (True, True, 0), (False, True, 0), (False, True, 100)])
+def test_decode_step_fully_flag_chained(uniform_qkv, concurrent, wide_kelems):
+    """chain_norms on top of the two chained blocks: the RMSNorm points are hand-off cells too (o-proj's last finaliser releases
+    the residual stream to the gate/up CTAs, down's to the next layer's QKV CTAs), so inside the layer stack no launch waits for
+    a whole grid.  `concurrent`: the five launches of a layer run in concurrent host threads, the last one started first."""
+    H.set_tuning(wide_kelems=wide_kelems)
+    H.lib().teal_emu_set_concurrent(1 if concurrent else 0)
+    thr = [dict(t, k=t["q"], v=t["q"]) for t in THR] if uniform_qkv else THR
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), thr)
+    dec.chain_attn = dec.chain_mlp = dec.chain_norms = True
+    dec.concurrent_chain = concurrent
+    orc = O.OracleDecoder(CFG, _state_dict(CFG), thr, max_seq=64)
+    dec.reset(TOKS[0])
+    for i, t in enumerate(TOKS):
+        dec.token[0] = t
+        dec.step(True)                     # (asserts that the workspace -- counters, accumulators, every hand-off cell -- is zero again)
+        with torch.no_grad():
+            want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
+        got = torch.from_numpy(dec.logits.astype(np.float32))
+        assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2, i

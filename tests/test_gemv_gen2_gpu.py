@@ -75,11 +75,13 @@ def test_decode_step(gen2):
     D.test_graph_replay_equals_eager_and_is_deterministic_in_tokens()
 
 
-def test_flag_chained_blocks_in_the_decode_step():
+@pytest.mark.parametrize("norms", [False, True])
+def test_flag_chained_blocks_in_the_decode_step(norms):
     """TEAL_CHAIN_MLP / TEAL_CHAIN_ATTN: consumers start on the tiles / heads they need (no griddepcontrol.wait); logits == oracle,
     graph replay == eager, tokens deterministic."""
     dec, orc = D._mk(D.THR)
     dec.chain_mlp = dec.chain_attn = True
+    dec.chain_norms = norms
     import torch
     toks = [3, 17, 42, 8, 77, 300, 5, 11]
     dec.capture("sparse")

@@ -80,6 +80,10 @@ def test_opt_in_branches(cpu_decoder):
     _check(dec, "sparse", THR)
     dec.chain_mlp, dec.chain_attn = False, True
     _check(dec, "dense_own", [None] * CFG["n_layer"])
+    dec.chain_mlp = dec.chain_attn = dec.chain_norms = True       # no grid-wide wait left inside the layer stack
+    _check(dec, "sparse", THR)
+    _check(dec, "dense_own", [None] * CFG["n_layer"])
+    assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2
 
 
 def test_sampling_branch(cpu_decoder):

@@ -69,18 +69,18 @@ def main():
             ops.set_tuning()
         return rec
 
-    def run_chain(mlp, attn):
-        dec.chain_mlp, dec.chain_attn = mlp, attn
+    def run_chain(mlp, attn, norms=False):
+        dec.chain_mlp, dec.chain_attn, dec.chain_norms = mlp, attn, norms
         try:
-            return dict(run({}), tuning={"chain_mlp": int(mlp), "chain_attn": int(attn)})
+            return dict(run({}), tuning={"chain_mlp": int(mlp), "chain_attn": int(attn), "chain_norms": int(norms)})
         finally:
-            dec.chain_mlp = dec.chain_attn = False
+            dec.chain_mlp = dec.chain_attn = dec.chain_norms = False
 
     base = run({})
     base_logits = base.pop("dense_logits", None)
     emit(base)
-    for mlp, attn in ((True, False), (False, True), (True, True)):
-        rec = run_chain(mlp, attn)
+    for mlp, attn, norms in ((True, False, False), (False, True, False), (True, True, False), (True, True, True)):
+        rec = run_chain(mlp, attn, norms)
         lg = rec.pop("dense_logits", None)
         if lg is not None and base_logits is not None:
             rec["dense_logits_max_abs_diff_vs_default"] = round(float((lg - base_logits).abs().max()), 4)
