@@ -491,7 +491,8 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
       st_cg_f4(p.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
       __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
       if (p.out_mode == kOutAddResidual) {  // h = x + y in fp16 (gpt-fast/model.py:160-161)
-        const uint2 r = *reinterpret_cast<const uint2*>(p.resid + y0 + c);
+        // (chained twins: the residual stream was written by a grid that may still be running -> read it at L2)
+        const uint2 r = (CHAIN != 0) ? __ldcg(reinterpret_cast<const uint2*>(p.resid + y0 + c)) : *reinterpret_cast<const uint2*>(p.resid + y0 + c);
         h0 = __hadd2(*reinterpret_cast<const __half2*>(&r.x), h0);
         h1 = __hadd2(*reinterpret_cast<const __half2*>(&r.y), h1);
       }
