@@ -6,13 +6,15 @@
 set -u
 mkdir -p gpurun_out
 export TEAL_PROGRAM_GPU_TESTS=1 TEAL_GEN2_GPU_TESTS=1 TEAL_SAMPLING_GPU_TESTS=1
+# 0. the one-minute overview first (it survives a cut-off call): default vs flag-chained blocks / RMSNorm hand-offs vs
+#    one-change-at-a-time variants vs generations 2 / 3, tokens/s + dense-mode logits check against the default kernels
+timeout 150 python tools/quick_ab.py --deadline 90 --steps 64 --out gpurun_out/r02_quick_ab.jsonl > /dev/null 2>&1; echo "quick_ab rc=$?"
+cat gpurun_out/r02_quick_ab.jsonl
 # 1. validated suite first (must stay green), then the opt-in tests of the unvalidated kernels
 timeout 600 python -m pytest tests -m gpu -x -q -k "not gen2 and not unvalidated and not sampling_gpu" > gpurun_out/r02_gpu_tests_validated.log 2>&1; echo "validated suite rc=$?"
 timeout 900 python -m pytest tests/test_gemv_gen2_gpu.py -q > gpurun_out/r02_gpu_tests_gen2.log 2>&1; echo "gen2/gen3 tests rc=$?"
 timeout 300 python -m pytest tests/test_sampling_gpu.py -q > gpurun_out/r02_gpu_tests_sampling.log 2>&1; echo "sampling tests rc=$?"
 timeout 300 python -m pytest tests/test_step_program_gpu.py -q -k unvalidated > gpurun_out/r02_gpu_tests_program_variants.log 2>&1; echo "step-program variants rc=$?"
-# 2a. quickest overview: default vs flag-chained MLP pair vs one-change-at-a-time variants vs generations
-timeout 120 python tools/quick_ab.py --deadline 60 --steps 64 --out gpurun_out/r02_quick_ab.jsonl > /dev/null 2>&1; echo "quick_ab rc=$?"
 # 2. decode-step A/B on Llama-3-8B @50 %: graph engine under every dispatch setting, then the step-program sweeps
 timeout 420 python tools/bench_engines.py --quick --graph-tunes --out gpurun_out/r02_graph_tunes.jsonl > /dev/null 2>&1; echo "graph tunes rc=$?"
 timeout 300 python tools/bench_engines.py --sweep 3 --out gpurun_out/r02_program_sweep3.jsonl > /dev/null 2>&1; echo "sweep3 rc=$?"
