@@ -1090,6 +1090,8 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
   if (gp.chain) {  // flag-chained MLP pair (gate/up -> down): CHAIN twins of the two default variants
     constexpr int kChainCounter0 = 2048, kChainReady0 = 3072, kChainAcc0 = 65536;  // consumer's own regions of the workspace
     if (variant != 1 && variant != 2) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches: only the default row-chunk variants");
+    if ((gp.chain == 1 || gp.chain == 3) && out_cols_total > kChainAcc0)
+      return set_error(TEAL_ERR_UNSUPPORTED, "chained producer: its accumulators would reach into the consumer's region");
     if (gp.chain != 3 && (gp.chain_rows < 32 || gp.chain_ctiles < 1 || gp.chain_cols < 64 || gp.tp))
       return set_error(TEAL_ERR_BAD_ARG, "chained launches: bad consumer description");
     p.chain_ready = reinterpret_cast<unsigned*>(workspace) + kChainReady0;
