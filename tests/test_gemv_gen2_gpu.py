@@ -1,5 +1,6 @@
-"""Generation-2 row-chunk kernel (rowchunk_gemv2_kernel: shared-memory survivor list, rolling load ring, FHFMA,
-optional speculative L2 prefetch) through the SAME parity tests as the production kernel.
+"""Opt-in kernels through the SAME parity tests as the production kernel: row-chunk generations 2 / 3
+(rowchunk_gemv2_kernel: shared-memory survivor list, rolling load ring, FHFMA, optional speculative L2 prefetch, warp-wise
+completion) and the flag-chained decode step (TEAL_CHAIN_*).
 
 It was written after round 1's GPU budget was spent: compiled for sm_100a and SASS-checked, never run on hardware.
 Nothing selects it by default (teal_set_tuning(TEAL_TUNE_GENERATION, 2) / config ids 42-49 are opt-in), and these
