@@ -173,10 +173,12 @@ template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false, int OP
 __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
   constexpr int CIN = CHAIN / 10, COUT = CHAIN % 10;
-  long long* const dbg = TIMED ? p.dbg_time + (size_t)blockIdx.x * 16 : nullptr;
+  // (the chained twins are profiled through the same hook, decided at run time: they are experimental anyway)
+  constexpr bool kCanStamp = TIMED || CHAIN != 0;
+  long long* const dbg = (kCanStamp && (TIMED || p.dbg_time)) ? p.dbg_time + (size_t)blockIdx.x * 16 : nullptr;
   auto stamp = [&](int i) {
-    if constexpr (TIMED) {
-      if (threadIdx.x == 0) dbg[i] = globaltimer_ns();
+    if constexpr (kCanStamp) {
+      if (threadIdx.x == 0 && (TIMED || dbg)) dbg[i] = globaltimer_ns();
     }
   };
   stamp(0);
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     my_nnz += __popc(mask);
     if (p.mode == kModeSurvivors) mask = 0u;  // parity hook: thresholds only, no weights
     if (k0 == kbeg + warp * 32) stamp(2);     // first survivor set known
-    [[maybe_unused]] bool first_batch = TIMED && k0 == kbeg + warp * 32;
+    [[maybe_unused]] bool first_batch = kCanStamp && k0 == kbeg + warp * 32;
     while (mask) {
       int bit[U];
       uint4 wv[U][VEC];
@@ -341,8 +343,8 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
           }
         }
       }
-      if constexpr (TIMED) {
-        if (first_batch) {  // the first rows have arrived from DRAM and been consumed
+      if constexpr (kCanStamp) {
+        if (first_batch && (TIMED || dbg)) {  // the first rows have arrived from DRAM and been consumed
           first_batch = false;
           if (threadIdx.x == 0) dbg[3] = globaltimer_ns() + (long long)(acc[0][0].x == 1.2345e-30f);
         }
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     const int last = ((int)old + 1 == p.target) ? 1 : 0;
     if (last) fence_acq_rel_gpu();
     s_last = last;
-    if constexpr (TIMED) {
+    if (kCanStamp && (TIMED || dbg)) {
       unsigned smid = blockIdx.x;
 #ifndef TEAL_EMU
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1088,6 +1090,7 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
 
   void (*kern)(const RcParams) = var.kern;
   if (gp.chain) {  // flag-chained MLP pair (gate/up -> down): CHAIN twins of the two default variants
+    if (grid <= kTimelineMaxCtas) p.dbg_time = next_debug_timeline_slot();  // (null unless teal_set_debug_timeline armed it)
     constexpr int kChainCounter0 = 2048, kChainReady0 = 3072, kChainAcc0 = 65536;  // consumer's own regions of the workspace
     if (variant != 1 && variant != 2) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches: only the default row-chunk variants");
     if ((gp.chain == 1 || gp.chain == 3) && out_cols_total > kChainAcc0)

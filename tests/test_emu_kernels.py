@@ -593,3 +593,24 @@ def test_decode_step_fully_flag_chained(uniform_qkv, concurrent, wide_kelems):
             want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
         got = torch.from_numpy(dec.logits.astype(np.float32))
         assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2, i
+
+
+def test_timeline_of_a_chained_step():
+    """The chained twins stamp through the same hook (decided at run time): slot i = i-th row-chunk launch of the step."""
+    L = H.lib()
+    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    dec.chain_attn = dec.chain_mlp = dec.chain_norms = True
+    n = 4 * CFG["n_layer"]
+    buf = H.aligned((n * 4096 * 16,), np.int64, 0)
+    H.check(L.teal_set_debug_timeline(H.ptr(buf), n), "timeline")
+    try:
+        dec.reset(3)
+        dec.token[0] = 3
+        dec.step(True)
+    finally:
+        H.check(L.teal_set_debug_timeline(None, 0), "timeline off")
+    t = buf.reshape(n, 4096, 16)
+    for s in range(n):
+        used = t[s][t[s][:, 0] > 0]
+        assert len(used) > 0 and (used[:, 0] <= used[:, 1]).all() and (used[:, 1] <= used[:, 4]).all(), s
+        assert int(used[:, 10].sum()) >= 1

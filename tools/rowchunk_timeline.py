@@ -69,12 +69,16 @@ def main():
     ap.add_argument("--sparsity", type=float, default=0.5)
     ap.add_argument("--mode", default="sparse")
     ap.add_argument("--per-launch", action="store_true")
+    ap.add_argument("--chain", default="", help="comma list of mlp,attn,norms: profile the flag-chained step (TEAL_CHAIN_*); "
+                                                "split 'wait_producer' is then the time a CTA spent polling its tiles / hand-off cell")
     ap.add_argument("--out", default="gpurun_out/r02_rowchunk_timeline.jsonl")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     a = ModelArgs.from_name(args.workload)
     dec = SparseDecoder(a, max_seq=128, out_cap=128)
     dec.calibrate(args.sparsity, n_tokens=4)
+    chain = set(filter(None, args.chain.split(",")))
+    dec.chain_mlp, dec.chain_attn, dec.chain_norms = "mlp" in chain, "attn" in chain, "norms" in chain
     n_launch = 4 * a.n_layer
     # capture() runs one eager warm-up step before it captures: slots 0 .. n-1 go to the warm-up, n .. 2n-1 to the graph
     buf = torch.zeros(2 * n_launch * SLOT_CTAS * 16, dtype=torch.int64, device=dec.dev)
