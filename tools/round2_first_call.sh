@@ -24,6 +24,7 @@ timeout 300 python tools/bench_gemv.py --configs 31,32,42,43,44,45,46,50,51,52 -
     --out gpurun_out/r02_bench_gemv.jsonl > /dev/null 2>&1; echo "bench_gemv rc=$?"
 # 4. where the step's time goes: in-kernel timeline of the production kernels inside the graph replay
 timeout 240 python tools/rowchunk_timeline.py --per-launch --out gpurun_out/r02_rowchunk_timeline.jsonl > gpurun_out/r02_rowchunk_timeline.txt 2>&1; echo "timeline rc=$?"
+timeout 240 python tools/rowchunk_timeline.py --chain mlp,attn,norms --out gpurun_out/r02_rowchunk_timeline_chained.jsonl > gpurun_out/r02_rowchunk_timeline_chained.txt 2>&1; echo "chained timeline rc=$?"
 # 5. is FHFMA (generation 2's arithmetic) slower than conversions + FFMA2?
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fhfma_rate tools/micro/fhfma_rate.cu && timeout 60 /tmp/fhfma_rate > gpurun_out/r02_micro_fhfma_rate.txt 2>&1; echo "fhfma_rate rc=$?"
 tail -n 40 gpurun_out/r02_graph_tunes.jsonl
