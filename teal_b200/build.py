@@ -38,18 +38,30 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One nvcc -c per source, in parallel (the sources share no device symbols), then one link."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if verbose else [])
+    jobs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        cmd = [_nvcc(), *flags, "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        jobs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs = []
+    for src, obj, proc in jobs:
+        out, err = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}\n{err}")
+        if verbose:
+            print(err)
+        objs.append(obj)
+    res = subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     return LIB
 
 
