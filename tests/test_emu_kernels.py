@@ -614,3 +614,64 @@ def test_timeline_of_a_chained_step():
         used = t[s][t[s][:, 0] > 0]
         assert len(used) > 0 and (used[:, 0] <= used[:, 1]).all() and (used[:, 1] <= used[:, 4]).all(), s
         assert int(used[:, 10].sum()) >= 1
+
+
+@pytest.mark.parametrize("Z,N", [(4096, 11008), (11008, 4096), (4096, 4096), (4096, 6144)])
+def test_baseline_shapes_at_full_size(Z, N):
+    """BASELINE.json config 1 (Llama-2-7B gate_proj 4096 -> 11008, batch 1, 50 %) and its sibling projections at their real
+    sizes through the default dispatch on the emulation (the wide- and narrow-tile production kernels, multi-wave grids)."""
+    H.lib().teal_emu_set_sm_count(8)
+    _check_gemv(Z, N, 0.6745, seed=Z + N)
+
+
+def test_llama3_8b_mlp_block_at_full_size_chained_and_unchained():
+    """One Llama-3-8B MLP block (4096 -> 2 x 14336 -> 4096) at full size: fused RMSNorm + gate/up + SiLU*mul -> down +
+    residual, unchained and flag-chained with the two launches overlapping (consumer first); both against the oracle."""
+    import threading
+    import time
+    L = H.lib()
+    L.teal_emu_set_sm_count(8)
+    dim, inter, eps, tg, tu, td = 4096, 14336, 1e-5, 0.6745, 0.6745, 0.01
+    resid, nw, W1, W3, W2 = _chain_case(dim, inter, 7)
+    W1, W3, W2 = (W1 * 0.4).half(), (W3 * 0.4).half(), (W2 * 0.4).half()
+    ws = H.Workspace(1 << 17)
+    xa0 = resid.reshape(-1).numpy()
+    nwa = H.aligned((dim,), np.float16, nw.numpy())
+    W1c, W3c, W2c = H.column_major(W1.numpy()), H.column_major(W3.numpy()), H.column_major(W2.numpy())
+    ssq = H.aligned((64,), np.float32, 0)
+    ssq[0] = float((resid.float() ** 2).sum())
+    xn = O.rms_norm(resid, nw, eps)
+    h_ref = (torch.nn.functional.silu(O.sparse_linear_f32(xn, W1, tg).half()) * O.sparse_linear_f32(xn, W3, tu).half()).reshape(-1)
+    for chained in (False, True):
+        xa = H.aligned((dim,), np.float16, xa0)
+        h, y, ssq_out = H.aligned((inter,), np.float16, 0), H.aligned((dim,), np.float16, 0), H.aligned((64,), np.float32, 0)
+        if chained:
+            calls = [lambda: H.check(L.teal_norm_sparse_gate_up_chain_f16(H.ptr(xa), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(W1c), H.ptr(W3c), H.ptr(h),
+                                                                          dim, inter, inter, inter, tg, tu, 0, H.ptr(ws.buf), ws.nbytes, None), "p"),
+                     lambda: H.check(L.teal_sparse_gemv_residual_chain_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim,
+                                                                           dim, td, 0, H.ptr(ws.buf), ws.nbytes, None), "c")]
+            errs = []
+
+            def guarded(c):
+                try:
+                    c()
+                except Exception as e:  # noqa: BLE001
+                    errs.append(e)
+            tc, tp = threading.Thread(target=guarded, args=(calls[1],)), threading.Thread(target=guarded, args=(calls[0],))
+            tc.start()
+            time.sleep(0.1)
+            tp.start()
+            tp.join(timeout=300)
+            tc.join(timeout=300)
+            assert not errs and not tc.is_alive()
+        else:
+            H.check(L.teal_norm_sparse_gate_up_f16(H.ptr(xa), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(W1c), H.ptr(W3c), H.ptr(h), None, dim, inter,
+                                                   inter, inter, tg, tu, H.ptr(ws.buf), ws.nbytes, None), "gate_up")
+            H.check(L.teal_sparse_gemv_residual_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim, dim, td,
+                                                    H.ptr(ws.buf), ws.nbytes, None), "down")
+        ws.assert_clean()
+        h_t = torch.from_numpy(h.copy())
+        assert ((h_t.float() - h_ref.float()).abs() <= h_ref.float().abs() * 2.0 ** -8 + 2e-3).all(), chained
+        want = (resid.reshape(-1) + O.sparse_linear_f32(h_t.reshape(1, 1, -1), W2, td).reshape(-1).half()).float()
+        y_t = torch.from_numpy(y.copy()).float()
+        assert ((y_t - want).abs() <= want.abs() * 2.0 ** -9 + 2e-3).all(), chained
