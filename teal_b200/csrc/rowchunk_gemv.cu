@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
     if (tid == 0) {  // the producer's whole output (residual stream + sum-of-squares partials)
       const long long w0 = clock64();
       while (rc_ld_acquire_gpu(p.chain_all_in) == 0u) {
+        __nanosleep(64);  // ~1000 resident CTAs poll this one cell: keep the line's request rate well below one L2 slice's
         if (clock64() - w0 > 4000000000ll) __trap();
       }
     }
