@@ -117,6 +117,26 @@ def test_product_never_imports_the_oracle():
                 assert "teal_oracle" not in src, f
 
 
+def test_product_has_no_cpu_execution_path():
+    """The CPU emulation of the kernels (tests/emu) is test infrastructure like the oracle: the Python package never refers to
+    it, the shipped library exports none of its symbols and was built without TEAL_EMU (no emulation twin of any inline-PTX
+    helper is in it -- the twins exist only behind `#ifdef TEAL_EMU` in the .cu sources)."""
+    import ctypes
+    import re
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "teal_b200")
+    for f in os.listdir(root):
+        if f.endswith(".py"):
+            src = open(os.path.join(root, f)).read()
+            assert not re.search(r"tests[/.]emu|libteal_emu|TEAL_EMU|harness", src), f
+    from teal_b200 import build
+    assert not any("TEAL_EMU" in flag for flag in build.NVCC_FLAGS)
+    lib = build.build()
+    syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    assert "teal_emu_" not in syms and "emu" not in " ".join(s.split()[-1] for s in syms.splitlines() if "teal" in s)
+    assert not hasattr(ctypes.CDLL(lib), "teal_emu_set_concurrent")
+
+
 def test_hf_self_attn_patch_and_setters():
     from teal_b200.hf import SparseLinear, patch_mlp, patch_self_attn, set_sparsities
 
