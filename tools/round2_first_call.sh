@@ -8,7 +8,8 @@ mkdir -p gpurun_out
 export TEAL_PROGRAM_GPU_TESTS=1 TEAL_GEN2_GPU_TESTS=1 TEAL_SAMPLING_GPU_TESTS=1
 # 0. the one-minute overview first (it survives a cut-off call): default vs flag-chained blocks / RMSNorm hand-offs vs
 #    one-change-at-a-time variants vs generations 2 / 3, tokens/s + dense-mode logits check against the default kernels
-timeout 150 python tools/quick_ab.py --deadline 90 --steps 64 --out gpurun_out/r02_quick_ab.jsonl > /dev/null 2>&1; echo "quick_ab rc=$?"
+timeout 150 python tools/quick_ab.py --only tunes --deadline 90 --steps 64 --out gpurun_out/r02_quick_ab.jsonl > /dev/null 2>&1; echo "quick_ab tunes rc=$?"
+timeout 90 python tools/quick_ab.py --only chain --steps 64 --out gpurun_out/r02_quick_ab.jsonl > /dev/null 2>&1; echo "quick_ab chain rc=$?"
 cat gpurun_out/r02_quick_ab.jsonl
 # 1. validated suite first (must stay green), then the opt-in tests of the unvalidated kernels
 timeout 600 python -m pytest tests -m gpu -x -q -k "not gen2 and not unvalidated and not sampling_gpu" > gpurun_out/r02_gpu_tests_validated.log 2>&1; echo "validated suite rc=$?"
