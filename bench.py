@@ -76,47 +76,89 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference(args_model, sparsity, reps, threads=None):
-    """The reference's CPU path for this workload: SparsifyFn.apply + F.linear per projection
-    (utils/utils.py:51-52; it masks, it does not skip rows), timed on ONE layer + the lm_head and scaled
-    by the layer count.  Uses the oracle port (oracle/teal_oracle.py) -- the checker, never the product."""
-    import torch
+def _reference_sparsify():
+    """The reference's own SparsifyFn (utils/utils.py:9-55) from oracle/_ref (fetched by oracle/fetch_ref.py, git-ignored,
+    travels with gpurun) -> kind "reference"; else the oracle port of the same two lines -> kind "port"."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(os.path.join(ref, "utils", "utils.py")):
+        try:
+            sys.path.insert(0, ref)
+            from utils.utils import SparsifyFn  # the reference's class, unmodified
+
+            def make(thr):
+                fn = SparsifyFn(None, init_threshold=thr)
+                fn.threshold = thr  # what set_threshold() leaves (utils.py:28-30)
+                return fn.apply     # x.abs().gt(threshold) * x (utils.py:51-52)
+            return make, "reference"
+        except Exception:
+            pass
+        finally:
+            if ref in sys.path:
+                sys.path.remove(ref)
     from oracle import teal_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    return (lambda thr: (lambda x: O.sparsify_apply(x, thr))), "port"
+
+
+def cpu_reference(args_model, sparsity, steps, warmup=1, budget_s=None, threads=None):
+    """The reference's CPU path for this workload, timed for real: every step is ONE whole token -- n_layer layer passes of
+    SparsifyFn.apply + F.linear per projection (utils/utils.py:51-52: it masks, it does not skip rows) over a rotating pool of
+    4 distinct layer weight sets (1.7 GB fp16 for the 8B shape: nothing stays in the CPU caches) + the dense lm_head.
+    `steps` x ms_per_step is the wall time of the timed region.  With budget_s the number of steps is cut so that the timed
+    region stays near the budget (cpu_baseline leg).  All host threads (torchrun sets OMP_NUM_THREADS=1: undone here)."""
+    import torch
+    import torch.nn.functional as F
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    make, kind = _reference_sparsify()
     a = args_model
     kv = a.n_local_heads * a.head_dim
     g = torch.Generator().manual_seed(0)
     shapes = {"qkv": (a.dim + 2 * kv, a.dim), "o": (a.dim, a.dim), "gate": (a.intermediate_size, a.dim),
               "up": (a.intermediate_size, a.dim), "down": (a.dim, a.intermediate_size)}
-    W = {k: (torch.randn(n, z, generator=g) * 0.02).half() for k, (n, z) in shapes.items()}
+    npool = 4
+    pool = [{k: (torch.randn(n, z, generator=g) * 0.02).half() for k, (n, z) in shapes.items()} for _ in range(npool)]
     lm = (torch.randn(a.vocab_size, a.dim, generator=g) * 0.02).half()
-    x = torch.randn(1, 1, a.dim, generator=g).half()
-    h = torch.randn(1, 1, a.intermediate_size, generator=g).half()
-    tx = float(x.abs().float().flatten().kthvalue(max(1, int(a.dim * sparsity))).values)
-    th = float(h.abs().float().flatten().kthvalue(max(1, int(a.intermediate_size * sparsity))).values)
+    x0 = torch.randn(1, 1, a.dim, generator=g).half()
 
-    def layer_once():
-        O.qkv_sparse_linear(x, W["qkv"], tx, tx, tx, kv)
-        O.sparse_linear(x, W["o"], tx)
-        O.sparse_linear(torch.nn.functional.silu(O.sparse_linear(x, W["gate"], tx)) * O.sparse_linear(x, W["up"], tx),
-                        W["down"], th)
+    def quantile_thr(v):
+        return float(v.abs().float().flatten().kthvalue(max(1, int(v.numel() * sparsity))).values)
 
-    layer_once()
-    torch.nn.functional.linear(x, lm)
-    per_step = []
-    for _ in range(reps):
+    def norm(v):
+        vf = v.float()
+        return (vf * torch.rsqrt(vf.pow(2).mean(-1, keepdim=True) + a.norm_eps)).half()
+
+    fns = {}
+
+    def sp(site, v):  # thresholds are fixed on first use (calibration), like the reference's set_threshold
+        if site not in fns:
+            fns[site] = make(quantile_thr(v))
+        return fns[site](v)
+
+    def token():
+        x = x0
+        for li in range(a.n_layer):
+            W, s = pool[li % npool], li % npool
+            qkv = F.linear(sp((s, "qkv"), norm(x)), W["qkv"])
+            att = qkv[..., : a.dim]  # (attention itself is not part of the threshold+matmul path; context is short)
+            x = x + F.linear(sp((s, "o"), att), W["o"])
+            xn = norm(x)
+            h = F.silu(F.linear(sp((s, "gate"), xn), W["gate"])) * F.linear(sp((s, "up"), xn), W["up"])
+            x = x + F.linear(sp((s, "down"), h), W["down"])
+        return F.linear(norm(x), lm)
+
+    for _ in range(max(1, warmup)):
         t0 = time.perf_counter()
-        layer_once()
-        t1 = time.perf_counter()
-        torch.nn.functional.linear(x, lm)
-        t2 = time.perf_counter()
-        per_step.append((t1 - t0) * a.n_layer + (t2 - t1))
-    per_step.sort()
-    sec = per_step[len(per_step) // 2]
-    return {"value": 1.0 / sec, "unit": "tok/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{reps} x (one layer: qkv,o,gate,up,down threshold+F.linear fp16) x {a.n_layer} layers + lm_head, "
-                      f"median; reference CPU path masks then runs the dense matmul"}, sec
+        token()
+        one = time.perf_counter() - t0
+    if budget_s is not None:
+        steps = max(1, min(steps, int(budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        token()
+    sec = (time.perf_counter() - t0) / steps
+    return {"value": 1.0 / sec, "unit": "tok/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{steps} whole tokens, each {a.n_layer} layer passes (qkv,o,gate,up,down: SparsifyFn.apply + F.linear, fp16) "
+                      f"over a rotating pool of {npool} layer weight sets + lm_head; wall time / steps; the reference CPU path "
+                      f"masks, then runs the dense matmul"}, sec, steps
 
 
 def main():
@@ -155,16 +197,16 @@ def main():
     config = {"workload": f"{args.workload} full decode step (random-init fp16, synthetic-calibrated thresholds)",
               "sparsity": args.sparsity, "context": "positions 0..steps (short context, generate.py:171)",
               "sampling": "greedy", "parallelism": f"tp{world}" if world > 1 else "single",
-              "l2": "weights (>= 8 GB per GPU) far exceed the 126 MB L2; every step streams them from HBM"}
+              "l2": "weights (>= 8 GB per GPU) far exceed the 126 MB L2; every step streams them from HBM",
+              "engine": "graph"}
 
     # ------------------------------------------------------------------ reference arm: CPU threshold+matmul
     if args.impl == "reference":
         if rank != 0:
             return
-        reps = max(1, min(args.steps, 8))
-        base, sec = cpu_reference(margs, args.sparsity, reps)  # warms up once internally, then `reps` timed samples
+        base, sec, steps = cpu_reference(margs, args.sparsity, args.steps, warmup=min(args.warmup, 2))
         line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": "tok/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,7 +264,8 @@ def main():
 
     engine = args.engine if world == 1 else "graph"
     knobs = {k: int(v) for k, v in (kv.split("=") for kv in args.knob)}
-    config["engine"] = engine if not knobs else f"{engine} {knobs}"
+    if engine != "graph" or knobs:
+        config["engine"] = engine if not knobs else f"{engine} {knobs}"
 
     def timed(mode, steps, warmup, e2e=False):
         if engine == "program" and mode != "dense_cublas":
@@ -362,7 +405,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         try:
-            cpu, _ = cpu_reference(margs, args.sparsity, 3)
+            cpu, _, _ = cpu_reference(margs, args.sparsity, 16, warmup=1, budget_s=12.0)
         except Exception as e:
             cpu = {"value": None, "unit": "tok/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}
 

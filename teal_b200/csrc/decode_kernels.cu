@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   const int kvh = h / (n_head / n_kv);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   griddep_wait();
+  griddep_launch_dependents();  // n_head CTAs leave most of the machine free: the o-proj grid moves in and waits for us
   const int pos = pos_ptr[0];
 
   // ---- RoPE on q (this head) and on the new k (its kv head); v passes through ---------------------
@@ -179,7 +180,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
     }
     out[(size_t)h * HD + tid] = __float2half_rn(o / L);
   }
-  griddep_launch_dependents();
 }
 
 // ---- flag-chained attention block (opt-in, not yet run on hardware): the attention kernel between a QKV producer and an

@@ -36,14 +36,14 @@ static int g_tuning[TEAL_TUNE_COUNT] = {1, 0, 1, 1, 0, 0, 0, 0};  // generation 
 int tuning(int knob) { return (knob >= 0 && knob < TEAL_TUNE_COUNT) ? g_tuning[knob] : 0; }
 int set_tuning(int knob, int value) {
   if (knob < 0 || knob >= TEAL_TUNE_COUNT) return set_error(TEAL_ERR_BAD_ARG, "tuning knob out of range");
-  if (knob == TEAL_TUNE_GENERATION && (value < 1 || value > 3)) return set_error(TEAL_ERR_BAD_ARG, "generation must be 1, 2 or 3");
+  if (knob == TEAL_TUNE_GENERATION && (value < 1 || value > 5)) return set_error(TEAL_ERR_BAD_ARG, "generation must be 1 .. 5");
   if (knob == TEAL_TUNE_SPEC_ROWS && (value < 0 || value > 32)) return set_error(TEAL_ERR_BAD_ARG, "spec_rows must be 0..32");
   if (knob == TEAL_TUNE_SPEC_MODE && value != 1 && value != 2) return set_error(TEAL_ERR_BAD_ARG, "spec_mode must be 1 or 2");
   if (knob == TEAL_TUNE_FHFMA && value != 0 && value != 1) return set_error(TEAL_ERR_BAD_ARG, "fhfma must be 0 or 1");
   if ((knob == TEAL_TUNE_ROWS_WIDE || knob == TEAL_TUNE_ROWS_NARROW) && (value < 0 || value > 4096 || (value & 31)))
     return set_error(TEAL_ERR_BAD_ARG, "rows per CTA must be a multiple of 32 in [0, 4096]");
   if (knob == TEAL_TUNE_WIDE_KELEMS && value < 0) return set_error(TEAL_ERR_BAD_ARG, "wide_kelems must be >= 0");
-  if (knob == TEAL_TUNE_V1_OPTS && (value < 0 || value > 7)) return set_error(TEAL_ERR_BAD_ARG, "v1_opts is a bit mask 0..7");
+  if (knob == TEAL_TUNE_V1_OPTS && (value < 0 || value > 11)) return set_error(TEAL_ERR_BAD_ARG, "v1_opts is 0..11");
   g_tuning[knob] = value;
   return TEAL_OK;
 }
@@ -55,7 +55,7 @@ int set_config(int id) {
   if (id >= 100 && id < 200) { g_wave_balance = false; id -= 70; }  // 100 + v: rowchunk variant v without wave balancing
   g_sub_cols = 0;
   if (id >= 1000) { g_sub_cols = (id / 1000) * 256; id %= 1000; }  // e.g. 2014: sub-tile 512, 4 tiles
-  if (id < 0 || (id > kNumTmaConfigs && (id < 11 || id > 26) && (id < 30 || id > 59)) || g_sub_cols > 1024)
+  if (id < 0 || (id > kNumTmaConfigs && (id < 11 || id > 26) && (id < 30 || id > 79)) || g_sub_cols > 1024)
     return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
   g_forced_config = id;
   return TEAL_OK;
@@ -74,7 +74,7 @@ int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_
   if (id >= 11 && id <= 26 && !needs_rc)
     return launch_gather_gemv(p, workspace, ws_bytes, out_cols_total, stream, id - 10);
   int variant;
-  if (id >= 30 && id <= 59 && ((!p.tp && !p.chain) || id == 31 || id == 32)) {  // (the fused TP exchange exists for variants 1 and 2)
+  if (id >= 30 && id <= 79 && ((!p.tp && !p.chain) || id == 31 || id == 32)) {  // (the fused TP exchange exists for variants 1 and 2)
     variant = id - 30;
   } else {  // measured on B200 (profiles/r01_bench_gemv_history.jsonl): wide tiles pay off once a launch moves >= ~40 MB
     long long elems = 0;
@@ -85,6 +85,9 @@ int dispatch_gemv(GemvParams& p, void* workspace, size_t ws_bytes, int out_cols_
     } else if (g_tuning[TEAL_TUNE_GENERATION] == 2)  // opt-in, see rowchunk_gemv2_kernel
       variant = g_tuning[TEAL_TUNE_FHFMA] ? ((variant == 1) ? 13 : 15) : ((variant == 1) ? 12 : 14);
     if (!p.tp && !p.chain && g_tuning[TEAL_TUNE_GENERATION] == 3) variant = (variant == 1) ? 20 : 21;  // ... with warp-wise completion
+    if (!p.tp && !p.chain && g_tuning[TEAL_TUNE_GENERATION] == 4) variant = (variant == 1) ? 24 : 25;  // cp.async rings
+    if (!p.tp && !p.chain && g_tuning[TEAL_TUNE_GENERATION] == 5)  // lean list-driven loop, batch structure
+      variant = g_tuning[TEAL_TUNE_FHFMA] ? ((variant == 1) ? 30 : 31) : ((variant == 1) ? 32 : 33);
   }
   return launch_rowchunk(p, workspace, ws_bytes, out_cols_total, stream, variant);
 }

@@ -60,6 +60,16 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p, uint64_t policy) {
   return r;
 }
 
+// the same without the L2 cache-policy descriptor (the descriptor costs two R2UR per load)
+__device__ __forceinline__ uint4 ld_stream_nohint_u4(const void* p) {
+  uint4 r;
+#ifdef TEAL_EMU
+  memcpy(&r, p, sizeof r);
+#else
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
+  return r;
+}
 // f32 += f16 * f16 (FHFMA): the product of two fp16 values is exact in fp32, so this is fma(float(w), float(x), acc)
 __device__ __forceinline__ void rc_fhfma2(float2& acc, uint32_t w2, unsigned short xh) {
 #ifdef TEAL_EMU
@@ -109,6 +119,26 @@ __device__ __forceinline__ uint64_t rc_row_address(uint64_t base, uint32_t row, 
   return a;
 }
 #endif
+
+// cp.async (LDGSTS) ring helpers of the RING instantiations
+#ifdef TEAL_EMU
+__device__ __forceinline__ void rc_cp_async16(unsigned char* base, uint32_t off, const void* src, uint64_t) { memcpy(base + off, src, 16); }
+__device__ __forceinline__ void rc_cp_async_commit() {}
+template <int N> __device__ __forceinline__ void rc_cp_async_wait() {}
+__device__ __forceinline__ uint4 rc_lds_u4(const unsigned char* base, uint32_t off) { uint4 r; memcpy(&r, base + off, 16); return r; }
+#else
+__device__ __forceinline__ void rc_cp_async16(unsigned char* base, uint32_t off, const void* src, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(base) + off), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void rc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void rc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 rc_lds_u4(const unsigned char* base, uint32_t off) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(base) + off) : "memory");
+  return r;
+}
+#endif
+constexpr int kRcRingList = 128;  // list entries per warp of a RING instantiation (4 lane groups)
 
 // gpu-scope flag traffic of the flag-chained launches (CHAIN instantiations)
 #ifdef TEAL_EMU
@@ -169,8 +199,14 @@ __device__ __forceinline__ uint4 rc_ld_volatile_u4(const void* p) {
 //   2 = wait for the producer's WHOLE output (the RMSNorm consumers QKV and gate/up: `chain_all_in` holds the number of consumer
 //   CTAs once every tile of the producer is final).  COUT: 0 = none, 1 = release h tile pairs (gate/up), 3 = release QKV tiles,
 //   4 = count final tiles and release the whole output to the next RMSNorm consumer (o-proj, down).
-template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false, int OPT = 0, int CHAIN = 0>
-__global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
+// RING (> 0: slots per warp): the weight rows land in a per-warp shared-memory ring through cp.async (LDGSTS, L2 evict-first)
+//   instead of registers -- RING - 1 rows stay in flight per warp all the time (cp.async.wait_group is an in-order count, a
+//   register ring refilled row by row serialises on the load scoreboards), the bytes in flight per SM are bounded by shared
+//   memory (7 CTAs x 32 KB) instead of by the register file, and the survivors of the warp's lane groups are compacted into a
+//   per-warp list {local row, fp16 x} in shared memory first.
+template <int VEC, int U, int WARPS, bool TIMED = false, bool TP = false, int OPT = 0, int CHAIN = 0, int RING = 0>
+__global__ void __launch_bounds__(WARPS * 32, ((OPT != 0 || CHAIN != 0) && RING == 0 && !TP && !TIMED) ? 28 / WARPS : 0)
+rowchunk_gemv_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
   constexpr int CIN = CHAIN / 10, COUT = CHAIN % 10;
   // (the chained twins are profiled through the same hook, decided at run time: they are experimental anyway)
@@ -184,7 +220,10 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
   stamp(0);
   constexpr int kRcWarps = WARPS;
   constexpr int kRcThreads = WARPS * 32;
-  __shared__ __align__(16) float s_red[kRcWarps][COLS];
+  constexpr size_t kRedBytes = (size_t)kRcWarps * COLS * 4, kRingBytes = (size_t)RING * kRcWarps * COLS * 2;
+  __shared__ __align__(16) unsigned char s_raw[kRedBytes > kRingBytes ? kRedBytes : kRingBytes];
+  float (*const s_red)[COLS] = reinterpret_cast<float (*)[COLS]>(s_raw);  // (RING: the ring first, the warp partials afterwards)
+  __shared__ uint32_t s_list[RING > 0 ? kRcWarps : 1][RING > 0 ? kRcRingList : 1];
   __shared__ float s_ssq[kRcWarps];
   __shared__ int s_last;
 
@@ -281,6 +320,78 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
   const int kbeg = kc * p.rows_per_cta;
   const int kend = min(p.Z, kbeg + p.rows_per_cta);
   int my_nnz = 0;
+  if constexpr (RING > 0) {
+    // ---- per-warp survivor list in shared memory --------------------------------------------------------------------
+    uint32_t* const list = s_list[warp];
+    int n = 0;
+    for (int k0 = kbeg + warp * 32; k0 < kend; k0 += kRcWarps * 32) {
+      const int k = k0 + lane;
+      float xf = 0.f;
+      if (k < kend) {
+        const __half xh = p.x[k];
+        if (p.in_mode == kInRmsNorm) {
+          xf = __half2float(__hmul(__float2half_rn(__half2float(xh) * rs), p.norm_w[k]));
+          if (p.x_out && ct == 0) p.x_out[k] = __float2half_rn(xf);
+        } else {
+          xf = __half2float(xh);
+        }
+      }
+      const bool keep = (k < kend) && !(fabsf(xf) <= thr);  // strict >, NaN kept (it must poison y like mask*x)
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (p.keep_out && ct == 0 && k < kend) p.keep_out[k] = keep ? 1 : 0;
+      if (keep) list[n + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(k - kbeg) | ((uint32_t)__half_as_ushort(__float2half_rn(xf)) << 16);
+      n += __popc(mask);
+    }
+    __syncwarp();
+    my_nnz = n;
+    if (p.mode == kModeSurvivors) n = 0;  // parity hook: thresholds only, no weights
+    stamp(2);
+    // ---- cp.async ring: RING - 1 rows in flight, every lane copies and later reads its own 16-byte pieces -----------
+    constexpr uint32_t ROWB = COLS * 2;
+    const uint32_t ring0 = (uint32_t)warp * (RING * ROWB) + (uint32_t)lane * 16u;  // byte offset into s_raw
+    const __half* const wrow0 = wbase + (long long)kbeg * ldw;
+    auto issue = [&](int i) {
+      const uint32_t ent = list[i];
+      const __half* src = wrow0 + (long long)(ent & 0xffffu) * ldw;
+      const uint32_t dst = ring0 + (uint32_t)(i % RING) * ROWB;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (vact[v]) rc_cp_async16(s_raw, dst + 512u * v, src + 256 * v, policy);
+    };
+#pragma unroll
+    for (int i = 0; i < RING - 1; ++i) {
+      if (i < n) issue(i);
+      rc_cp_async_commit();
+    }
+    for (int c = 0; c < n; ++c) {
+      if (c + RING - 1 < n) issue(c + RING - 1);
+      rc_cp_async_commit();
+      rc_cp_async_wait<RING - 1>();
+      const uint32_t ent = list[c];
+      const unsigned short xb = (unsigned short)(ent >> 16);
+      const float xs = __half2float(__ushort_as_half(xb));
+      const float2 x2 = make_float2(xs, xs);
+      const uint32_t slot = ring0 + (uint32_t)(c % RING) * ROWB;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (vact[v]) {
+          const uint4 wv = rc_lds_u4(s_raw, slot + 512u * v);
+          if constexpr ((OPT & 2) != 0) {
+            rc_fhfma2(acc[v][0], wv.x, xb);
+            rc_fhfma2(acc[v][1], wv.y, xb);
+            rc_fhfma2(acc[v][2], wv.z, xb);
+            rc_fhfma2(acc[v][3], wv.w, xb);
+          } else {
+            rc_ffma2(acc[v][0], __half22float2(*reinterpret_cast<const __half2*>(&wv.x)), x2);
+            rc_ffma2(acc[v][1], __half22float2(*reinterpret_cast<const __half2*>(&wv.y)), x2);
+            rc_ffma2(acc[v][2], __half22float2(*reinterpret_cast<const __half2*>(&wv.z)), x2);
+            rc_ffma2(acc[v][3], __half22float2(*reinterpret_cast<const __half2*>(&wv.w)), x2);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the warp partials below overwrite the rings
+  } else
   for (int k0 = kbeg + warp * 32; k0 < kend; k0 += kRcWarps * 32) {
     const int k = k0 + lane;
     float xf = 0.f;
@@ -317,7 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv_kernel(const __grid_
             src = wbase + (long long)(k0 + bit[u]) * ldw;
 #pragma unroll
           for (int v = 0; v < VEC; ++v)
-            if (vact[v]) wv[u][v] = ld_stream_u4(src + 256 * v, policy);
+            if (vact[v]) wv[u][v] = (OPT & 8) ? ld_stream_nohint_u4(src + 256 * v) : ld_stream_u4(src + 256 * v, policy);
         }
       }
 #pragma unroll
@@ -729,7 +840,7 @@ __device__ __forceinline__ void rc2_finish_warp(const RcParams& p, const RcSeg& 
 
 // The gather loop of generation 2.  `list` (shared-space address) holds n entries {fp16 bits of x | lane offset << 16};
 // row i+U is requested as soon as row i has been consumed (ring slot i % U, statically indexed by the unrolled u).
-template <int VEC, int U, bool FH, bool FULL>
+template <int VEC, int U, bool FH, bool FULL, bool BATCH = false>
 __device__ __forceinline__ void rc2_gather(float2 (&acc)[VEC][4], const uint32_t* list, int n, uint64_t wrow, uint32_t ldwb,
                                            uint64_t policy, const bool (&vact)[VEC]) {
   uint4 buf[U][VEC];
@@ -746,6 +857,38 @@ __device__ __forceinline__ void rc2_gather(float2 (&acc)[VEC][4], const uint32_t
     const uint64_t src = rc_row_address(wrow, ent[u] >> 16, ldwb);                                               \
     _Pragma("unroll") for (int v = 0; v < VEC; ++v) if (FULL || vact[v])                                         \
         buf[u][v] = ld_stream_u4(reinterpret_cast<const char*>(src) + 512 * v, policy);                          \
+  }
+  if constexpr (BATCH) {  // all requests of a batch are issued before its first row is consumed, nothing is refilled in between
+    for (int base = 0; base < n; base += U) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (base + u < n) RC2_ISSUE(u, base + u)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (base + u < n) {
+          const unsigned short xb = (unsigned short)(ent[u] & 0xffffu);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if (FULL || vact[v]) {
+              if (FH) {
+                rc_fhfma2(acc[v][0], buf[u][v].x, xb);
+                rc_fhfma2(acc[v][1], buf[u][v].y, xb);
+                rc_fhfma2(acc[v][2], buf[u][v].z, xb);
+                rc_fhfma2(acc[v][3], buf[u][v].w, xb);
+              } else {
+                const float xs = __half2float(__ushort_as_half(xb));
+                const float2 x2 = make_float2(xs, xs);
+                rc_ffma2(acc[v][0], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].x)), x2);
+                rc_ffma2(acc[v][1], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].y)), x2);
+                rc_ffma2(acc[v][2], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].z)), x2);
+                rc_ffma2(acc[v][3], __half22float2(*reinterpret_cast<const __half2*>(&buf[u][v].w)), x2);
+              }
+            }
+          }
+        }
+      }
+    }
+    return;
   }
 #pragma unroll
   for (int u = 0; u < U; ++u)
@@ -779,8 +922,8 @@ __device__ __forceinline__ void rc2_gather(float2 (&acc)[VEC][4], const uint32_t
 #undef RC2_ISSUE
 }
 
-template <int VEC, int U, int WARPS, bool FH, bool WW>
-__global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv2_kernel(const __grid_constant__ RcParams p) {
+template <int VEC, int U, int WARPS, bool FH, bool WW, bool BATCH = false>
+__global__ void __launch_bounds__(WARPS * 32, BATCH ? 28 / WARPS : 0) rowchunk_gemv2_kernel(const __grid_constant__ RcParams p) {
   constexpr int COLS = 256 * VEC;
   constexpr int kCap = kRc2MaxPass * 32;
   __shared__ __align__(16) float s_red[WW ? 1 : WARPS][WW ? 4 : COLS];  // warp-wise completion needs no staging
@@ -883,9 +1026,9 @@ __global__ void __launch_bounds__(WARPS * 32) rowchunk_gemv2_kernel(const __grid
   const uint32_t* list = &s_list[warp][0];
   const uint64_t wrow = reinterpret_cast<uint64_t>(wrow0);
   if (wcols == COLS)  // CTA-uniform: a full tile needs no per-lane column predicates
-    rc2_gather<VEC, U, FH, true>(acc, list, n, wrow, ldwb, policy, vact);
+    rc2_gather<VEC, U, FH, true, BATCH>(acc, list, n, wrow, ldwb, policy, vact);
   else
-    rc2_gather<VEC, U, FH, false>(acc, list, n, wrow, ldwb, policy, vact);
+    rc2_gather<VEC, U, FH, false, BATCH>(acc, list, n, wrow, ldwb, policy, vact);
   if (p.probe && lane == 0) {  // measurement probe: gathered vs dense weight bytes
     atomicAdd(p.probe, (unsigned long long)my_nnz * (unsigned long long)wcols * 2ull);
     if (warp == 0) atomicAdd(p.probe + 1, (unsigned long long)max(0, kend - kbeg) * (unsigned long long)wcols * 2ull);
@@ -977,6 +1120,8 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
 #define TEAL_RC(V, UU, W, R) {V, UU, W, R, 1, 0, rowchunk_gemv_kernel<V, UU, W>}
 #define TEAL_RC2(V, UU, W, R, FH) {V, UU, W, R, 2, 0, rowchunk_gemv2_kernel<V, UU, W, FH, false>}
 #define TEAL_RC2W(V, UU, W, R) {V, UU, W, R, 2, 1, rowchunk_gemv2_kernel<V, UU, W, true, true>}
+#define TEAL_RC2B(V, UU, W, R, FH) {V, UU, W, R, 2, 0, rowchunk_gemv2_kernel<V, UU, W, FH, false, true>}
+#define TEAL_RCR(V, W, R, D, O) {V, D, W, R, 4, 0, rowchunk_gemv_kernel<V, 1, W, false, false, O, 0, D>}
   static const Variant kVariants[] = {
       TEAL_RC(1, 8, 4, 128),   // 0
       TEAL_RC(2, 4, 4, 128),   // 1
@@ -1004,10 +1149,36 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       TEAL_RC2W(1, 8, 2, 64),         // 21
       TEAL_RC2W(2, 4, 4, 256),        // 22: 64 lanes per warp (half the REDs and arrivals)
       TEAL_RC2W(1, 8, 4, 256),        // 23
+      // cp.async rings in shared memory (RING instantiations of the generation-1 kernel)
+      TEAL_RCR(2, 4, 128, 8, 0),      // 24: the shape of variant 1, 8 x 1 KB per warp
+      TEAL_RCR(1, 2, 64, 8, 0),       // 25: the shape of variant 2, 8 x 512 B per warp
+      TEAL_RCR(2, 4, 128, 6, 0),      // 26
+      TEAL_RCR(1, 4, 128, 8, 0),      // 27
+      TEAL_RCR(1, 2, 64, 16, 0),      // 28
+      TEAL_RCR(2, 4, 128, 8, 2),      // 29: variant 24 with FHFMA
+      // generation 2's lean instruction stream (list + one IMAD.WIDE per row) with generation 1's batch structure
+      TEAL_RC2B(2, 4, 4, 128, true),  // 30
+      TEAL_RC2B(1, 8, 2, 64, true),   // 31
+      TEAL_RC2B(2, 4, 4, 128, false), // 32
+      TEAL_RC2B(1, 8, 2, 64, false),  // 33
+      TEAL_RC2B(1, 8, 4, 128, true),  // 34
+      TEAL_RC2B(2, 4, 2, 64, true),   // 35
+      TEAL_RC2B(2, 4, 4, 256, true),  // 36
+      TEAL_RC2B(1, 8, 2, 128, true),  // 37
+      TEAL_RC2B(1, 8, 2, 256, true),  // 38
+      TEAL_RC2B(1, 8, 4, 256, true),  // 39
+      TEAL_RC2B(1, 8, 4, 512, true),  // 40
+      TEAL_RC2B(1, 8, 1, 64, true),   // 41
+      TEAL_RC2B(1, 8, 1, 128, true),  // 42
+      TEAL_RC2B(2, 4, 2, 128, true),  // 43
+      TEAL_RC2B(2, 4, 2, 256, true),  // 44
+      TEAL_RC2B(2, 4, 4, 512, true),  // 45
   };
 #undef TEAL_RC
 #undef TEAL_RC2
 #undef TEAL_RC2W
+#undef TEAL_RCR
+#undef TEAL_RC2B
   constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
   if (variant < 0 || variant >= kNumVariants) variant = 0;
   const Variant& var = kVariants[variant];
@@ -1065,11 +1236,13 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
       int r = (int)((gp.Z + nk - 1) / nk);
       if (r < 32 * var.warps) r = 32 * var.warps;
       if (var.gen == 2 && r > 32 * kRc2MaxPass * var.warps) continue;  // a generation-2 warp owns <= kRc2MaxPass lane groups
+      if (var.gen == 4 && r > kRcRingList * var.warps) continue;       // a RING warp lists <= kRcRingList lanes
       const long long cost = (r > rows) ? (r - rows) : 2ll * (rows - r);  // prefer the nominal chunk, lean towards larger
       if (cost < best_cost) { best_cost = cost; best_rows = r; }
     }
     rows = best_rows;
   }
+  if (var.gen == 4 && rows > kRcRingList * var.warps) rows = kRcRingList * var.warps;
   p.rows_per_cta = rows;
   p.nkchunks = (gp.Z + rows - 1) / rows;
   if (var.gen == 2) {  // (variants of generations 2 and 3: the same kernel template)
@@ -1156,13 +1329,15 @@ int launch_rowchunk(GemvParams& gp, void* workspace, size_t ws_bytes, int out_co
 #define TEAL_OPT_ROW(V, UU, W) {nullptr, rowchunk_gemv_kernel<V, UU, W, false, false, 1>, rowchunk_gemv_kernel<V, UU, W, false, false, 2>, \
                                 rowchunk_gemv_kernel<V, UU, W, false, false, 3>, rowchunk_gemv_kernel<V, UU, W, false, false, 4>,          \
                                 rowchunk_gemv_kernel<V, UU, W, false, false, 5>, rowchunk_gemv_kernel<V, UU, W, false, false, 6>,          \
-                                rowchunk_gemv_kernel<V, UU, W, false, false, 7>}
-    static const K kOpt[2][8] = {TEAL_OPT_ROW(2, 4, 4), TEAL_OPT_ROW(1, 8, 2)};
+                                rowchunk_gemv_kernel<V, UU, W, false, false, 7>, rowchunk_gemv_kernel<V, UU, W, false, false, 10>,         \
+                                rowchunk_gemv_kernel<V, UU, W, false, false, 14>, rowchunk_gemv_kernel<V, UU, W, false, false, 8>,        \
+                                rowchunk_gemv_kernel<V, UU, W, false, false, 12>}
+    static const K kOpt[2][12] = {TEAL_OPT_ROW(2, 4, 4), TEAL_OPT_ROW(1, 8, 2)};
 #undef TEAL_OPT_ROW
-    if (opts & 4)
+    if (opts == 4 || opts == 5 || opts == 6 || opts == 7 || opts == 9 || opts == 11)
       for (int s = 0; s < p.nseg && gp.mode != kModeSurvivors; ++s)
         if (p.seg[s].ldw <= 0 || p.seg[s].ldw >= (1ll << 30)) return set_error(TEAL_ERR_UNSUPPORTED, "32-bit row offsets: ldw out of range");
-    kern = kOpt[variant - 1][opts & 7];
+    kern = kOpt[variant - 1][opts];  // 8, 9 = FHFMA + {no L2 hint, no hint + 32-bit offsets}; 10, 11 = the same with conversions + FFMA2
   } else if ((variant == 1 || variant == 2) && grid <= kTimelineMaxCtas) {  // profiling: the two default variants have a TIMED twin
     if (long long* slot = next_debug_timeline_slot()) {           // teal_set_debug_timeline: one slot per launch, in launch order
       p.dbg_time = slot;

@@ -247,10 +247,22 @@ class SparseDecoder:
         return 1
 
     # ------------------------------------------------------------------ weights
-    def _colmajor_rand(self, g, n, z, std=0.02):
-        """fp16 [Z][N] storage viewed as the logical [N, Z] weight (stride (1, N))."""
+    def _colmajor_rand(self, g, n, z, std=0.02, style=None, splits=None):
+        """fp16 [Z][N] storage viewed as the logical [N, Z] weight (stride (1, N)).  Under TP the FULL matrix is drawn
+        (same seed on every rank => the same model everywhere) and this rank keeps its gpt-fast/tp.py shard: colwise =
+        output columns (wqkv per q / k / v region, tp.py:72-78), rowwise = input lanes.  One matrix at a time, so the
+        transient is one full projection (<= 470 MB for the 70B shapes), never the whole model."""
+        from . import tp as _tp
         w = torch.empty(z, n, dtype=torch.float16, device=self.dev)
         w.normal_(0.0, std, generator=g)
+        if self.world > 1 and style is not None:
+            r, ws = self.rank, self.world
+            if splits is not None:   # fused wqkv, storage [Z][q | k | v]: shard every region, re-concatenate
+                w = torch.cat([_tp.shard(t, 1, r, ws) for t in w.split(list(splits), dim=1)], dim=1).contiguous()
+            elif style == "colwise":
+                w = _tp.shard(w, 1, r, ws).contiguous()
+            else:                     # rowwise: this rank's input lanes
+                w = _tp.shard(w, 0, r, ws).contiguous()
         return w.T
 
     def _build_weights(self, seed, sd):
@@ -265,12 +277,15 @@ class SparseDecoder:
             self.tok_emb = torch.empty(a.vocab_size, a.dim, dtype=f16, device=dev).normal_(0, 1.0, generator=g)
             self.lm_head = torch.empty(a.vocab_size, a.dim, dtype=f16, device=dev).normal_(0, 0.02, generator=g)
             self.final_norm = torch.ones(a.dim, dtype=f16, device=dev)
+            kv = a.n_local_heads * a.head_dim
             for _ in range(a.n_layer):
-                # random init is generated per rank at the sharded shape (same seed => TP ranks differ only in
-                # which slice they would hold; for synthetic weights the values themselves are irrelevant)
-                L = dict(wqkv=self._colmajor_rand(g, self.nqkv_l, a.dim), wo=self._colmajor_rand(g, a.dim, self.dim_l),
-                         w1=self._colmajor_rand(g, self.inter_l, a.dim), w3=self._colmajor_rand(g, self.inter_l, a.dim),
-                         w2=self._colmajor_rand(g, a.dim, self.inter_l),
+                # ONE seeded model, sharded like gpt-fast/tp.py:54-156: every rank draws the same full matrices in the same
+                # order and keeps its slice, so TP-N logits can be compared with the single-GPU model's
+                L = dict(wqkv=self._colmajor_rand(g, a.dim + 2 * kv, a.dim, style="colwise", splits=(a.dim, kv, kv)),
+                         wo=self._colmajor_rand(g, a.dim, a.dim, style="rowwise"),
+                         w1=self._colmajor_rand(g, a.intermediate_size, a.dim, style="colwise"),
+                         w3=self._colmajor_rand(g, a.intermediate_size, a.dim, style="colwise"),
+                         w2=self._colmajor_rand(g, a.dim, a.intermediate_size, style="rowwise"),
                          attn_norm=torch.ones(a.dim, dtype=f16, device=dev), ffn_norm=torch.ones(a.dim, dtype=f16, device=dev))
                 self.layers.append(L)
         else:

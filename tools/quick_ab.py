@@ -17,8 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import teal_b200.ops as ops  # noqa: E402
 from teal_b200.model import ModelArgs, SparseDecoder  # noqa: E402
 
-TUNES = [dict(v1_opts=1), dict(v1_opts=2), dict(v1_opts=4), dict(v1_opts=7), dict(generation=2, fhfma=0), dict(rows_wide=256), dict(generation=2), dict(generation=3), dict(generation=2, spec_rows=4), dict(generation=3, spec_rows=8, spec_mode=2),
-         dict(generation=2, spec_rows=8), dict(generation=3, spec_rows=4)]
+TUNES = [dict(generation=5), dict(generation=5, fhfma=0), dict(v1_opts=9), dict(generation=2)]
 
 
 def main():
@@ -27,7 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--workload", default="llama-3-8b")
     ap.add_argument("--out", default="gpurun_out/r01_quick_ab.jsonl")
-    ap.add_argument("--only", default="all", choices=["all", "tunes", "chain"],
+    ap.add_argument("--configs", default="", help="comma-separated teal_set_config ids: tokens/s with every GEMV launch forced to that kernel variant")
+    ap.add_argument("--only", default="all", choices=["all", "tunes", "chain", "configs"],
                     help="the chained variants spin on flags: a protocol bug on hardware traps and poisons the CUDA context, so "
                          "run them in their own process (tunes first, chain second)")
     args = ap.parse_args()
@@ -82,13 +82,24 @@ def main():
     base = run({})
     base_logits = base.pop("dense_logits", None)
     emit(base)
-    for mlp, attn, norms in (() if args.only == "tunes" else ((True, False, False), (False, True, False), (True, True, False), (True, True, True))):
+    for mlp, attn, norms in (() if args.only in ("tunes", "configs") else ((True, False, False), (False, True, False), (True, True, False), (True, True, True))):
         rec = run_chain(mlp, attn, norms)
         lg = rec.pop("dense_logits", None)
         if lg is not None and base_logits is not None:
             rec["dense_logits_max_abs_diff_vs_default"] = round(float((lg - base_logits).abs().max()), 4)
         emit(rec)
-    for tune in ([] if args.only == "chain" else TUNES):
+    for cfg in ([int(c) for c in args.configs.split(",")] if args.configs else []):
+        ops.set_config(cfg)
+        try:
+            rec = run({})
+        finally:
+            ops.set_config(0)
+        rec["config"] = cfg
+        lg = rec.pop("dense_logits", None)
+        if lg is not None and base_logits is not None:
+            rec["dense_logits_max_abs_diff_vs_default"] = round(float((lg - base_logits).abs().max()), 4)
+        emit(rec)
+    for tune in ([] if args.only in ("chain", "configs") else TUNES):
         if time.time() - T0 > args.deadline:
             emit({"skipped": tune})
             continue
