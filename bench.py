@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- decode tok/s, batch 1, Llama-3-8B-shaped random-init model at 50 % activation sparsity.
 
-One "step" = one decoded token through the whole hot path (160 fused sparse-GEMV launches +
+One "step" = one decoded token through the whole hot path (128 fused sparse-GEMV launches +
 attention + lm_head + arg-max), replayed from one captured CUDA graph.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload llama-3-8b] [--sparsity 0.5]
-    python bench.py --impl reference ...      # the reference's CPU threshold+matmul (oracle port)
+    python bench.py --impl reference ...      # the reference's own CPU path (SparsifyFn.apply + F.linear), whole tokens
 
 Prints ONE JSON line (see README / DESIGN.md section 7 for the fields).  For N > 1 launch with
 torchrun; the model is tensor-parallel (gpt-fast/tp.py topology) => "scaling": "strong".
@@ -174,17 +174,13 @@ def main():
                          "(SURVEY.md section 8d, config 5): non-uniform thresholds, 3-threshold QKV, gate != up")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense baselines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--config", type=int, default=0, help="teal_set_config id (tuning)")
-    ap.add_argument("--engine", default="graph", choices=["graph", "program"],
-                    help="graph: one launch per projection group in a CUDA graph (default, fastest measured); program: the "
-                         "whole step as one persistent data-flow kernel (teal_step_program_*, single GPU)")
-    ap.add_argument("--knob", action="append", default=[], metavar="NAME=INT", help="step-program tuning knob (repeatable)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary legs (reference-default sampling, 70B TP leg)")
+    ap.add_argument("--config", type=int, default=0, help="teal_set_config id (kernel variant / K chunk; 0 = by launch size)")
+    ap.add_argument("--repeats", type=int, default=3, help="timed repetitions of the K steps (value = median, spread reported)")
     ap.add_argument("--top-k", type=int, default=0, help="with --temperature: sample like the reference's generate.py default "
-                    "(--temperature 0.8 --top-k 200) instead of greedy arg-max (opt-in: the sampling kernel has not run on hardware yet)")
+                    "(--temperature 0.8 --top-k 200) instead of greedy arg-max in the HEADLINE number")
     ap.add_argument("--temperature", type=float, default=0.0)
-    ap.add_argument("--tune", action="append", default=[], metavar="NAME=INT",
-                    help="opt-in experimental dispatch knob (teal_set_tuning): generation=2|3, spec_rows=R, spec_mode=1|2 "
-                         "(default: generation 1, the hardware-validated kernels)")
+    ap.add_argument("--tp70b", action="store_true", help="add the Llama-2-70B leg (tp_70b object) at this world size")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -200,7 +196,7 @@ def main():
               "l2": "weights (>= 8 GB per GPU) far exceed the 126 MB L2; every step streams them from HBM",
               "engine": "graph"}
 
-    # ------------------------------------------------------------------ reference arm: CPU threshold+matmul
+    # ------------------------------------------------------------------ reference arm: the reference's CPU path
     if args.impl == "reference":
         if rank != 0:
             return
@@ -224,86 +220,78 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        dist.init_process_group("nccl", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
+        dist.init_process_group("nccl", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=180))
         pg = dist.group.WORLD
     from teal_b200 import ops
     from teal_b200.model import SparseDecoder
     ops.set_config(args.config)
-    tune = {k: int(v) for k, v in (kv.split("=") for kv in args.tune)}
-    if tune:
-        ops.set_tuning(**tune)
-        config["tuning"] = tune
+    if args.config:
+        config["kernel_config"] = args.config
     K, Wm = args.steps, args.warmup
     max_seq = max(256, K + Wm + 16)
-    dec = SparseDecoder(margs, device=f"cuda:{local_rank}", max_seq=max_seq, rank=rank, world=world, process_group=pg,
-                        out_cap=max_seq)
-    if args.profile == "greedy-means":
-        sp = {"q": 0.589, "k": 0.469, "v": 0.300, "o": 0.566, "gate": 0.474, "up": 0.417, "down": 0.582}
-        config["sparsity_profile"] = sp
-        thr = dec.calibrate(sp, n_tokens=8)
-    else:
-        thr = dec.calibrate(args.sparsity, n_tokens=8)
-    lib = dec.lib
-    if world > 1:
-        config["tp_exchange"] = ("fused into the row-parallel GEMV finalisers" if getattr(dec, "tp_gemv", False) else
-                                 "one-shot peer-memory kernel" if dec.tp_fused else "nccl all-reduce")
-    if getattr(dec, "chain_mlp", False):
-        config["chain_mlp"] = "flag-chained gate/up -> down (TEAL_CHAIN_MLP=1)"
-    if getattr(dec, "chain_norms", False) and dec.chain_mlp and dec.chain_attn:
-        config["chain_norms"] = "hand-off cells at the RMSNorm points (TEAL_CHAIN_NORMS=1)"
-    if getattr(dec, "chain_attn", False):
-        config["chain_attn"] = "flag-chained QKV -> attention -> o-proj (TEAL_CHAIN_ATTN=1)"
-    if args.temperature > 0:
-        dec.set_sampling(args.temperature, args.top_k, seed=0)
-        config["sampling"] = f"top_k={args.top_k} temperature={args.temperature} (generate.py:49-66 on device)"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    engine = args.engine if world == 1 else "graph"
-    knobs = {k: int(v) for k, v in (kv.split("=") for kv in args.knob)}
-    if engine != "graph" or knobs:
-        config["engine"] = engine if not knobs else f"{engine} {knobs}"
-
-    def timed(mode, steps, warmup, e2e=False):
-        if engine == "program" and mode != "dense_cublas":
-            dec.capture(mode, engine="program", **knobs)
+    def build(margs_, sparsity):
+        dec_ = SparseDecoder(margs_, device=f"cuda:{local_rank}", max_seq=max_seq, rank=rank, world=world, process_group=pg,
+                             out_cap=max_seq)
+        if args.profile == "greedy-means":
+            sp = {"q": 0.589, "k": 0.469, "v": 0.300, "o": 0.566, "gate": 0.474, "up": 0.417, "down": 0.582}
+            config["sparsity_profile"] = sp
+            thr_ = dec_.calibrate(sp, n_tokens=8)
         else:
-            dec.capture(mode)
-        dec.reset(1)
+            thr_ = dec_.calibrate(sparsity, n_tokens=8)
+        return dec_, thr_
+
+    def timed(dec_, mode, steps, warmup, e2e=False):
+        """K graph replays, CUDA events on the replay stream (max over ranks); e2e: the public-API loop with the token
+        H2D from pinned memory and the sampled token D2H + sync every step."""
+        if dec_.graph is None or dec_.graph_mode != mode:
+            dec_.capture(mode)
+        dec_.reset(1)
         host_in = torch.ones(1, dtype=torch.int32).pin_memory()
         host_out = torch.zeros(1, dtype=torch.int32).pin_memory()
-        with torch.cuda.stream(dec.stream):
+        with torch.cuda.stream(dec_.stream):
             for _ in range(warmup):
-                dec.graph.replay()
-            dec.stream.synchronize()
+                dec_.graph.replay()
+            dec_.stream.synchronize()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t_wall = time.perf_counter()
-            e0.record(dec.stream)
+            e0.record(dec_.stream)
             for _ in range(steps):
-                if e2e:  # public-API loop: token H2D from pinned memory, step, sampled token D2H
-                    dec.token.copy_(host_in, non_blocking=True)
-                    dec.graph.replay()
-                    host_out.copy_(dec.token, non_blocking=True)
-                    dec.stream.synchronize()
+                if e2e:
+                    dec_.token.copy_(host_in, non_blocking=True)
+                    dec_.graph.replay()
+                    host_out.copy_(dec_.token, non_blocking=True)
+                    dec_.stream.synchronize()
                     host_in.copy_(host_out)
                 else:
-                    dec.graph.replay()
-            e1.record(dec.stream)
-            dec.stream.synchronize()
+                    dec_.graph.replay()
+            e1.record(dec_.stream)
+            dec_.stream.synchronize()
             wall = time.perf_counter() - t_wall
             barrier()
         ms = e0.elapsed_time(e1)
         if e2e:
             ms = max(ms, wall * 1e3)
         if world > 1:
-            t = torch.tensor([ms], device=dec.dev)
+            t = torch.tensor([ms], device=dec_.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
         return ms / steps
+
+    dec, thr = build(margs, args.sparsity)
+    lib = dec.lib
+    if world > 1:
+        config["tp_exchange"] = ("fused into the row-parallel GEMV finalisers" if getattr(dec, "tp_gemv", False) else
+                                 "one-shot peer-memory kernel" if dec.tp_fused else "nccl all-reduce")
+    if args.temperature > 0:
+        dec.set_sampling(args.temperature, args.top_k, seed=0)
+        config["sampling"] = f"top_k={args.top_k} temperature={args.temperature} (generate.py:49-66 on device)"
 
     probe = torch.zeros(2, dtype=torch.int64, device=dec.dev)
     sampler = ClockSampler(local_rank)
@@ -312,14 +300,25 @@ def main():
     ncu_window = os.environ.get("TEAL_NCU_WINDOW") == "1"  # ncu --profile-from-start off: profile only this region
     if ncu_window:
         torch.cuda.profiler.start()
-    ms_step = timed("sparse", K, Wm)
+    reps = [timed(dec, "sparse", K, Wm) for _ in range(max(1, args.repeats))]
     if ncu_window:
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed("sparse", K, Wm, e2e=True)
+    ms_step = sorted(reps)[len(reps) // 2]
+    ms_e2e = timed(dec, "sparse", K, Wm, e2e=True)
     kernels_per_step = dec.kernels_per_step
     launches = kernels_per_step * K
+
+    # the reference's default sampling (generate.py:353-354: temperature 0.8, top_k 200) as a second reported number
+    sampled = None
+    if not args.no_extra and args.temperature <= 0:
+        try:
+            dec.set_sampling(0.8, 200, seed=0)
+            sampled = {"tok_s": 1e3 / timed(dec, "sparse", max(16, K // 2), 4), "sampling": "top_k=200 temperature=0.8 (generate.py:49-66,353-354 on device)"}
+        except Exception as e:  # noqa: BLE001
+            sampled = {"error": repr(e)[:200]}
+        dec.set_sampling(0.0)
 
     # measured kept fraction / algorithmic bytes of one step (eager, outside the timed region)
     lib.teal_set_bytes_probe(probe.data_ptr())
@@ -335,7 +334,7 @@ def main():
     if not args.no_dense:
         for mode in ("dense_own", "dense_cublas"):
             try:
-                dense[mode] = 1e3 / timed(mode, max(16, K // 2), 4)
+                dense[mode] = 1e3 / timed(dec, mode, max(16, K // 2), 4)
             except Exception as e:  # keep the headline even if a baseline variant fails
                 dense[mode] = None
                 if rank == 0:
@@ -347,7 +346,7 @@ def main():
     peak, peak_kind = measured_peak()
     a = margs
     rf = None
-    # every rank replays 4 sparse steps (they contain the TP all-reduces) to capture each layer's real MLP input
+    # every rank replays 4 sparse steps (they contain the TP exchanges) to capture each layer's real MLP input
     dec.set_thresholds(thr)
     dec.reset(1)
     with torch.cuda.stream(dec.stream):
@@ -362,7 +361,7 @@ def main():
         ws = ops.workspace(dec.dev, dec.stream.cuda_stream)
         probe.zero_()
         t_l = [t for t in thr]
-        reps = max(1, 96 // a.n_layer)
+        nrep = max(1, 96 // a.n_layer)
         with torch.cuda.stream(dec.stream):
             def gate_up_all():
                 for li, Wl in enumerate(dec.layers):
@@ -383,24 +382,42 @@ def main():
                 g.replay()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(dec.stream)
-            for _ in range(reps):
+            for _ in range(nrep):
                 g.replay()
             e1.record(dec.stream)
             dec.stream.synchronize()
-        n_l = reps * a.n_layer
+        n_l = nrep * a.n_layer
         us = e0.elapsed_time(e1) * 1e3 / n_l
         alg = int(probe[0]) / a.n_layer + a.dim * 2 + dec.inter_l * 2  # gathered rows + x + h per launch
-        traffic = None
-        try:  # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu --set full capture (per launch)
+        # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu --set full capture (per launch):
+        # a STATIC record of that capture, only reported while the capture is of the kernel that ran here
+        kname = "sparse_gemv_kernel<1,8,2>"
+        traffic, traffic_src = None, None
+        try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("traffic_bytes") if world == 1 else None
+                rec = json.load(f).get(args.workload, {})
+            if world == 1 and rec.get("kernel") == kname and not args.config:
+                traffic, traffic_src = rec.get("traffic_bytes"), f"static: {rec.get('source')}"
         except Exception:
-            traffic = None
-        kname = {1: "rowchunk_gemv_kernel<2,4,4>", 2: "rowchunk_gemv2_kernel<2,4,4,FH>", 3: "rowchunk_gemv2_kernel<2,4,4,FH,WW>"}[tune.get("generation", 1)]
+            pass
         rf = {"bound": "hbm", "kernel": f"{kname} (fused RMSNorm + gate/up gather-GEMV + SiLU*mul)", "achieved": alg / us / 1e3,
-              "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
-              "us_per_launch": us, "alg_bytes_per_launch": alg, "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),
+              "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": traffic, "traffic_source": traffic_src,
+              "peak_kind": f"of {peak_kind}", "us_per_launch": us, "alg_bytes_per_launch": alg,
+              "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),
               "timing": "CUDA events on the launching stream, graph of n_layer launches, each layer on its own weights and its own real decode input (L2 defeated)"}
+
+    # ------------------------------------------------------------------ Llama-2-70B leg (north_star's TP target; opt-in: 137 GB at N = 1)
+    tp70 = None
+    if args.tp70b and args.workload != "llama-2-70b":
+        del dec
+        torch.cuda.empty_cache()
+        m70 = ModelArgs.from_name("70B")
+        d70, _ = build(m70, args.sparsity)
+        k70 = max(8, K // 4)
+        ms70 = timed(d70, "sparse", k70, 3)
+        dn70 = None if args.no_dense else 1e3 / timed(d70, "dense_own", k70, 3)
+        tp70 = {"workload": "llama-2-70b", "tok_s": 1e3 / ms70, "ms_per_step": ms70, "dense_tok_s": dn70, "steps": k70, "n_gpus": world}
+        dec = d70
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -418,7 +435,9 @@ def main():
                 "dtype": "f16", "data": "synthetic", "config": config,
                 "e2e": {"value": 1e3 / ms_e2e, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "clocks": clocks, "roofline": rf, "cpu_baseline": cpu,
+                "value_spread": {"tok_s_min": 1e3 / max(reps), "tok_s_max": 1e3 / min(reps), "repeats": len(reps)},
                 "dense_tok_s": dense, "speedup_vs_dense": (tok_s / best_dense) if best_dense else None,
+                "sampled": sampled, "tp_70b": tp70,
                 "kept_fraction": gathered / max(1.0, dense_eq),
                 "step_weight_bytes": step_bytes, "step_hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                 "kernels_per_step": kernels_per_step}

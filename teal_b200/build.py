@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libteal_b200.so")
-SOURCES = ["api.cu", "dispatch.cu", "sparse_gemv.cu", "gather_gemv.cu", "rowchunk_gemv.cu", "decode_kernels.cu", "step_program.cu"]
+SOURCES = ["api.cu", "gemv.cu", "decode_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]  # no --use_fast_math: denormals and exact division matter for parity
 
@@ -28,13 +28,28 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+STAMP = LIB + ".srchash"  # content hash of the sources the library was built from (travels with the .so)
+
+
+def source_hash() -> str:
+    """sha256 over the CUDA sources, their headers and the flags: content-based, so a snapshot copy that changes
+    modification times (gpurun) never triggers a rebuild, and an edited source always does."""
+    import hashlib
+    deps = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     deps.append(os.path.join(HERE, "..", "include", "teal_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -59,9 +74,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(err)
         objs.append(obj)
-    res = subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs], capture_output=True, text=True)
+    tmp = LIB + f".tmp{os.getpid()}"
+    res = subprocess.run([_nvcc(), "-shared", "-o", tmp, *objs], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB)  # atomic: a concurrent loader never sees a half-written library
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

@@ -51,13 +51,11 @@ static int fill_common(GemvParams& p, const void* x, void* y, int Z) {
   return TEAL_OK;
 }
 
-// Assign threshold slots, merging equal thresholds so that the scan runs once per distinct value.
-static int slot_for(GemvParams& p, float thr) {
-  for (int k = 0; k < p.nthr; ++k)
-    if (p.thr[k] == thr) return k;
-  p.thr[p.nthr] = thr;
-  return p.nthr++;
+LaunchCtx& launch_ctx() {
+  static thread_local LaunchCtx ctx;
+  return ctx;
 }
+int gemv_num_variants();
 
 }  // namespace teal
 
@@ -82,24 +80,30 @@ int teal_workspace_init(void* workspace, size_t workspace_bytes_, void* stream) 
   return TEAL_OK;
 }
 
-int teal_set_config(int config_id) { return set_config(config_id); }
-int teal_set_tuning(int knob, int value) { return set_tuning(knob, value); }
+// ---- launch context of the calling thread (thread-local: no process-wide state) ------------------------------------
+int teal_set_config(int config_id) {
+  LaunchCtx& c = launch_ctx();
+  if (config_id == 0) { c.variant = -1; c.lanes_per_warp = 0; return TEAL_OK; }
+  const int v = (config_id & 15) - 1, lanes = (config_id >> 4) * 32;
+  if (config_id < 0 || v < 0 || v >= gemv_num_variants() || lanes > kListCap) return set_error(TEAL_ERR_BAD_ARG, "config id out of range");
+  c.variant = v;
+  c.lanes_per_warp = lanes;
+  return TEAL_OK;
+}
 int teal_set_bytes_probe(void* device_u64x2) {
-  set_bytes_probe(reinterpret_cast<unsigned long long*>(device_u64x2));
+  launch_ctx().probe = reinterpret_cast<unsigned long long*>(device_u64x2);
   return TEAL_OK;
 }
 int teal_set_pdl(int enabled) {
-  set_pdl(enabled != 0);
+  launch_ctx().pdl = enabled != 0;
   return TEAL_OK;
 }
-int teal_set_debug_timestamps(void* device_buf) {
-  set_debug_timestamps(reinterpret_cast<long long*>(device_buf));
-  return TEAL_OK;
-}
-
 int teal_set_debug_timeline(void* device_buf, int slots) {
   if (device_buf && slots <= 0) return set_error(TEAL_ERR_BAD_ARG, "timeline: slots must be positive");
-  set_debug_timeline(reinterpret_cast<long long*>(device_buf), slots);
+  LaunchCtx& c = launch_ctx();
+  c.timeline = reinterpret_cast<long long*>(device_buf);
+  c.timeline_slots = device_buf ? slots : 0;
+  c.timeline_next = 0;
   return TEAL_OK;
 }
 
@@ -114,8 +118,8 @@ int teal_sparse_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, i
   p.seg[0].ldw = ldw;
   p.seg[0].ncols = N;
   p.seg[0].out_col0 = 0;
-  p.seg[0].thr_slot = slot_for(p, round_threshold_fp16(threshold));
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+  p.seg[0].thr = round_threshold_fp16(threshold);
+  return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_sparse_qkv_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, int kv_size,
@@ -132,18 +136,18 @@ int teal_sparse_qkv_gemv_f16(const void* x, const void* wt, void* y, int Z, int 
   const __half* w = reinterpret_cast<const __half*>(wt);
   if (tq == tk && tk == tv) {  // uniform sparsity: one region, one survivor list
     p.nseg = 1;
-    p.seg[0] = GemvSeg{w, ldw, N, 0, slot_for(p, tq), 0, 0, 0};
+    p.seg[0] = GemvSeg{w, ldw, N, 0, tq};
   } else {
     const int cols[3] = {n_q, kv_size, kv_size};
     const float thr[3] = {tq, tk, tv};
     int c0 = 0;
     for (int r = 0; r < 3; ++r) {
       if (cols[r] == 0) continue;
-      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, slot_for(p, thr[r]), 0, 0, 0};
+      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, thr[r]};
       c0 += cols[r];
     }
   }
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+  return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, void* h, int Z, int I, int64_t ldw1,
@@ -154,9 +158,9 @@ int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, voi
   if (!w1t || !w3t || !h || I <= 0 || ldw1 < I || ldw3 < I) return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / h / I / ldw");
   p.mode = kModePairSilu;
   p.nseg = 2;
-  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
-  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, slot_for(p, round_threshold_fp16(threshold_up)), 0, 0, 0};
-  return dispatch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, round_threshold_fp16(threshold_gate)};
+  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, round_threshold_fp16(threshold_up)};
+  return launch_sparse_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- fused variants used by the decode pipeline --------------------------------------------------
@@ -191,18 +195,18 @@ int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps,
   const __half* w = reinterpret_cast<const __half*>(wt);
   if (tq == tk && tk == tv) {
     p.nseg = 1;
-    p.seg[0] = GemvSeg{w, ldw, N, 0, slot_for(p, tq), 0, 0, 0};
+    p.seg[0] = GemvSeg{w, ldw, N, 0, tq};
   } else {
     const int cols[3] = {n_q, kv_size, kv_size};
     const float thr[3] = {tq, tk, tv};
     int c0 = 0;
     for (int r = 0; r < 3; ++r) {
       if (cols[r] == 0) continue;
-      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, slot_for(p, thr[r]), 0, 0, 0};
+      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, thr[r]};
       c0 += cols[r];
     }
   }
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+  return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
@@ -217,9 +221,9 @@ int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, 
   if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
   p.x_out = reinterpret_cast<__half*>(xn_out);
   p.nseg = 2;
-  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
-  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, slot_for(p, round_threshold_fp16(threshold_up)), 0, 0, 0};
-  return dispatch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, round_threshold_fp16(threshold_gate)};
+  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, round_threshold_fp16(threshold_up)};
+  return launch_sparse_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y, float* ssq_out, int Z,
@@ -233,111 +237,8 @@ int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* res
   p.resid = reinterpret_cast<const __half*>(resid);
   p.ssq_out = ssq_out;
   p.nseg = 1;
-  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
-}
-
-// ---- flag-chained MLP pair (opt-in): gate/up releases h tile by tile, down starts on the tiles it needs ------------
-int teal_norm_sparse_gate_up_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
-                                       const void* w3t, void* h, int Z, int I, int64_t ldw1, int64_t ldw3, double threshold_gate,
-                                       double threshold_up, int wait_all, void* workspace, size_t workspace_bytes_, void* stream) {
-  GemvParams p;
-  if (int rc = fill_common(p, x, h, Z)) return rc;
-  if (!w1t || !w3t || !h || !norm_w || !ssq_in || I <= 0 || ldw1 < I || ldw3 < I)
-    return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / h / norm_w / ssq_in / I / ldw");
-  p.chain_wait_all = wait_all;
-  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
-  p.mode = kModePairSilu;
-  if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
-  p.nseg = 2;
-  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, slot_for(p, round_threshold_fp16(threshold_gate)), 0, 0, 0};
-  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, slot_for(p, round_threshold_fp16(threshold_up)), 0, 0, 0};
-  p.chain = 1;
-  chain_describe(Z, I, &p.chain_rows, &p.chain_ctiles, &p.chain_cols);
-  return dispatch_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
-}
-
-int teal_sparse_gemv_residual_chain_f16(const void* h, const void* wt, const void* resid, void* y, float* ssq_out, int I, int N,
-                                        int64_t ldw, double threshold, int release_all_ctas, void* workspace, size_t workspace_bytes_,
-                                        void* stream) {
-  GemvParams p;
-  if (int rc = fill_common(p, h, y, I)) return rc;
-  p.chain_release_all = release_all_ctas;
-  if (!wt || !y || !resid || N <= 0 || ldw < N) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw");
-  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
-  p.mode = kModePlain;
-  p.out_mode = kOutAddResidual;
-  p.resid = reinterpret_cast<const __half*>(resid);
-  p.ssq_out = ssq_out;
-  p.nseg = 1;
-  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
-  p.chain = 2;
-  chain_describe(N, I, &p.chain_rows, &p.chain_ctiles, &p.chain_cols);
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
-}
-
-// ---- flag-chained attention block (opt-in): QKV releases tile by tile, attention starts per head, o-proj per K chunk ----
-int teal_norm_sparse_qkv_gemv_chain_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt, void* y,
-                                        int Z, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
-                                        double threshold_v, int n_head, int n_kv_head, int head_dim, int wait_all, void* workspace,
-                                        size_t workspace_bytes_, void* stream) {
-  GemvParams p;
-  if (int rc = fill_common(p, x, y, Z)) return rc;
-  p.chain_wait_all = wait_all;
-  if (!wt || !y || !norm_w || !ssq_in || N != (n_head + 2 * n_kv_head) * head_dim || ldw < N || kv_size != n_kv_head * head_dim)
-    return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / norm_w / ssq_in / N / ldw / kv_size");
-  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
-  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k), tv = round_threshold_fp16(threshold_v);
-  ChainAttn ca;
-  if (int rc = chain_attn_describe(&ca, workspace, workspace_bytes_, Z, n_head, n_kv_head, head_dim, tq == tk && tk == tv)) return rc;
-  p.mode = kModePlain;
-  if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
-  const __half* w = reinterpret_cast<const __half*>(wt);
-  const float thr[3] = {tq, tk, tv};
-  for (int s = 0; s < ca.nseg; ++s)
-    p.seg[p.nseg++] = GemvSeg{w + ca.seg_col0[s], ldw, ca.seg_ncols[s], ca.seg_col0[s], slot_for(p, thr[s]), 0, 0, 0};
-  p.chain = 3;
-  p.ca = &ca;
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
-}
-
-int teal_attn_decode_chain_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos, void* out,
-                               int n_head, int n_kv_head, int head_dim, int max_seq, int dim, double threshold_q, double threshold_k,
-                               double threshold_v, void* workspace, size_t workspace_bytes_, void* stream) {
-  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k), tv = round_threshold_fp16(threshold_v);
-  ChainAttn ca;
-  if (int rc = chain_attn_describe(&ca, workspace, workspace_bytes_, dim, n_head, n_kv_head, head_dim, tq == tk && tk == tv)) return rc;
-  return launch_attn_decode_chain(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(freqs_cis),
-                                  reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), pos,
-                                  reinterpret_cast<__half*>(out), max_seq, ca, reinterpret_cast<cudaStream_t>(stream));
-}
-
-int teal_sparse_o_proj_chain_f16(const void* att, const void* wt, const void* resid, void* y, float* ssq_out, int Z, int N, int64_t ldw,
-                                 double threshold, int n_head, int n_kv_head, int head_dim, int release_all_ctas, void* workspace,
-                                 size_t workspace_bytes_, void* stream) {
-  GemvParams p;
-  if (int rc = fill_common(p, att, y, Z)) return rc;
-  p.chain_release_all = release_all_ctas;
-  if (!wt || !y || !resid || N <= 0 || ldw < N || Z != n_head * head_dim) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw / Z");
-  if (forced_config() || tuning(TEAL_TUNE_GENERATION) != 1) return set_error(TEAL_ERR_UNSUPPORTED, "chained launches need the default dispatch");
-  ChainAttn ca;
-  if (int rc = chain_attn_describe(&ca, workspace, workspace_bytes_, N, n_head, n_kv_head, head_dim, true)) return rc;
-  p.mode = kModePlain;
-  p.out_mode = kOutAddResidual;
-  p.resid = reinterpret_cast<const __half*>(resid);
-  p.ssq_out = ssq_out;
-  p.nseg = 1;
-  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
-  p.chain = 4;
-  p.chain_rows = ca.rows_o;
-  p.chain_ctiles = ca.ctiles_o;
-  p.chain_cols = head_dim;
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
-}
-
-int teal_chain_consumer_ctas(int kind, int dim, int a, int b, int c, double threshold_q, double threshold_k, double threshold_v) {
-  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k), tv = round_threshold_fp16(threshold_v);
-  return chain_consumer_ctas(kind, dim, a, b, c, tq == tk && tk == tv);
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, round_threshold_fp16(threshold)};
+  return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
@@ -362,8 +263,8 @@ int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_
   p.ssq_out = ssq_out;
   p.tp = &tp;
   p.nseg = 1;
-  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, slot_for(p, round_threshold_fp16(threshold)), 0, 0, 0};
-  return dispatch_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(wt), ldw, N, 0, round_threshold_fp16(threshold)};
+  return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- the rest of the decode step -------------------------------------------------------------------
@@ -412,13 +313,12 @@ int teal_survivors_f16(const void* x, int Z, double threshold, int32_t* idx_out,
   if (!idx_out || !count_out) return set_error(TEAL_ERR_BAD_ARG, "null output");
   p.mode = kModeSurvivors;
   p.nseg = 0;
-  p.nthr = 0;
-  slot_for(p, round_threshold_fp16(threshold));
+  p.seg[0].thr = round_threshold_fp16(threshold);
   // the production kernel writes its keep mask into the upper quarter of idx_out (Z bytes of scratch); a
   // single-CTA pass then turns it into the sorted index list (it never overtakes the mask bytes it still needs)
   p.keep_out = reinterpret_cast<unsigned char*>(idx_out) + (size_t)3 * Z;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (int rc = dispatch_gemv(p, nullptr, 0, 0, s)) return rc;
+  if (int rc = launch_sparse_gemv(p, nullptr, 0, 0, s)) return rc;
   return launch_mask_to_indices(p.keep_out, Z, idx_out, count_out, s);
 }
 

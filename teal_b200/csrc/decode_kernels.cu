@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   griddep_wait();
   griddep_launch_dependents();  // n_head CTAs leave most of the machine free: the o-proj grid moves in and waits for us
   const int pos = pos_ptr[0];
+  if (pos < 0 || pos >= max_seq) {  // beyond the KV cache / RoPE table (the host raises before this can happen): touch nothing
+    if (tid < HD) out[(size_t)h * HD + tid] = __ushort_as_half((unsigned short)0x7e00);  // NaN: a silent wrong token is worse
+    return;
+  }
 
   // ---- RoPE on q (this head) and on the new k (its kv head); v passes through ---------------------
   const __half* qh = qkv + (size_t)h * HD;
@@ -179,176 +183,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
       o = fmaf(s_acc[w][tid], f, o);
     }
     out[(size_t)h * HD + tid] = __float2half_rn(o / L);
-  }
-}
-
-// ---- flag-chained attention block (opt-in, not yet run on hardware): the attention kernel between a QKV producer and an
-// o-proj consumer that are all in flight together.  A copy of attn_decode_kernel -- which stays
-// untouched, it is hardware-validated -- with the wait / release protocol of the CHAIN row-chunk twins.
-#ifdef TEAL_EMU
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) { ::emu::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-#else
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-#endif
-__device__ __forceinline__ float2 chain_ld_half2(const __half* p) {  // written by a grid that is still running: read at L2
-  const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(p));
-  return __half22float2(*reinterpret_cast<const __half2*>(&v));
-}
-
-template <int HD>
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_chain_kernel(
-    const __half* __restrict__ qkv,    // [n_head*HD | n_kv*HD | n_kv*HD]
-    const __half* __restrict__ freqs,  // [max_seq][HD/2][2] fp16 (cos, sin)
-    __half* __restrict__ k_cache,      // [n_kv][max_seq][HD]
-    __half* __restrict__ v_cache, const int* __restrict__ pos_ptr, __half* __restrict__ out,  // [n_head*HD]
-    int n_head, int n_kv, int max_seq, float scale, const __grid_constant__ ChainAttn ca) {
-  static_assert(HD % 64 == 0 && HD <= 256, "head_dim");
-  constexpr int EPL = HD / 32;  // elements per lane (4 for HD = 128)
-  __shared__ float s_q[HD];
-  __shared__ float s_knew[HD];
-  __shared__ float s_vnew[HD];
-  __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
-  __shared__ float s_acc[kAttnWarps][HD];
-
-  const int h = blockIdx.x;
-  const int kvh = h / (n_head / n_kv);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // flag-chained launch: no griddepcontrol.wait -- threads 0..5 wait for the (<= 2) QKV tiles of the head's q / k / v slices
-  griddep_launch_dependents();
-  if (tid < 6) {
-    int ca0, cb0;
-    chain_slice(ca, h, tid >> 1, &ca0, &cb0);
-    const int t_first = chain_tile_of(ca, ca0), t_last = chain_tile_of(ca, cb0 - 1);
-    if ((tid & 1) <= t_last - t_first) {
-      const unsigned* cell = ca.ready_qkv + t_first + (tid & 1);
-      const long long w0 = clock64();
-      while (ld_acquire_gpu_u32(cell) == 0u) {
-        if (clock64() - w0 > 4000000000ll) __trap();
-      }
-    }
-  }
-  __syncthreads();
-  const int pos = pos_ptr[0];
-
-  // ---- RoPE on q (this head) and on the new k (its kv head); v passes through ---------------------
-  const __half* qh = qkv + (size_t)h * HD;
-  const __half* kh = qkv + (size_t)n_head * HD + (size_t)kvh * HD;
-  const __half* vh = qkv + (size_t)(n_head + n_kv) * HD + (size_t)kvh * HD;
-  const __half* fr = freqs + (size_t)pos * HD;  // HD/2 pairs * 2
-  if (tid < HD / 2) {
-    const float c = __half2float(fr[2 * tid]), s = __half2float(fr[2 * tid + 1]);
-    const float2 qf = chain_ld_half2(qh + 2 * tid), kf2 = chain_ld_half2(kh + 2 * tid);
-    const float q0 = qf.x, q1 = qf.y;
-    const float k0 = kf2.x, k1 = kf2.y;
-    // model.py:309-315, result cast back to fp16 (type_as)
-    const __half qa = __float2half_rn(q0 * c - q1 * s), qb = __float2half_rn(q1 * c + q0 * s);
-    const __half ka = __float2half_rn(k0 * c - k1 * s), kb = __float2half_rn(k1 * c + k0 * s);
-    s_q[2 * tid] = __half2float(qa);
-    s_q[2 * tid + 1] = __half2float(qb);
-    s_knew[2 * tid] = __half2float(ka);
-    s_knew[2 * tid + 1] = __half2float(kb);
-    if (h % (n_head / n_kv) == 0) {  // one CTA per kv head appends to the cache (model.py:93-94)
-      k_cache[((size_t)kvh * max_seq + pos) * HD + 2 * tid] = ka;
-      k_cache[((size_t)kvh * max_seq + pos) * HD + 2 * tid + 1] = kb;
-    }
-  } else if (tid < HD / 2 + HD / 2) {
-    const int i = tid - HD / 2;
-    const float2 vf2 = chain_ld_half2(vh + 2 * i);
-    const __half v0 = __float2half_rn(vf2.x), v1 = __float2half_rn(vf2.y);
-    s_vnew[2 * i] = __half2float(v0);
-    s_vnew[2 * i + 1] = __half2float(v1);
-    if (h % (n_head / n_kv) == 0) {
-      v_cache[((size_t)kvh * max_seq + pos) * HD + 2 * i] = v0;
-      v_cache[((size_t)kvh * max_seq + pos) * HD + 2 * i + 1] = v1;
-    }
-  }
-  __syncthreads();
-  if (tid < 6) {  // q, k, v are in shared memory: this CTA is done with the tiles it waited for
-    int ca0, cb0;
-    chain_slice(ca, h, tid >> 1, &ca0, &cb0);
-    const int t_first = chain_tile_of(ca, ca0), t_last = chain_tile_of(ca, cb0 - 1);
-    if ((tid & 1) <= t_last - t_first) atomicSub(ca.ready_qkv + t_first + (tid & 1), 1u);
-  }
-
-  // ---- online-softmax attention: warp w takes positions w, w + kAttnWarps, ... ---------------------
-  float qreg[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) qreg[e] = s_q[lane * EPL + e];
-  float m = -CUDART_INF_F, l = 0.f, acc[EPL];
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  const __half* kbase = k_cache + (size_t)kvh * max_seq * HD;
-  const __half* vbase = v_cache + (size_t)kvh * max_seq * HD;
-  // 4 positions per iteration so that the 8 global loads of a lane are independent (latency-bound at short context)
-  constexpr int PB = 4;
-  for (int p0 = warp; p0 <= pos; p0 += kAttnWarps * PB) {
-    float kk[PB][EPL], vv[PB][EPL];
-#pragma unroll
-    for (int b = 0; b < PB; ++b) {
-      const int p = p0 + b * kAttnWarps;
-      if (p < pos) {
-        const __half2* kp = reinterpret_cast<const __half2*>(kbase + (size_t)p * HD + lane * EPL);
-        const __half2* vp = reinterpret_cast<const __half2*>(vbase + (size_t)p * HD + lane * EPL);
-#pragma unroll
-        for (int e = 0; e < EPL / 2; ++e) {
-          const float2 kf = __half22float2(kp[e]), vf = __half22float2(vp[e]);
-          kk[b][2 * e] = kf.x; kk[b][2 * e + 1] = kf.y;
-          vv[b][2 * e] = vf.x; vv[b][2 * e + 1] = vf.y;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) { kk[b][e] = s_knew[lane * EPL + e]; vv[b][e] = s_vnew[lane * EPL + e]; }
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < PB; ++b) {
-      const int p = p0 + b * kAttnWarps;
-      if (p <= pos) {
-        float s = 0.f;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) s = fmaf(qreg[e], kk[b][e], s);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        s *= scale;
-        const float mn = fmaxf(m, s);
-        const float corr = __expf(m - mn), pe = __expf(s - mn);
-        l = l * corr + pe;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pe, vv[b][e], acc[e] * corr);
-        m = mn;
-      }
-    }
-  }
-  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) s_acc[warp][lane * EPL + e] = acc[e];
-  __syncthreads();
-  // ---- merge the warps' partial softmaxes ---------------------------------------------------------
-  if (tid < HD) {
-    float M = -CUDART_INF_F;
-#pragma unroll
-    for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, s_m[w]);
-    float L = 0.f, o = 0.f;
-#pragma unroll
-    for (int w = 0; w < kAttnWarps; ++w) {
-      const float f = (s_m[w] == -CUDART_INF_F) ? 0.f : __expf(s_m[w] - M);
-      L = fmaf(s_l[w], f, L);
-      o = fmaf(s_acc[w][tid], f, o);
-    }
-    out[(size_t)h * HD + tid] = __float2half_rn(o / L);
-  }
-  __syncthreads();
-  if (tid == 0) {  // the head's output is final: release it to the o-proj CTAs whose K chunk overlaps it
-    __threadfence();
-    st_release_gpu_u32(ca.ready_att + h, chain_att_readers(ca, h));
   }
 }
 
@@ -755,7 +589,7 @@ static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = launch_ctx().pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   if (e != cudaSuccess) return set_cuda_error(e, what);
   return TEAL_OK;
@@ -778,21 +612,6 @@ int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, 
     return launch_pdl(attn_decode_kernel<64>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, freqs,
                       k_cache, v_cache, pos, out, n_head, n_kv, max_seq, scale);
   return set_error(TEAL_ERR_UNSUPPORTED, "attn_decode: head_dim must be 64 or 128");
-}
-
-int launch_attn_decode_chain(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos, __half* out,
-                             int max_seq, const ChainAttn& ca, cudaStream_t stream) {
-  if (!qkv || !freqs || !k_cache || !v_cache || !pos || !out || ca.n_head <= 0 || ca.n_kv <= 0 || ca.n_head % ca.n_kv || !ca.ready_qkv ||
-      !ca.ready_att || ca.hd > ca.cols)
-    return set_error(TEAL_ERR_BAD_ARG, "attn_decode_chain: bad argument");
-  const float scale = 1.0f / sqrtf((float)ca.hd);
-  if (ca.hd == 128)
-    return launch_pdl(attn_decode_chain_kernel<128>, dim3(ca.n_head), dim3(kAttnThreads), 0, stream, "attn chain launch", qkv, freqs,
-                      k_cache, v_cache, pos, out, ca.n_head, ca.n_kv, max_seq, scale, ca);
-  if (ca.hd == 64)
-    return launch_pdl(attn_decode_chain_kernel<64>, dim3(ca.n_head), dim3(kAttnThreads), 0, stream, "attn chain launch", qkv, freqs,
-                      k_cache, v_cache, pos, out, ca.n_head, ca.n_kv, max_seq, scale, ca);
-  return set_error(TEAL_ERR_UNSUPPORTED, "attn_decode_chain: head_dim must be 64 or 128");
 }
 
 int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,

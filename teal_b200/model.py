@@ -141,7 +141,10 @@ class SparseDecoder:
         self.thresholds: List[Optional[Dict[str, float]]] = [None] * a.n_layer
         self._build_weights(seed, state_dict)
         f16, dev = torch.float16, self.dev
-        self.freqs = precompute_freqs_cis(min(a.block_size, self.max_seq), self.hd, a.rope_base).to(dev).contiguous()
+        # one RoPE row per cache position: the reference caps max_seq_length at block_size (generate.py:171) -- longer
+        # caches get their own rows instead of reading past the table
+        self.freqs = precompute_freqs_cis(self.max_seq, self.hd, a.rope_base).to(dev).contiguous()
+        self.steps_enqueued = 0  # host-side mirror of the device position (bounds check, see _check_room)
         self.k_cache = [torch.zeros(self.n_kv_l, self.max_seq, self.hd, dtype=f16, device=dev) for _ in range(a.n_layer)]
         self.v_cache = [torch.zeros(self.n_kv_l, self.max_seq, self.hd, dtype=f16, device=dev) for _ in range(a.n_layer)]
         # step state (device resident so the graph replays unchanged)
@@ -162,38 +165,41 @@ class SparseDecoder:
             self._setup_peer_exchange()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_mode = None
-        self.graph_engine = None
-        self.program = None          # StepProgram (engine="program"): the whole step as one persistent kernel
-        self.program_mode = None
-        self.program_tuning = None
-        self.program_scratch = None
         self.taps = None  # calibration taps
         self.force_tp_path = False  # tests: take the (plain GEMV -> all-reduce -> residual_add) route at world == 1
         self.ffn_inputs = None  # when a list: per-layer copies of (x, ssq) entering the MLP block (bench roofline)
         self.kernels_per_step = 0
         self.sampling = None  # None = greedy arg-max; else dict(temperature, top_k, seed): generate.py:49-66 on device
-        # opt-in (not yet run on hardware): flag-chained MLP pair -- down starts on the h tiles it needs instead of waiting
-        # for the whole gate/up grid (teal_*_chain_f16)
-        self.chain_mlp = os.environ.get("TEAL_CHAIN_MLP") == "1" and world == 1
-        # ... and the flag-chained attention block: QKV releases its tiles, attention starts per head, o-proj per K chunk
-        self.chain_attn = os.environ.get("TEAL_CHAIN_ATTN") == "1" and world == 1
-        # ... and the two RMSNorm points between the blocks as hand-off cells instead of grid-wide waits (needs both blocks chained)
-        self.chain_norms = os.environ.get("TEAL_CHAIN_NORMS") == "1" and world == 1
 
     # ------------------------------------------------------------------ TP exchange buffers
     def _setup_peer_exchange(self):
-        """Symmetric (peer-mapped) memory for the fused one-shot all-reduce: two fp16 partial buffers [dim] + a flag
-        array per rank.  Falls back to NCCL all-reduce (all ranks together) if symmetric memory is unavailable."""
+        """Symmetric (peer-mapped) memory for the TP exchange step: two fp16 partial buffers [dim] + a flag array per rank.
+        TEAL_TP_ALLREDUCE = gemv (default: the exchange fused into the row-parallel GEMV's tile finalisers) | fused (one-shot
+        peer-memory kernel after a plain GEMV) | nccl (ncclAllReduce + residual add).  Every rank first agrees on what
+        is available (all_reduce MIN) and only then enters the collective rendezvous, so a rank-local failure (import,
+        environment) falls back to NCCL on all ranks together instead of hanging the others inside rendezvous."""
         import ctypes
-        import os
         import torch.distributed as dist
+        mode = os.environ.get("TEAL_TP_ALLREDUCE", "gemv")
+        want = {"nccl": 0, "fused": 1, "gemv": 2}.get(mode, 0)
+        symm = None
+        if want:
+            try:
+                import torch.distributed._symmetric_memory as symm
+            except Exception as e:  # noqa: BLE001
+                want, self._symm_error = 0, repr(e)
+        flag = torch.tensor([want], device=self.dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+        want = int(flag.item())
+        self.tp_fused, self.tp_gemv = False, False
+        if want == 0:
+            if self.rank == 0:
+                print(f"[teal_b200] TP exchange: NCCL all-reduce ({getattr(self, '_symm_error', 'TEAL_TP_ALLREDUCE=' + mode)})", flush=True)
+            return
+        dim, ws = self.args.dim, self.world
+        pg = self.pg if self.pg is not None else dist.group.WORLD
         ok = 1
-        try:
-            if os.environ.get("TEAL_TP_ALLREDUCE", "fused") != "fused":
-                raise RuntimeError("disabled by TEAL_TP_ALLREDUCE")
-            import torch.distributed._symmetric_memory as symm
-            dim, ws = self.args.dim, self.world
-            pg = self.pg if self.pg is not None else dist.group.WORLD
+        try:  # from here on every rank makes the same collective calls; a failure is reported through the second vote
             if hasattr(symm, "enable_symm_mem_for_group"):
                 try:
                     symm.enable_symm_mem_for_group(pg.group_name)
@@ -209,10 +215,7 @@ class SparseDecoder:
             self.tp_flags = (ctypes.c_void_p * ws)(*[p + 4 * dim for p in ptrs])
             self.tp_part = [t[par * dim * 2:(par + 1) * dim * 2].view(torch.float16).view(1, 1, dim) for par in (0, 1)]
             self.tp_epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)
-            self.tp_gemv = False
-            if os.environ.get("TEAL_TP_ALLREDUCE", "fused") == "gemv":
-                # opt-in (not yet run on hardware): the exchange fused into the row-parallel GEMV's tile finalisers
-                # (teal_sparse_gemv_tp_exchange_f16) -- per parity a flag array [world * 64] per rank, local epochs [64]
+            if want == 2:  # per parity a flag array [world * 64] per rank, local epochs [64]
                 t2 = symm.empty(2 * ws * 64 * 4, dtype=torch.uint8, device=self.dev)
                 t2.zero_()
                 hdl2 = symm.rendezvous(t2, pg)
@@ -221,16 +224,15 @@ class SparseDecoder:
                 self._symm2 = (t2, hdl2)
                 self.tp_tile_flags = [(ctypes.c_void_p * ws)(*[p + par * ws * 64 * 4 for p in p2]) for par in (0, 1)]
                 self.tp_tile_epochs = [torch.zeros(64, dtype=torch.int32, device=self.dev) for _ in (0, 1)]
-                self.tp_gemv = True
-        except Exception as e:  # noqa: BLE001 - any failure means: use NCCL
-            ok = 0
-            self._symm_error = repr(e)
+        except Exception as e:  # noqa: BLE001
+            ok, self._symm_error = 0, repr(e)
         flag = torch.tensor([ok], device=self.dev, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
         torch.cuda.synchronize()
-        self.tp_fused = bool(int(flag.item()))
-        if not self.tp_fused and self.rank == 0:
-            print(f"[teal_b200] fused peer-memory all-reduce unavailable ({getattr(self, '_symm_error', 'peer failed')}); "
+        if int(flag.item()):
+            self.tp_fused, self.tp_gemv = True, want == 2
+        elif self.rank == 0:
+            print(f"[teal_b200] peer-memory TP exchange unavailable ({getattr(self, '_symm_error', 'a peer failed')}); "
                   "using NCCL all-reduce", flush=True)
 
     def _exchange(self, parity: int, sp):
@@ -317,7 +319,6 @@ class SparseDecoder:
         self.thresholds = list(thresholds)
         self.sparse = any(t is not None for t in thresholds)
         self.graph = None
-        self.program = None
 
     def calibrate(self, sparsities, n_tokens: int = 16, seed: int = 7):
         """Synthetic-model calibration through the reference's own path: run dense
@@ -362,6 +363,7 @@ class SparseDecoder:
         self.token.fill_(int(first_token))
         self.pos.zero_()
         self.argmax.zero_()
+        self.steps_enqueued = 0
 
     def _allreduce(self, t):
         if self.world > 1:
@@ -385,27 +387,7 @@ class SparseDecoder:
             W = L[li]
             t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else dense_t
             tap = self.taps[li] if self.taps is not None else None
-            chain_attn = self.chain_attn and tap is None and mode != "dense_cublas" and self.world == 1 and not self.force_tp_path
-            chain_norms = chain_attn and self.chain_mlp and self.chain_norms
-            rel_o = rel_d = 0  # grid sizes of the next RMSNorm consumers (the hand-off cells are released to that many CTAs)
-            if chain_norms:
-                rel_o = lib.teal_chain_consumer_ctas(1, a.dim, self.inter_l, 0, 0, 0.0, 0.0, 0.0)
-                if li + 1 < a.n_layer:
-                    tn = self.thresholds[li + 1] if (mode == "sparse" and self.thresholds[li + 1] is not None) else dense_t
-                    rel_d = lib.teal_chain_consumer_ctas(0, a.dim, self.n_head_l, self.n_kv_l, self.hd, tn["q"], tn["k"], tn["v"])
-            if chain_attn:
-                chk(lib.teal_norm_sparse_qkv_gemv_chain_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps, ssq, W["wqkv"].data_ptr(),
-                                                            self.qkv.data_ptr(), a.dim, self.nqkv_l, W["wqkv"].stride(1), self.kv_l, t["q"], t["k"],
-                                                            t["v"], self.n_head_l, self.n_kv_l, self.hd, 1 if (chain_norms and li > 0) else 0,
-                                                            wsp, wsn, sp), "qkv_chain")
-                chk(lib.teal_attn_decode_chain_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
-                                                   self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(), self.n_head_l,
-                                                   self.n_kv_l, self.hd, self.max_seq, a.dim, t["q"], t["k"], t["v"], wsp, wsn, sp), "attn_chain")
-                chk(lib.teal_sparse_o_proj_chain_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), self.x.data_ptr(), ssq,
-                                                     self.dim_l, a.dim, W["wo"].stride(1), t["o"], self.n_head_l, self.n_kv_l, self.hd, rel_o,
-                                                     wsp, wsn, sp), "o_chain")
-                n_launch += 2  # (the o projection is counted with the MLP launches below)
-            elif mode == "dense_cublas":
+            if mode == "dense_cublas":
                 xn = _rms_norm(self.x, W["attn_norm"], a.norm_eps)
                 torch.matmul(xn, W["wqkv"].T, out=self.qkv)
             else:
@@ -417,7 +399,7 @@ class SparseDecoder:
                     "norm_qkv")
                 if tap is not None:
                     tap["attn_h1"].append(xn_out.flatten().float().cpu())
-            if not chain_attn:  # (the chained block above already ran attention and the o projection)
+            if True:  # attention block: RoPE + KV append + attention, then the o projection
                 chk(lib.teal_attn_decode_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
                                              self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
                                              self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
@@ -451,15 +433,6 @@ class SparseDecoder:
                     n_launch += self._exchange(0, sp)
             if self.ffn_inputs is not None:
                 self.ffn_inputs.append((self.x.clone(), self.ssq.clone()))
-            if self.chain_mlp and tap is None and self.world == 1 and not self.force_tp_path:
-                chk(lib.teal_norm_sparse_gate_up_chain_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq, W["w1"].data_ptr(),
-                                                           W["w3"].data_ptr(), self.h.data_ptr(), a.dim, self.inter_l, W["w1"].stride(1),
-                                                           W["w3"].stride(1), t["gate"], t["up"], 1 if chain_norms else 0, wsp, wsn, sp),
-                    "gate_up_chain")
-                chk(lib.teal_sparse_gemv_residual_chain_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(), self.x.data_ptr(), ssq,
-                                                            self.inter_l, a.dim, W["w2"].stride(1), t["down"], rel_d, wsp, wsn, sp), "down_chain")
-                n_launch += 3
-                continue
             xn_out = torch.empty_like(self.x) if tap is not None else None
             chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq,
                                                  W["w1"].data_ptr(), W["w3"].data_ptr(), self.h.data_ptr(),
@@ -495,102 +468,55 @@ class SparseDecoder:
                              self.out_tokens.data_ptr(), self.out_tokens.numel(), sp), "advance")
         self.kernels_per_step = n_launch + 2
 
-    # ------------------------------------------------------------------ step program (one kernel per token)
-    def build_program(self, mode: str = "sparse", **tuning):
-        """Plan the whole step (same buffers, same arithmetic as `_enqueue_step`) into a `StepProgram`: one persistent
-        data-flow kernel per token instead of 5 launches per layer.  `tuning`: the knobs of teal_step_desc
-        (rows_small, rows_large, group_qkv, group_gate_up, head_rows, wide_melems, ctas_per_sm, ...)."""
-        from . import program as _prog
-        if self.world != 1:
-            raise NotImplementedError("the step program is single-GPU (the TP exchange step is not a phase yet)")
-        if mode not in ("sparse", "dense_own"):
-            raise ValueError("step program modes: 'sparse', 'dense_own'")
-        if mode == "sparse" and not self.sparse:
-            raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
-        if self.sampling is not None:
-            raise NotImplementedError("the step program decodes greedily (sampling is not a phase yet): use engine='graph'")
-        a = self.args
-        d = _lib.StepDesc()
-        d.dim, d.n_head, d.n_kv_head, d.head_dim = a.dim, self.n_head_l, self.n_kv_l, self.hd
-        d.inter, d.vocab, d.max_seq, d.eps = self.inter_l, a.vocab_size, self.max_seq, a.norm_eps
-        d.tok_emb, d.token, d.ssq_init = self.tok_emb.data_ptr(), self.token.data_ptr(), None
-        d.lm_head, d.final_norm, d.ld_head = self.lm_head.data_ptr(), self.final_norm.data_ptr(), a.dim
-        d.freqs_cis, d.pos, d.out_tokens = self.freqs.data_ptr(), self.pos.data_ptr(), self.out_tokens.data_ptr()
-        d.argmax_packed, d.out_cap = self.argmax.data_ptr(), self.out_tokens.numel()
-        d.x, d.qkv, d.att, d.h, d.logits = (t.data_ptr() for t in (self.x, self.qkv, self.att, self.h, self.logits))
-        for k, v in tuning.items():
-            _prog.set_knob(d, k, v)  # debug_times: a device address
-        layers = []
-        for li, W in enumerate(self.layers):
-            t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else None
-            layers.append(_prog.layer_desc(
-                wqkv=W["wqkv"].data_ptr(), wo=W["wo"].data_ptr(), w1=W["w1"].data_ptr(), w3=W["w3"].data_ptr(),
-                w2=W["w2"].data_ptr(), attn_norm=W["attn_norm"].data_ptr(), ffn_norm=W["ffn_norm"].data_ptr(),
-                k_cache=self.k_cache[li].data_ptr(), v_cache=self.v_cache[li].data_ptr(), ld_qkv=W["wqkv"].stride(1),
-                ld_o=W["wo"].stride(1), ld_1=W["w1"].stride(1), ld_3=W["w3"].stride(1), ld_2=W["w2"].stride(1), thr=t))
-        d.scratch = 256  # placeholder: sizes() only validates that it is non-null
-        prog = _prog.StepProgram(d, layers)
-        self.program_scratch = torch.zeros(prog.scratch_bytes, dtype=torch.uint8, device=self.dev)
-        d.scratch = self.program_scratch.data_ptr()
-        prog.plan().upload(self.dev)
-        torch.cuda.synchronize()
-        self.program, self.program_mode, self.program_tuning = prog, mode, dict(tuning)
-        return prog
-
-    def _enqueue_program(self):
-        self.program.run(torch.cuda.current_stream().cuda_stream)
-        self.kernels_per_step = 1
-
     # ------------------------------------------------------------------ public API
-    def capture(self, mode: str = "sparse", pdl: bool = True, engine: str = "graph", **tuning):
-        """Capture one decode step into a CUDA graph (generate.py:420's reduce-overhead equivalent).
-        engine="graph": one launch per projection group (PDL chain); engine="program": the whole step as one
-        persistent data-flow kernel (`build_program`)."""
+    def _check_room(self, n_new: int):
+        """The device position advances without the host looking; the host mirrors it so that a step can never run past
+        the KV cache / RoPE table / output buffer (the reference sizes its caches from the request, generate.py:171-176)."""
+        if self.steps_enqueued + n_new > self.max_seq:
+            raise ValueError(f"decode position would reach {self.steps_enqueued + n_new} > max_seq {self.max_seq}: "
+                             "construct the decoder with a larger max_seq or reset()")
+        if self.steps_enqueued + n_new > self.out_tokens.numel():
+            raise ValueError(f"{self.steps_enqueued + n_new} tokens do not fit out_cap {self.out_tokens.numel()}")
+
+    def capture(self, mode: str = "sparse", pdl: bool = True):
+        """Capture one decode step into a CUDA graph (generate.py:420's reduce-overhead equivalent): one launch per
+        projection group in a programmatic-dependent-launch chain.  The PDL switch is launch context of the calling
+        thread (teal_set_pdl is thread-local), so decoders captured from different threads do not interfere."""
         if mode == "sparse" and not self.sparse:
             raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
-        if engine == "program":
-            if self.program is None or self.program_mode != mode or self.program_tuning != tuning:
-                self.build_program(mode, **tuning)
+        self.lib.teal_set_pdl(1 if (pdl and mode != "dense_cublas") else 0)
+        try:
             with torch.cuda.stream(self.stream):
+                ops.workspace(self.dev, self.stream.cuda_stream)
                 saved = (self.token.clone(), self.pos.clone())
-                self._enqueue_program()  # warm-up outside capture (function attributes, occupancy query)
+                self._enqueue_step(mode)  # warm-up outside capture (allocations, lazy init)
                 self.stream.synchronize()
                 self.token.copy_(saved[0]); self.pos.copy_(saved[1]); self.argmax.zero_()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.stream):
-                    self._enqueue_program()
-            torch.cuda.synchronize()
-            self.graph, self.graph_mode, self.graph_engine = g, mode, engine
-            return g
-        if engine != "graph":
-            raise ValueError("engine: 'graph' or 'program'")
-        self.lib.teal_set_pdl(1 if (pdl and mode != "dense_cublas") else 0)
-        with torch.cuda.stream(self.stream):
-            ops.workspace(self.dev, self.stream.cuda_stream)
-            saved = (self.token.clone(), self.pos.clone())
-            self._enqueue_step(mode)  # warm-up outside capture (allocations, lazy init)
-            self.stream.synchronize()
-            self.token.copy_(saved[0]); self.pos.copy_(saved[1]); self.argmax.zero_()
-            g = torch.cuda.CUDAGraph()
-            # TP: the NCCL watchdog thread polls events while we capture -> capture errors must be thread-local
-            cap_mode = "thread_local" if self.world > 1 else "global"
-            with torch.cuda.graph(g, stream=self.stream, capture_error_mode=cap_mode):
-                self._enqueue_step(mode)
-        self.lib.teal_set_pdl(0)
+                # TP: the NCCL watchdog thread polls events while we capture -> capture errors must be thread-local
+                cap_mode = "thread_local" if self.world > 1 else "global"
+                with torch.cuda.graph(g, stream=self.stream, capture_error_mode=cap_mode):
+                    self._enqueue_step(mode)
+        finally:
+            self.lib.teal_set_pdl(0)
         torch.cuda.synchronize()
-        self.graph, self.graph_mode, self.graph_engine = g, mode, "graph"
+        self.graph, self.graph_mode = g, mode
         return g
 
     def decode_one_token(self):
         """Replay the captured step (device-side token/position; no host sync)."""
+        self._check_room(1)
         self.graph.replay()
+        self.steps_enqueued += 1
 
-    def generate(self, first_token: int, n_new: int, mode: str = "sparse", engine: str = "graph") -> torch.Tensor:
-        if self.graph is None or self.graph_mode != mode or self.graph_engine != engine:
-            self.capture(mode, engine=engine)
+    def generate(self, first_token: int, n_new: int, mode: str = "sparse") -> torch.Tensor:
+        if self.graph is None or self.graph_mode != mode:
+            self.capture(mode)
         self.reset(first_token)
+        self._check_room(n_new)
         for _ in range(n_new):
             self.graph.replay()
+        self.steps_enqueued += n_new
         torch.cuda.synchronize()
         return self.out_tokens[:n_new].clone()
 

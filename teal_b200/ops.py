@@ -271,18 +271,13 @@ class SparseQKVGEMV(BaseKernel):
         return torch.matmul(x, weight.T)
 
 
-def set_config(config_id: int) -> None:
-    """Benchmark knob: force a tile configuration (0 = default heuristic)."""
+def set_config(config_id: int = 0, variant: int = -1, lanes_per_warp: int = 0) -> None:
+    """Benchmark / parity-test knob of the calling thread (``teal_set_config``): force the kernel variant (0..4) and / or
+    the input lanes one warp owns; ``set_config()`` restores the by-size default."""
+    if variant >= 0:
+        config_id = (variant + 1) + 16 * (lanes_per_warp // 32)
     _lib.check(_lib.load().teal_set_config(int(config_id)), "teal_set_config")
 
 
-TUNING_KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5, "v1_opts": 6, "wide_kelems": 7}  # TEAL_TUNE_* of include/teal_b200.h
-TUNING_DEFAULTS = {"generation": 1, "spec_rows": 0, "spec_mode": 1, "fhfma": 1, "rows_wide": 0, "rows_narrow": 0, "v1_opts": 0, "wide_kelems": 0}
+NUM_VARIANTS = 5  # kernel variants of csrc/gemv.cu (tile width x warps per CTA)
 
-
-def set_tuning(**knobs: int) -> None:
-    """Opt-in experimental knobs of the default dispatch (``teal_set_tuning``), e.g. ``set_tuning(generation=2,
-    spec_rows=4)``; ``set_tuning()`` restores the defaults (generation 1: the hardware-validated kernel)."""
-    lib = _lib.load()
-    for name, value in (knobs or TUNING_DEFAULTS).items():
-        _lib.check(lib.teal_set_tuning(TUNING_KNOBS[name], int(value)), f"teal_set_tuning({name})")

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "teal_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libteal_emu.so")
-KERNEL_SOURCES = ["api.cu", "dispatch.cu", "rowchunk_gemv.cu", "decode_kernels.cu", "step_program.cu"]
+KERNEL_SOURCES = ["api.cu", "gemv.cu", "decode_kernels.cu"]
 CUDA_INC = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
 FLAGS = ["-std=c++17", "-O1", "-g", "-fPIC", "-DTEAL_EMU", "-pthread", "-I", CUDA_INC, "-I", HERE,
          "-include", os.path.join(HERE, "cuda_emu.h"), "-Wno-attributes", "-Wno-unknown-pragmas"]

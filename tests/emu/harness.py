@@ -73,18 +73,14 @@ def set_config(cfg):
     check(lib().teal_set_config(int(cfg)), "teal_set_config")
 
 
-KNOBS = {"generation": 0, "spec_rows": 1, "spec_mode": 2, "fhfma": 3, "rows_wide": 4, "rows_narrow": 5, "v1_opts": 6, "wide_kelems": 7}
-
-
-def set_tuning(generation=1, spec_rows=0, spec_mode=1, fhfma=1, rows_wide=0, rows_narrow=0, v1_opts=0, wide_kelems=0):
-    for k, v in (("generation", generation), ("spec_rows", spec_rows), ("spec_mode", spec_mode), ("fhfma", fhfma),
-                 ("rows_wide", rows_wide), ("rows_narrow", rows_narrow), ("v1_opts", v1_opts), ("wide_kelems", wide_kelems)):
-        check(lib().teal_set_tuning(KNOBS[k], int(v)), f"teal_set_tuning({k})")
+def set_variant(variant=-1, lanes_per_warp=0):
+    """teal_set_config: force kernel variant / input lanes per warp (-1 / 0 = the by-size default)."""
+    set_config(0 if variant < 0 else (variant + 1) + 16 * (lanes_per_warp // 32))
 
 
 class EmuDecoder:
-    """The buffers and call sequence of teal_b200.model.SparseDecoder (`_enqueue_step`, `build_program`) on numpy
-    arrays against the emulation library: one decode step = the same C-ABI calls in the same order."""
+    """The buffers and call sequence of teal_b200.model.SparseDecoder (`_enqueue_step`) on numpy arrays against the
+    emulation library: one decode step = the same C-ABI calls in the same order."""
     PROJS = ("q", "k", "v", "o", "gate", "up", "down")
 
     def __init__(self, cfg: dict, sd: dict, thresholds, max_seq: int = 64):
@@ -119,12 +115,7 @@ class EmuDecoder:
         self.h, self.logits = aligned((self.inter,), f16, 0), aligned((self.vocab,), f16, 0)
         self.ssq = aligned((64,), np.float32, 0)
         self.ws = Workspace(1 << 17)   # the product's size (teal_b200/ops.py)
-        self.program = None
         self.sampling = None   # dict(temperature, top_k, seed) as in SparseDecoder.set_sampling
-        self.chain_mlp = False  # SparseDecoder.chain_mlp: the flag-chained gate/up -> down pair
-        self.chain_attn = False  # SparseDecoder.chain_attn: the flag-chained QKV -> attention -> o-proj block
-        self.concurrent_chain = False  # launch the kernels of a chained block from concurrent host threads, consumers first
-        self.chain_norms = False  # SparseDecoder.chain_norms: hand-off cells instead of grid-wide waits at the two RMSNorm points
 
     def reset(self, token):
         self.token[0], self.pos[0], self.argmax[0] = token, 0, 0
@@ -140,44 +131,12 @@ class EmuDecoder:
         check(L.teal_embed_f16(ptr(self.tok_emb), ptr(self.token), ptr(self.x), ssq, self.dim, None), "embed")
         for li, W in enumerate(self.layers):
             t = self.thresholds[li] if (sparse and self.thresholds[li] is not None) else {p: -1.0 for p in self.PROJS}
-            norms = self.chain_attn and self.chain_mlp and self.chain_norms
-            rel_o = rel_d = 0
-            if norms:
-                rel_o = L.teal_chain_consumer_ctas(1, self.dim, self.inter, 0, 0, 0.0, 0.0, 0.0)
-                if li + 1 < len(self.layers):
-                    tn = self.thresholds[li + 1] if (sparse and self.thresholds[li + 1] is not None) else {p: -1.0 for p in self.PROJS}
-                    rel_d = L.teal_chain_consumer_ctas(0, self.dim, self.n_head, self.n_kv, self.hd, tn["q"], tn["k"], tn["v"])
-            attn_calls = [
-                lambda: check(L.teal_norm_sparse_qkv_gemv_chain_f16(
-                    ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), self.dim, self.nqkv, self.nqkv, self.kv,
-                    t["q"], t["k"], t["v"], self.n_head, self.n_kv, self.hd, 1 if (norms and li > 0) else 0, wsp, wsn, None), "qkv_chain"),
-                lambda: check(L.teal_attn_decode_chain_f16(
-                    ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att), self.n_head, self.n_kv,
-                    self.hd, self.max_seq, self.dim, t["q"], t["k"], t["v"], wsp, wsn, None), "attn_chain"),
-                lambda: check(L.teal_sparse_o_proj_chain_f16(
-                    ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim, t["o"], self.n_head, self.n_kv,
-                    self.hd, rel_o, wsp, wsn, None), "o_chain")]
-            mlp_calls = [
-                lambda: check(L.teal_norm_sparse_gate_up_chain_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]),
-                                                                   ptr(self.h), self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"],
-                                                                   1 if norms else 0, wsp, wsn, None), "gate_up_chain"),
-                lambda: check(L.teal_sparse_gemv_residual_chain_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter,
-                                                                    self.dim, self.dim, t["down"], rel_d, wsp, wsn, None), "down_chain")]
-            if norms:  # the five launches of the layer form one chain (the o-proj -> gate/up hand-off is a cell, not a grid-wide wait)
-                self._run_chain(attn_calls + mlp_calls)
-                continue
-            if self.chain_attn:
-                self._run_chain(attn_calls)
-            else:
-                check(L.teal_norm_sparse_qkv_gemv_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), None,
-                                                      self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], wsp, wsn, None), "norm_qkv")
-                check(L.teal_attn_decode_f16(ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att),
-                                             self.n_head, self.n_kv, self.hd, self.max_seq, None), "attn")
-                check(L.teal_sparse_gemv_residual_f16(ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim,
-                                                      t["o"], wsp, wsn, None), "o_proj")
-            if self.chain_mlp:
-                self._run_chain(mlp_calls)
-                continue
+            check(L.teal_norm_sparse_qkv_gemv_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), None,
+                                                  self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], wsp, wsn, None), "norm_qkv")
+            check(L.teal_attn_decode_f16(ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att),
+                                         self.n_head, self.n_kv, self.hd, self.max_seq, None), "attn")
+            check(L.teal_sparse_gemv_residual_f16(ptr(self.att), ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim, self.dim,
+                                                  t["o"], wsp, wsn, None), "o_proj")
             check(L.teal_norm_sparse_gate_up_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), ptr(self.h), None,
                                                  self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], wsp, wsn, None), "gate_up")
             check(L.teal_sparse_gemv_residual_f16(ptr(self.h), ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter, self.dim, self.dim,
@@ -190,63 +149,3 @@ class EmuDecoder:
                                          ptr(self.argmax), None, None), "sample")
         check(L.teal_advance(ptr(self.argmax), ptr(self.token), ptr(self.pos), ptr(self.out_tokens), self.out_tokens.size, None), "advance")
         ws.assert_clean()
-
-    def _run_chain(self, calls):
-        """The launches of one flag-chained block, in stream order -- or, with `concurrent_chain`, from concurrent host threads
-        with the LAST launch started first (every consumer grid is alive and polling before its producer runs)."""
-        if not self.concurrent_chain:
-            for c in calls:
-                c()
-            return
-        import threading
-        import time
-        errors = []
-
-        def guarded(c):
-            try:
-                c()
-            except Exception as e:  # noqa: BLE001
-                errors.append(e)
-
-        threads = [threading.Thread(target=guarded, args=(c,)) for c in reversed(calls)]
-        for th in threads:
-            th.start()
-            time.sleep(0.02)
-        for th in threads:
-            th.join(timeout=300)
-        if errors or any(th.is_alive() for th in threads):
-            raise RuntimeError(f"chained block failed: {errors}")
-
-    def build_program(self, sparse=True, **tuning):
-        """SparseDecoder.build_program against the emulation library (host blob == "device" blob)."""
-        from teal_b200 import _lib as binding
-        from teal_b200 import program as prog
-        d = binding.StepDesc()
-        d.dim, d.n_head, d.n_kv_head, d.head_dim = self.dim, self.n_head, self.n_kv, self.hd
-        d.inter, d.vocab, d.max_seq, d.eps = self.inter, self.vocab, self.max_seq, self.eps
-        a = lambda arr: arr.ctypes.data
-        d.tok_emb, d.token, d.ssq_init = a(self.tok_emb), a(self.token), None
-        d.lm_head, d.final_norm, d.ld_head = a(self.lm_head), a(self.final_norm), self.dim
-        d.freqs_cis, d.pos, d.out_tokens = a(self.freqs), a(self.pos), a(self.out_tokens)
-        d.argmax_packed, d.out_cap = a(self.argmax), self.out_tokens.size
-        d.x, d.qkv, d.att, d.h, d.logits = a(self.x), a(self.qkv), a(self.att), a(self.h), a(self.logits)
-        for k, v in tuning.items():
-            prog.set_knob(d, k, v)
-        layers = []
-        for li, W in enumerate(self.layers):
-            t = self.thresholds[li] if (sparse and self.thresholds[li] is not None) else None
-            layers.append(prog.layer_desc(wqkv=a(W["wqkv"]), wo=a(W["wo"]), w1=a(W["w1"]), w3=a(W["w3"]), w2=a(W["w2"]),
-                                          attn_norm=a(W["attn_norm"]), ffn_norm=a(W["ffn_norm"]), k_cache=a(W["k_cache"]),
-                                          v_cache=a(W["v_cache"]), ld_qkv=self.nqkv, ld_o=self.dim, ld_1=self.inter, ld_3=self.inter,
-                                          ld_2=self.dim, thr=t))
-        d.scratch = 256
-        p = prog.StepProgram(d, layers, lib=self.L)
-        self.program_scratch = aligned((p.scratch_bytes,), np.uint8, 0)
-        d.scratch = a(self.program_scratch)
-        p.plan()
-        self.program = p
-        return p
-
-    def step_program(self):
-        p = self.program
-        check(self.L.teal_step_program_run(p.host, ctypes.cast(p.host, ctypes.c_void_p), None), "step_program_run")

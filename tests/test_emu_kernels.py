@@ -1,8 +1,7 @@
 """The CUDA kernels' LOGIC on the CPU: the production .cu sources compiled as C++ against tests/emu/cuda_emu.h (fibers
 for threads, real atomics, warp collectives through per-warp slots) and driven through the same C ABI, checked against
-the oracle.  This is how kernels that have not run on a B200 yet (generation-2 row-chunk kernel, experimental
-step-program paths) are exercised in the CPU suite; the hardware-validated kernels run through the same emulation
-first, which validates the emulator itself.  It proves indexing / masks / pipelines / protocols, not the memory model
+the oracle.  The CPU suite exercises the kernel logic (indexing, masks, lists, the arrival / finaliser protocol, the TP
+exchange with concurrent emulated ranks) through the same entry points the GPU tests use.  It proves indexing / masks / pipelines / protocols, not the memory model
 and not speed.  The -m gpu tests remain the parity tests proper."""
 import os
 import sys
@@ -16,20 +15,18 @@ from oracle import teal_oracle as O
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 import harness as H  # noqa: E402
 
-V1_CFGS = [30, 31, 32, 33, 35, 38, 40]      # hardware-validated row-chunk variants (emulator self-check)
-GEN2_CFGS = [42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53]   # 50+: warp-wise completion
+VARIANTS = [0, 1, 2, 3, 4]          # kernel variants of csrc/gemv.cu (tile width x warps per CTA)
+LANES = [0, 32, 96, 256, 512]       # input lanes per warp (0 = chosen by launch size)
 
 
 @pytest.fixture(autouse=True)
 def _defaults():
     H.lib()
     H.set_config(0)
-    H.set_tuning()
     H.lib().teal_emu_set_sm_count(4)
     H.lib().teal_emu_set_concurrent(0)
     yield
     H.set_config(0)
-    H.set_tuning()
 
 
 def _mk(Z, N, seed, scale=1.0):
@@ -66,33 +63,24 @@ def _check_gemv(Z, N, thr, seed=0):
 SHAPES = [(200, 264), (512, 1024), (1000, 776), (96, 8), (2048, 520)]
 
 
-@pytest.mark.parametrize("cfg", V1_CFGS)
-def test_emulator_reproduces_the_validated_kernels(cfg):
-    H.set_config(cfg)
-    for Z, N in SHAPES[:3]:
-        _check_gemv(Z, N, 0.6745, seed=cfg)
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("lanes", LANES)
+def test_every_variant_and_k_chunk_matches_oracle(variant, lanes):
+    """All kernel variants x forced lanes per warp (several 32-lane groups per warp, more than one request pass, ragged
+    last chunk, partial last column tile) against the oracle."""
+    H.set_variant(variant, lanes)
+    for i, (Z, N) in enumerate(SHAPES):
+        _check_gemv(Z, N, 0.6745, seed=i)
 
 
-@pytest.mark.parametrize("cfg", GEN2_CFGS)
-@pytest.mark.parametrize("spec", [(0, 1), (4, 1), (8, 2), (32, 1)])
-def test_gen2_gemv_matches_oracle(cfg, spec):
-    H.set_config(cfg)
-    H.set_tuning(generation=2, spec_rows=spec[0], spec_mode=spec[1])
-    for Z, N in SHAPES:
-        _check_gemv(Z, N, 0.6745, seed=cfg + spec[0])
-
-
-@pytest.mark.parametrize("cfg", [43, 45, 46, 50, 53])
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("thr", [0.0, 100.0, 0.05, 2.0])
-def test_gen2_sparsity_extremes(cfg, thr):
-    H.set_config(cfg)
-    H.set_tuning(generation=2, spec_rows=4)
+def test_sparsity_extremes(variant, thr):
+    H.set_variant(variant, 64)
     _check_gemv(1000, 776, thr, seed=3)
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3])
-def test_default_dispatch_and_survivors_bit_exact(gen):
-    H.set_tuning(generation=gen)
+def test_default_dispatch_and_survivors_bit_exact():
     for Z, thr in [(8, 0.5), (200, 0.3), (4096, 0.6745), (4096, 0.0), (4096, 100.0), (11008, 0.0203768)]:
         g = torch.Generator().manual_seed(Z)
         x = torch.randn(1, 1, Z, generator=g).half()
@@ -103,7 +91,7 @@ def test_default_dispatch_and_survivors_bit_exact(gen):
         cnt = H.aligned((1,), np.int32, 0)
         H.check(H.lib().teal_survivors_f16(H.ptr(xa), Z, thr, H.ptr(idx), H.ptr(cnt), None), "survivors")
         want = O.survivor_indices(x, thr)
-        assert int(cnt[0]) == len(want) and np.array_equal(idx[: len(want)], want), (gen, Z, thr)
+        assert int(cnt[0]) == len(want) and np.array_equal(idx[: len(want)], want), (Z, thr)
     _check_gemv(512, 1024, 0.6745)
 
 
@@ -115,9 +103,7 @@ def _tie_vector():
     return x, t
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3])
-def test_tie_rule_and_nan(gen):
-    H.set_tuning(generation=gen)
+def test_tie_rule_and_nan():
     x, t = _tie_vector()
     Z = x.numel()
     xa = H.aligned((Z,), np.float16, x.reshape(-1).numpy())
@@ -128,10 +114,8 @@ def test_tie_rule_and_nan(gen):
     assert got == [2, 4, 6, 7]          # the two ties and the zeros are dropped, NaN is gathered (poisons y like mask*x)
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3])
 @pytest.mark.parametrize("uniform", [True, False])
-def test_qkv_region_thresholds(gen, uniform):
-    H.set_tuning(generation=gen, spec_rows=4 if gen >= 2 else 0)
+def test_qkv_region_thresholds(uniform):
     Z, N, kv = 256, 640, 128                       # N_q = 384: the k/v regions do not start on a 256-column tile
     x, W = _mk(Z, N, 5)
     tq, tk, tv = (0.5, 0.5, 0.5) if uniform else (0.3, 0.8, 1.2)
@@ -146,11 +130,11 @@ def test_qkv_region_thresholds(gen, uniform):
     assert ((torch.from_numpy(y.copy()).float() - want).abs() <= _tol(want)).all()
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3])
-def test_fused_layer_half_steps(gen):
+@pytest.mark.parametrize("variant,lanes", [(-1, 0), (2, 32), (1, 96)])
+def test_fused_layer_half_steps(variant, lanes):
     """RMSNorm+gate/up+SiLU*mul -> down+residual (+ sum of squares) -> RMSNorm+QKV from the partials: the decode step's
     GEMV chain (gpt-fast/model.py:159-161,258-259,286-291) on one small layer."""
-    H.set_tuning(generation=gen, spec_rows=8 if gen >= 2 else 0, spec_mode=2)
+    H.set_variant(variant, lanes)
     L = H.lib()
     dim, inter, eps = 256, 776, 1e-5
     g = torch.Generator().manual_seed(11)
@@ -255,34 +239,13 @@ def _run_and_compare(dec, sparse, step):
         assert int(dec.token[0]) == int(torch.argmax(got))         # fused arg-max == torch.argmax of the fp16 logits
 
 
-@pytest.mark.parametrize("gen,sparse", [(1, False), (1, True), (2, False), (2, True), (3, False), (3, True), (20, True)])
-def test_decode_step_launch_per_projection(gen, sparse):
-    if gen == 20:   # generation 2 with conversions + FFMA2 instead of FHFMA
-        H.set_tuning(generation=2, fhfma=0)
-    else:
-        H.set_tuning(generation=gen, spec_rows=4 if gen >= 2 else 0)
+@pytest.mark.parametrize("variant,lanes,sparse", [(-1, 0, False), (-1, 0, True), (2, 32, True), (1, 96, True), (4, 64, True)])
+def test_decode_step_launch_per_projection(variant, lanes, sparse):
+    """SparseDecoder._enqueue_step's call sequence (embed | 5 launches per layer | lm_head + arg-max | advance) on the
+    emulation against OracleDecoder (pinned to the reference's gpt-fast Transformer by tests/golden/gptfast_dense.npz)."""
+    H.set_variant(variant, lanes)
     dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
     _run_and_compare(dec, sparse, lambda: dec.step(sparse))
-
-
-PROGRAM_KNOBS = [
-    dict(),                                                        # hardware-validated default (emulator self-check)
-    dict(rows_small=32, rows_large=64), dict(group_qkv=1, group_gate_up=2), dict(wide_melems=1), dict(head_rows=7),
-    # written after the GPU budget was spent -- never run on hardware:
-    dict(warps=2), dict(warps=2, rows_small=32), dict(opts=2), dict(opts=3, stagger_ns=100), dict(warps=2, opts=3, stagger_ns=50),
-    dict(rows_qkv=32, rows_o=128, rows_gate_up=64, rows_down=64), dict(opts=4), dict(opts=5), dict(warps=2, opts=7, stagger_ns=50),
-    dict(tiles_per_item=2), dict(tiles_per_item=4, warps=2, rows_small=64, rows_large=64),
-    dict(tiles_per_item=3, group_qkv=5, group_gate_up=6), dict(tiles_per_item=2, wide_melems=1, opts=4),
-]
-
-
-@pytest.mark.parametrize("knobs", PROGRAM_KNOBS, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()) or "default")
-def test_step_program_one_kernel_per_token(knobs):
-    H.lib().teal_emu_set_sm_count(2)
-    H.lib().teal_emu_set_concurrent(1)          # persistent kernel: all CTAs alive together, they wait on each other
-    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
-    dec.build_program(True, **knobs)
-    _run_and_compare(dec, True, dec.step_program)
 
 
 def test_decode_step_with_device_sampling():
@@ -302,7 +265,7 @@ def test_decode_step_with_device_sampling():
 
 
 def test_timeline_twins_record_every_cta_and_do_not_change_results():
-    """teal_set_debug_timeline: the TIMED twins of the two default kernels write monotone stamps for every CTA into one
+    """teal_set_debug_timeline: the TIMED twin of the kernel write monotone stamps for every CTA into one
     slot per launch; results are those of the production instantiation."""
     L = H.lib()
     slots, slot_ints = 3, 4096 * 16
@@ -312,7 +275,7 @@ def test_timeline_twins_record_every_cta_and_do_not_change_results():
     y_plain = _gemv(x, W, 0.6745, ws)
     H.check(L.teal_set_debug_timeline(H.ptr(buf), slots), "timeline")
     try:
-        y_timed = _gemv(x, W, 0.6745, ws)          # small launch -> variant 2 twin, slot 0
+        y_timed = _gemv(x, W, 0.6745, ws)          # slot 0
         _check_gemv(1000, 776, 0.5, seed=4)         # slot 1
     finally:
         H.check(L.teal_set_debug_timeline(None, 0), "timeline off")
@@ -321,27 +284,17 @@ def test_timeline_twins_record_every_cta_and_do_not_change_results():
     for s, (Z, N) in enumerate([(512, 1024), (1000, 776)]):
         used = t[s][t[s][:, 0] > 0]
         ctiles = (N + 255) // 256
-        assert len(used) % ctiles == 0 and len(used) >= ctiles * (Z // 64)     # every CTA of the grid reported
+        assert len(used) % ctiles == 0 and len(used) >= ctiles                  # every CTA of the grid reported
         for a, b in ((0, 1), (1, 2), (2, 4), (4, 5), (5, 6)):
             assert (used[:, a] <= used[:, b]).all(), (s, a, b)
         assert int(used[:, 10].sum()) == ctiles                                 # exactly one last arrival per column tile
         assert ((used[:, 7] > 0) == (used[:, 10] == 1)).all()                    # only the finaliser stamps [7]
     assert not t[2].any()                                                        # third slot untouched
-    # the analysis of tools/rowchunk_timeline.py digests these stamps
+    # the analysis of tools/gemv_timeline.py digests these stamps
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
-    import rowchunk_timeline as RT
+    import gemv_timeline as RT
     r = RT.analyse(t[1])
     assert r["ctas"] == len(t[1][t[1][:, 0] > 0]) and r["span_us"] >= 0 and r["split_us_p50"]["finalise(last only)"] is not None
-
-
-@pytest.mark.parametrize("gen", [1, 2, 3])
-@pytest.mark.parametrize("rows", [32, 96, 256, 512])
-def test_forced_k_chunk_sizes(gen, rows):
-    """TEAL_TUNE_ROWS_*: any multiple of 32 input lanes per CTA (several lane groups per warp, ragged last chunk)."""
-    H.set_tuning(generation=gen, rows_wide=rows, rows_narrow=rows)
-    _check_gemv(1000, 776, 0.6745, seed=rows)          # narrow variant
-    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
-    _run_and_compare(dec, True, lambda: dec.step(True))
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -395,7 +348,7 @@ def test_tp_peer_memory_allreduce_protocol(world):
         assert abs(float(ssq[r].sum()) - float((want.float() ** 2).sum())) <= 1e-3 * float((want.float() ** 2).sum())
 
 
-@pytest.mark.parametrize("world,Z,N,cfg", [(2, 256, 512, 0), (4, 512, 776, 0), (2, 2048, 1024, 0), (2, 512, 1032, 31), (4, 1024, 512, 31)])
+@pytest.mark.parametrize("world,Z,N,cfg", [(2, 256, 512, 0), (4, 512, 776, 0), (2, 2048, 1024, 0), (2, 512, 1032, 3 + 16), (4, 1024, 512, 2 + 32)])
 def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
     """teal_sparse_gemv_tp_exchange_f16 with `world` emulated ranks running concurrently: each rank gathers its Z/world
     lanes, the tile finalisers exchange partials over 'peer' memory -- x ends bit-identical on every rank and equals
@@ -404,7 +357,7 @@ def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
     import threading
     L = H.lib()
     L.teal_emu_set_concurrent(1)          # every CTA alive: finalisers wait for peers while the rest of the grid runs
-    H.set_config(cfg)                     # 0: the narrow default variant's TP twin, 31: the wide one's
+    H.set_config(cfg)                     # 0: the default variant's TP twin; the 512-column and the 4-warp twins with forced K chunks
     steps, Zs = 4, Z // world
     g = torch.Generator().manual_seed(world * 1000 + Z)
     W = (torch.randn(N, Z, generator=g) * 0.05).half()
@@ -453,225 +406,9 @@ def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
     assert abs(float(ssq[0].sum()) - float((got ** 2).sum())) <= 1e-3 * float((got ** 2).sum())
 
 
-@pytest.mark.parametrize("opts", [1, 2, 3, 4, 5, 6, 7])
-def test_generation1_one_change_at_a_time(opts):
-    """TEAL_TUNE_V1_OPTS: early x / norm-weight requests, FHFMA, 32-bit row offsets on the validated kernel structure."""
-    H.set_tuning(v1_opts=opts, rows_narrow=96 if opts & 1 else 0)     # (96: a warp owns a ragged second lane group)
-    for Z, N in SHAPES[:4]:
-        _check_gemv(Z, N, 0.6745, seed=opts)
-    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
-    _run_and_compare(dec, True, lambda: dec.step(True))
-
-
-def _chain_case(dim, inter, seed):
-    g = torch.Generator().manual_seed(seed)
-    resid = torch.randn(1, 1, dim, generator=g).half()
-    nw = (1 + 0.1 * torch.randn(dim, generator=g)).half()
-    W1, W3 = [(torch.randn(inter, dim, generator=g) * 0.05).half() for _ in range(2)]
-    W2 = (torch.randn(dim, inter, generator=g) * 0.05).half()
-    return resid, nw, W1, W3, W2
-
-
-@pytest.mark.parametrize("dim,inter,wide_kelems,concurrent", [(256, 704, 0, False), (256, 704, 0, True), (256, 1000, 0, True),
-                                                               (512, 1536, 100, True), (512, 1400, 100, False), (256, 704, 300, True)])
-def test_flag_chained_mlp_pair(dim, inter, wide_kelems, concurrent):
-    """teal_norm_sparse_gate_up_chain_f16 -> teal_sparse_gemv_residual_chain_f16: the down projection waits for h tile by
-    tile instead of for the whole gate/up grid.  `concurrent`: the two launches really overlap (two host threads; the
-    consumer is started FIRST and spins until the producer's finalisers release its tiles).  wide_kelems lowers the
-    wide-variant threshold so that the 512-column twins and mixed tile widths are exercised at emulation sizes.
-    Result == the unchained pair's (oracle tolerance), ready cells back to zero, workspace clean."""
-    import threading
-    L = H.lib()
-    L.teal_emu_set_concurrent(1)
-    H.set_tuning(wide_kelems=wide_kelems)
-    resid, nw, W1, W3, W2 = _chain_case(dim, inter, dim + inter)
-    tg, tu, td, eps = 0.4, 0.6, 0.02, 1e-5
-    ws = H.Workspace(1 << 17)                             # the product's size (teal_b200/ops.py): room for the second accumulator region
-    xa = H.aligned((dim,), np.float16, resid.reshape(-1).numpy())
-    nwa = H.aligned((dim,), np.float16, nw.numpy())
-    W1c, W3c, W2c = H.column_major(W1.numpy()), H.column_major(W3.numpy()), H.column_major(W2.numpy())
-    ssq = H.aligned((64,), np.float32, 0)
-    ssq[0] = float((resid.float() ** 2).sum())
-    for rep in range(2):                                  # twice on the same workspace: the cells reset themselves
-        h = H.aligned((inter,), np.float16, 0)
-        y = H.aligned((dim,), np.float16, 0)
-        ssq_out = H.aligned((64,), np.float32, 5.0)
-        errors = []
-
-        def produce():
-            try:
-                H.check(L.teal_norm_sparse_gate_up_chain_f16(H.ptr(xa), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(W1c), H.ptr(W3c), H.ptr(h), dim, inter,
-                                                             inter, inter, tg, tu, 0, H.ptr(ws.buf), ws.nbytes, None), "gate_up_chain")
-            except Exception as e:  # noqa: BLE001
-                errors.append(e)
-
-        def consume():
-            try:
-                H.check(L.teal_sparse_gemv_residual_chain_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim, dim, td, 0,
-                                                              H.ptr(ws.buf), ws.nbytes, None), "down_chain")
-            except Exception as e:  # noqa: BLE001
-                errors.append(e)
-
-        if concurrent:
-            tc, tp = threading.Thread(target=consume), threading.Thread(target=produce)
-            tc.start()
-            import time
-            time.sleep(0.05)                              # the consumer grid is alive and polling before any h tile exists
-            tp.start()
-            tp.join(timeout=120)
-            tc.join(timeout=120)
-            assert not tc.is_alive() and not tp.is_alive()
-        else:
-            produce()
-            consume()
-        assert not errors, errors
-        ws.assert_clean()                                 # counters, both accumulator regions and the ready cells are zero again
-        xn = O.rms_norm(resid, nw, eps)
-        g32, u32 = O.sparse_linear_f32(xn, W1, tg), O.sparse_linear_f32(xn, W3, tu)
-        h_ref = (torch.nn.functional.silu(g32.half()) * u32.half()).reshape(-1)
-        h_t = torch.from_numpy(h.copy())
-        assert ((h_t.float() - h_ref.float()).abs() <= h_ref.float().abs() * 2.0 ** -8 + 2e-3).all()
-        d32 = O.sparse_linear_f32(h_t.reshape(1, 1, -1), W2, td).reshape(-1)
-        want = (resid.reshape(-1) + d32.half()).float()
-        y_t = torch.from_numpy(y.copy()).float()
-        assert ((y_t - want).abs() <= want.abs() * 2.0 ** -9 + 2e-3).all(), (rep, float((y_t - want).abs().max()))
-        assert abs(float(ssq_out.sum()) - float((y_t ** 2).sum())) <= 1e-4 * float((y_t ** 2).sum())
-
-
-@pytest.mark.parametrize("wide_kelems", [0, 150])
-def test_decode_step_with_the_flag_chained_mlp_pair(wide_kelems):
-    H.set_tuning(wide_kelems=wide_kelems)
-    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
-    dec.chain_mlp = True
-    _run_and_compare(dec, True, lambda: dec.step(True))
-
-
-@pytest.mark.parametrize("uniform_qkv,concurrent,wide_kelems", [(True, False, 0), (False, False, 0), (True, True, 0), (False, True, 0),
-                                                                (False, True, 60), (True, True, 200)])
-def test_decode_step_with_flag_chained_blocks(uniform_qkv, concurrent, wide_kelems):
-    """Both blocks of every layer flag-chained: QKV -> attention -> o-proj (tiles / heads) and gate/up -> down (h tiles).
-    `concurrent`: the launches of a block run in concurrent host threads, last launch first, so every consumer grid is
-    polling before its producer starts.  3-threshold QKV (tiles per q | k | v region) and uniform QKV (one region, slices
-    share tiles); wide_kelems moves the narrow / wide variant boundary so that 512-column tiles hold several heads."""
-    H.set_tuning(wide_kelems=wide_kelems)
-    H.lib().teal_emu_set_concurrent(1 if concurrent else 0)
-    thr = [dict(t, k=t["q"], v=t["q"]) for t in THR] if uniform_qkv else THR
-    dec = H.EmuDecoder(CFG, _state_dict(CFG), thr)
-    dec.chain_attn = dec.chain_mlp = True
-    dec.concurrent_chain = concurrent
-    if uniform_qkv:
-        orc = O.OracleDecoder(CFG, _state_dict(CFG), thr, max_seq=64)
-        dec.reset(TOKS[0])
-        for i, t in enumerate(TOKS):
-            dec.token[0] = t
-            dec.step(True)
-            with torch.no_grad():
-                want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
-            got = torch.from_numpy(dec.logits.astype(np.float32))
-            assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2, i
-    else:
-        _run_and_compare(dec, True, lambda: dec.step(True))
-
-
-@pytest.mark.parametrize("uniform_qkv,concurrent,wide_kelems", [(False, False, 0), (True, True, 0), (False, True, 0), (False, True, 100)])
-def test_decode_step_fully_flag_chained(uniform_qkv, concurrent, wide_kelems):
-    """chain_norms on top of the two chained blocks: the RMSNorm points are hand-off cells too (o-proj's last finaliser releases
-    the residual stream to the gate/up CTAs, down's to the next layer's QKV CTAs), so inside the layer stack no launch waits for
-    a whole grid.  `concurrent`: the five launches of a layer run in concurrent host threads, the last one started first."""
-    H.set_tuning(wide_kelems=wide_kelems)
-    H.lib().teal_emu_set_concurrent(1 if concurrent else 0)
-    thr = [dict(t, k=t["q"], v=t["q"]) for t in THR] if uniform_qkv else THR
-    dec = H.EmuDecoder(CFG, _state_dict(CFG), thr)
-    dec.chain_attn = dec.chain_mlp = dec.chain_norms = True
-    dec.concurrent_chain = concurrent
-    orc = O.OracleDecoder(CFG, _state_dict(CFG), thr, max_seq=64)
-    dec.reset(TOKS[0])
-    for i, t in enumerate(TOKS):
-        dec.token[0] = t
-        dec.step(True)                     # (asserts that the workspace -- counters, accumulators, every hand-off cell -- is zero again)
-        with torch.no_grad():
-            want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
-        got = torch.from_numpy(dec.logits.astype(np.float32))
-        assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2, i
-
-
-def test_timeline_of_a_chained_step():
-    """The chained twins stamp through the same hook (decided at run time): slot i = i-th row-chunk launch of the step."""
-    L = H.lib()
-    dec = H.EmuDecoder(CFG, _state_dict(CFG), THR)
-    dec.chain_attn = dec.chain_mlp = dec.chain_norms = True
-    n = 4 * CFG["n_layer"]
-    buf = H.aligned((n * 4096 * 16,), np.int64, 0)
-    H.check(L.teal_set_debug_timeline(H.ptr(buf), n), "timeline")
-    try:
-        dec.reset(3)
-        dec.token[0] = 3
-        dec.step(True)
-    finally:
-        H.check(L.teal_set_debug_timeline(None, 0), "timeline off")
-    t = buf.reshape(n, 4096, 16)
-    for s in range(n):
-        used = t[s][t[s][:, 0] > 0]
-        assert len(used) > 0 and (used[:, 0] <= used[:, 1]).all() and (used[:, 1] <= used[:, 4]).all(), s
-        assert int(used[:, 10].sum()) >= 1
-
-
 @pytest.mark.parametrize("Z,N", [(4096, 11008), (11008, 4096), (4096, 4096), (4096, 6144)])
 def test_baseline_shapes_at_full_size(Z, N):
     """BASELINE.json config 1 (Llama-2-7B gate_proj 4096 -> 11008, batch 1, 50 %) and its sibling projections at their real
-    sizes through the default dispatch on the emulation (the wide- and narrow-tile production kernels, multi-wave grids)."""
+    sizes through the default dispatch on the emulation (single-wave K chunks chosen by the launcher)."""
     H.lib().teal_emu_set_sm_count(8)
     _check_gemv(Z, N, 0.6745, seed=Z + N)
-
-
-def test_llama3_8b_mlp_block_at_full_size_chained_and_unchained():
-    """One Llama-3-8B MLP block (4096 -> 2 x 14336 -> 4096) at full size: fused RMSNorm + gate/up + SiLU*mul -> down +
-    residual, unchained and flag-chained with the two launches overlapping (consumer first); both against the oracle."""
-    import threading
-    import time
-    L = H.lib()
-    L.teal_emu_set_sm_count(8)
-    dim, inter, eps, tg, tu, td = 4096, 14336, 1e-5, 0.6745, 0.6745, 0.01
-    resid, nw, W1, W3, W2 = _chain_case(dim, inter, 7)
-    W1, W3, W2 = (W1 * 0.4).half(), (W3 * 0.4).half(), (W2 * 0.4).half()
-    ws = H.Workspace(1 << 17)
-    xa0 = resid.reshape(-1).numpy()
-    nwa = H.aligned((dim,), np.float16, nw.numpy())
-    W1c, W3c, W2c = H.column_major(W1.numpy()), H.column_major(W3.numpy()), H.column_major(W2.numpy())
-    ssq = H.aligned((64,), np.float32, 0)
-    ssq[0] = float((resid.float() ** 2).sum())
-    xn = O.rms_norm(resid, nw, eps)
-    h_ref = (torch.nn.functional.silu(O.sparse_linear_f32(xn, W1, tg).half()) * O.sparse_linear_f32(xn, W3, tu).half()).reshape(-1)
-    for chained in (False, True):
-        xa = H.aligned((dim,), np.float16, xa0)
-        h, y, ssq_out = H.aligned((inter,), np.float16, 0), H.aligned((dim,), np.float16, 0), H.aligned((64,), np.float32, 0)
-        if chained:
-            calls = [lambda: H.check(L.teal_norm_sparse_gate_up_chain_f16(H.ptr(xa), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(W1c), H.ptr(W3c), H.ptr(h),
-                                                                          dim, inter, inter, inter, tg, tu, 0, H.ptr(ws.buf), ws.nbytes, None), "p"),
-                     lambda: H.check(L.teal_sparse_gemv_residual_chain_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim,
-                                                                           dim, td, 0, H.ptr(ws.buf), ws.nbytes, None), "c")]
-            errs = []
-
-            def guarded(c):
-                try:
-                    c()
-                except Exception as e:  # noqa: BLE001
-                    errs.append(e)
-            tc, tp = threading.Thread(target=guarded, args=(calls[1],)), threading.Thread(target=guarded, args=(calls[0],))
-            tc.start()
-            time.sleep(0.1)
-            tp.start()
-            tp.join(timeout=300)
-            tc.join(timeout=300)
-            assert not errs and not tc.is_alive()
-        else:
-            H.check(L.teal_norm_sparse_gate_up_f16(H.ptr(xa), H.ptr(nwa), eps, H.ptr(ssq), H.ptr(W1c), H.ptr(W3c), H.ptr(h), None, dim, inter,
-                                                   inter, inter, tg, tu, H.ptr(ws.buf), ws.nbytes, None), "gate_up")
-            H.check(L.teal_sparse_gemv_residual_f16(H.ptr(h), H.ptr(W2c), H.ptr(xa), H.ptr(y), H.ptr(ssq_out), inter, dim, dim, td,
-                                                    H.ptr(ws.buf), ws.nbytes, None), "down")
-        ws.assert_clean()
-        h_t = torch.from_numpy(h.copy())
-        assert ((h_t.float() - h_ref.float()).abs() <= h_ref.float().abs() * 2.0 ** -8 + 2e-3).all(), chained
-        want = (resid.reshape(-1) + O.sparse_linear_f32(h_t.reshape(1, 1, -1), W2, td).reshape(-1).half()).float()
-        y_t = torch.from_numpy(y.copy()).float()
-        assert ((y_t - want).abs() <= want.abs() * 2.0 ** -9 + 2e-3).all(), chained

@@ -78,7 +78,11 @@ def test_survivor_tie_rule(golden_dir):
     assert 0 not in got and 1 not in got and 2 in got
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 11, 12, 14, 18, 26, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 100, 101, 102])
+# teal_set_config ids: (variant + 1) + 16 * (lanes per warp / 32); 0 = chosen by launch size
+ALL_CFGS = [0] + [v + 1 + 16 * l for v in range(5) for l in (0, 1, 3, 8, 16)]
+
+
+@pytest.mark.parametrize("cfg", ALL_CFGS)
 def test_golden_cases_all_configs(golden_dir, cfg):
     ops = _ops()
     ops.set_config(cfg)
@@ -120,7 +124,7 @@ def test_full_size_vs_oracle(Z, N, sparsity):
 
 
 @pytest.mark.parametrize("sparsity", [0.0, 0.1, 0.4, 0.9, 0.99, 1.0])
-@pytest.mark.parametrize("cfg", [0, 2, 5, 12, 18, 31, 33, 36, 38, 41])
+@pytest.mark.parametrize("cfg", [0, 1 + 16, 2 + 64, 3, 3 + 32, 4 + 128, 5 + 256])
 def test_sparsity_sweep_config1(sparsity, cfg):
     """BASELINE config 1: Llama-2-7B gate_proj 4096 -> 11008."""
     ops = _ops()
@@ -313,7 +317,7 @@ def test_ssq_handoff_across_different_tilings():
     resid = torch.randn(1, 1, N, generator=g).half()
     nw = (1 + 0.1 * torch.randn(N, generator=g)).half()
     try:
-        for cfg, Z in ((32, 256), (31, 512), (30, 256), (33, 384)):  # 16, 8, 16, 8 column tiles
+        for cfg, Z in ((1, 256), (3, 512), (2, 256), (4, 384)):  # 16, 8, 16, 8 column tiles
             ops.set_config(cfg)
             x, W = _mk(Z, N, 100 + cfg)
             y = ops.gemv_residual(x.cuda(), _colmajor_cuda(W), resid.cuda(), 0.5, ssq_out=ssq)

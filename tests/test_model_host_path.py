@@ -1,7 +1,7 @@
 """teal_b200.model.SparseDecoder's own Python control flow on the CPU: the class is instantiated on CPU tensors with the
 CUDA plumbing (streams, availability check, workspace) stubbed and the library replaced by the CPU emulation of the kernels
-(tests/emu), so `_enqueue_step` -- the exact sequence of C-ABI calls the captured graph contains, including the opt-in
-chained / sampling branches -- runs for real and is checked against OracleDecoder.  CUDA-graph capture itself is not
+(tests/emu), so `_enqueue_step` -- the exact sequence of C-ABI calls the captured graph contains, including the sampling and
+TP-route branches -- runs for real and is checked against OracleDecoder.  CUDA-graph capture itself is not
 exercised here (that is what the -m gpu tests do)."""
 import os
 import sys
@@ -29,7 +29,6 @@ def cpu_decoder(monkeypatch):
     from teal_b200 import _lib, model, ops
     emu = H.lib()
     H.set_config(0)
-    H.set_tuning()
     emu.teal_emu_set_concurrent(0)
     monkeypatch.setattr(_lib, "load", lambda: emu)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
@@ -47,7 +46,7 @@ def cpu_decoder(monkeypatch):
         return dec
 
     yield make
-    H.set_tuning()
+    H.set_config(0)
 
 
 def _check(dec, mode, thresholds):
@@ -71,19 +70,28 @@ def test_default_step_sequence(cpu_decoder, mode):
     assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2
 
 
-def test_opt_in_branches(cpu_decoder):
-    dec = cpu_decoder(THR, TEAL_CHAIN_MLP="1", TEAL_CHAIN_ATTN="1")
-    assert dec.chain_mlp and dec.chain_attn
+def test_tp_route_at_world_one(cpu_decoder):
+    """force_tp_path: plain row-parallel GEMV -> (all-reduce, a no-op at world 1) -> residual add, the route TP ranks take
+    when the peer-memory exchange is unavailable -- two more launches per layer, same logits."""
+    dec = cpu_decoder(THR)
+    dec.force_tp_path = True
     _check(dec, "sparse", THR)
-    assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2
-    dec.chain_attn = False
-    _check(dec, "sparse", THR)
-    dec.chain_mlp, dec.chain_attn = False, True
-    _check(dec, "dense_own", [None] * CFG["n_layer"])
-    dec.chain_mlp = dec.chain_attn = dec.chain_norms = True       # no grid-wide wait left inside the layer stack
-    _check(dec, "sparse", THR)
-    _check(dec, "dense_own", [None] * CFG["n_layer"])
-    assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2
+    assert dec.kernels_per_step == 1 + 7 * CFG["n_layer"] + 2
+
+
+def test_position_is_bounded(cpu_decoder):
+    """The device position advances without the host looking: generate() / decode_one_token() refuse to run past the KV
+    cache, the RoPE table has one row per cache position (model.py:573)."""
+    dec = cpu_decoder(THR)
+    assert dec.freqs.shape[0] == dec.max_seq
+    dec.steps_enqueued = dec.max_seq - 1
+    dec._check_room(1)
+    with pytest.raises(ValueError):
+        dec._check_room(2)
+    dec.reset(1)
+    assert dec.steps_enqueued == 0
+    with pytest.raises(ValueError):
+        dec._check_room(dec.max_seq + 1)
 
 
 def test_sampling_branch(cpu_decoder):
@@ -95,13 +103,11 @@ def test_sampling_branch(cpu_decoder):
         want, _ = O.sample_topk(dec.logits.reshape(-1).clone(), 0.8, 20, O.sample_noise(5, CFG["vocab_size"], i))
         assert int(dec.token) == want
     assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 3
-    with pytest.raises(NotImplementedError):
-        dec.build_program("sparse")
     dec.set_sampling(0.0)
     assert dec.sampling is None
 
 
 def test_calibration_runs_through_the_taps(cpu_decoder):
-    dec = cpu_decoder([None] * CFG["n_layer"], TEAL_CHAIN_MLP="1", TEAL_CHAIN_ATTN="1")
-    thr = dec.calibrate(0.5, n_tokens=3)       # taps force the unchained entry points (they return the normalised x)
+    dec = cpu_decoder([None] * CFG["n_layer"])
+    thr = dec.calibrate(0.5, n_tokens=3)
     assert len(thr) == CFG["n_layer"] and all(v > 0 for t in thr for v in t.values())

@@ -1,6 +1,5 @@
-"""The sampling kernel on the GPU against the reference's own `sample()` (golden vectors) and inside the decode step.
-Written after the round's GPU budget was spent: it passes the CPU emulation (tests/test_sampling.py) but has not run on
-hardware yet, so it is opt-in (TEAL_SAMPLING_GPU_TESTS=1) and greedy decoding stays the default everywhere."""
+"""The sampling kernel on the GPU against the reference's own `sample()` (golden vectors) and inside the decode step
+(first hardware run: profiles/r02_call1_gpu_tests_sampling.log)."""
 import os
 
 import numpy as np
@@ -9,9 +8,7 @@ import torch
 
 from oracle import teal_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TEAL_SAMPLING_GPU_TESTS") != "1",
-                                 reason="sampling kernel not yet run on hardware (set TEAL_SAMPLING_GPU_TESTS=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _sample(logits, T, k, q=None, seed=0, pos=0):

@@ -103,7 +103,7 @@ def test_library_exports_every_declared_symbol():
     assert len(decl) >= 20
     for s in decl:
         assert hasattr(lib, s), s
-    assert lib.teal_abi_version() == 2 and lib.teal_compiled_arch() == 100
+    assert lib.teal_abi_version() == _lib.header_abi_version() and lib.teal_compiled_arch() == 100
     lib.teal_workspace_bytes.restype = ctypes.c_size_t
     assert lib.teal_workspace_bytes(4096) >= 4096 * 4
     # every declared symbol has a ctypes signature in the Python binding

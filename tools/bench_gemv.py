@@ -51,7 +51,7 @@ def time_graph(fn_list, iters=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="4096x14336,14336x4096,4096x4096,4096x6144,4096x11008,8192x28672")
-    ap.add_argument("--configs", default="1,2,3,4,5,6")
+    ap.add_argument("--configs", default="0", help="teal_set_config ids: (variant + 1) + 16 * (lanes per warp / 32), 0 = by size")
     ap.add_argument("--sparsities", default="0.5")
     ap.add_argument("--out", default="gpurun_out/bench_gemv.jsonl")
     ap.add_argument("--launches", type=int, default=48)

@@ -1,10 +1,10 @@
-"""Where does a decode step's time go?  In-kernel timeline of the production row-chunk kernels inside the real graph
+"""Where does a decode step's time go?  In-kernel timeline of the production sparse-GEMV kernel inside the real graph
 replay (run on the GPU box).
 
-Captures one decode step with the TIMED twins of the default kernels (teal_set_debug_timeline: globaltimer stamps per
+Captures one decode step with the TIMED twin of the kernel (teal_set_debug_timeline: globaltimer stamps per
 CTA, one slot per launch), replays it, and prints per projection kind -- averaged over the layers --
   * kernel span (first CTA start -> last CTA end), head (first CTA start -> first rows consumed anywhere),
-  * the gap to the previous row-chunk kernel (its last CTA end -> this kernel's first survivor set / first rows),
+  * the gap to the previous GEMV kernel (its last CTA end -> this kernel's first survivor set / first rows),
   * CTA lifetime distribution and its split: wait for producer | x + survivors | first DRAM rows | rest of the gather |
     reduce + RED | fence + arrival | (finaliser),
   * resident-CTA occupancy over time (how long HBM has < half / < quarter of the slots streaming: the tail),
@@ -12,7 +12,7 @@ CTA, one slot per launch), replays it, and prints per projection kind -- average
 One JSON line per kind (+ one per launch with --per-launch).  Timed kernels carry a few extra stores: treat absolute
 numbers as +-3 %, the structure is the point.
 
-    python tools/rowchunk_timeline.py [--workload llama-3-8b] [--sparsity 0.5] [--out gpurun_out/r02_rowchunk_timeline.jsonl]
+    python tools/gemv_timeline.py [--workload llama-3-8b] [--sparsity 0.5] [--out gpurun_out/gemv_timeline.jsonl]
 """
 import argparse
 import json
@@ -69,16 +69,12 @@ def main():
     ap.add_argument("--sparsity", type=float, default=0.5)
     ap.add_argument("--mode", default="sparse")
     ap.add_argument("--per-launch", action="store_true")
-    ap.add_argument("--chain", default="", help="comma list of mlp,attn,norms: profile the flag-chained step (TEAL_CHAIN_*); "
-                                                "split 'wait_producer' is then the time a CTA spent polling its tiles / hand-off cell")
-    ap.add_argument("--out", default="gpurun_out/r02_rowchunk_timeline.jsonl")
+    ap.add_argument("--out", default="gpurun_out/gemv_timeline.jsonl")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     a = ModelArgs.from_name(args.workload)
     dec = SparseDecoder(a, max_seq=128, out_cap=128)
     dec.calibrate(args.sparsity, n_tokens=4)
-    chain = set(filter(None, args.chain.split(",")))
-    dec.chain_mlp, dec.chain_attn, dec.chain_norms = "mlp" in chain, "attn" in chain, "norms" in chain
     n_launch = 4 * a.n_layer
     # capture() runs one eager warm-up step before it captures: slots 0 .. n-1 go to the warm-up, n .. 2n-1 to the graph
     buf = torch.zeros(2 * n_launch * SLOT_CTAS * 16, dtype=torch.int64, device=dec.dev)

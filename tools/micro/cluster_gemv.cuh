@@ -24,7 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "common.cuh"
+#include "../../teal_b200/csrc/common.cuh"
 
 namespace teal {
 

@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "../../teal_b200/csrc/cluster_gemv.cuh"
+#include "cluster_gemv.cuh"
 
 using namespace teal;
 

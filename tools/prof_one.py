@@ -6,7 +6,7 @@ import teal_b200.ops as ops
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--shapes", default="4096x14336")
-ap.add_argument("--configs", default="2")
+ap.add_argument("--configs", default="0")
 ap.add_argument("--sparsity", type=float, default=0.5)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--gate-up", action="store_true")
