@@ -44,8 +44,11 @@ typedef enum teal_status {
   TEAL_ERR_CUDA = -5         /* CUDA runtime error (message has the cudaError string) */
 } teal_status;
 
-#define TEAL_B200_ABI_VERSION 3
-#define TEAL_SSQ_PARTS 64 /* floats in a sum-of-squares partials buffer */
+#define TEAL_B200_ABI_VERSION 4
+#define TEAL_SSQ_PARTS 64    /* partial sums of squares (one per producer column tile, unused tail zero) */
+#define TEAL_SSQ_REPLICAS 32 /* identical copies of the partials: ~4000 consumer warps read them at the same instant, one copy
+                              * would be a single hot L2 line (measured: 1.4-2 us of every RMSNorm-fused launch) */
+#define TEAL_SSQ_FLOATS (TEAL_SSQ_PARTS * TEAL_SSQ_REPLICAS) /* floats in a sum-of-squares buffer: replica r at [r * PARTS] */
 
 int teal_abi_version(void);
 const char* teal_last_error(void);
@@ -89,10 +92,10 @@ int teal_sparse_gate_up_f16(const void* x, const void* w1t, const void* w3t, voi
  * residual stream x is computed in the kernel prologue, then thresholded; `xn_out` (nullable)
  * receives the normalised vector.  Replaces attention_norm + gemv1 (model.py:159,168) ...
  * Sum-of-squares hand-off: no CTA reads the whole vector for the norm.  The producer of x leaves
- * TEAL_SSQ_PARTS fp32 partial sums of squares (`ssq_out` of teal_embed_f16 /
- * teal_sparse_gemv_residual_f16: it writes its tiles' partials, the unused tail of the buffer must
- * be zero) and the consumer takes them as `ssq_in`; with ssq_in == NULL the library computes them
- * with one extra tiny launch. */
+ * TEAL_SSQ_PARTS fp32 partial sums of squares, replicated TEAL_SSQ_REPLICAS times (`ssq_out` of
+ * teal_embed_f16 / teal_sparse_gemv_residual_f16, a buffer of TEAL_SSQ_FLOATS floats: every replica
+ * is fully rewritten on every call) and the consumer takes the buffer as `ssq_in` (each CTA reads
+ * one replica); with ssq_in == NULL the library computes them with one extra tiny launch. */
 int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps, const float* ssq_in,
                                   const void* wt, void* y, void* xn_out, int Z, int N, int64_t ldw,
                                   int kv_size,
@@ -119,7 +122,8 @@ int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, fl
 /* RoPE(q, k) with the fp16 (cos, sin) table freqs_cis[max_seq][head_dim/2][2], KV-cache append at
  * *pos, attention of the one query token over positions [0, *pos], heads concatenated
  * (gpt-fast/model.py:170-186).  qkv: fp16 [n_head*hd | n_kv*hd | n_kv*hd]; caches fp16
- * [n_kv][max_seq][hd] (the reference's [1, H_kv, S, D], model.py:84); out: fp16 [n_head*hd]. */
+ * [n_kv][max_seq][hd] (the reference's [1, H_kv, S, D], model.py:84); out: fp16 [n_head*hd].
+ * *pos outside [0, max_seq) touches no memory and writes NaN (the caller must bound the position). */
 int teal_attn_decode_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache,
                          const int32_t* pos, void* out, int n_head, int n_kv_head, int head_dim,
                          int max_seq, void* stream);

@@ -10,7 +10,8 @@ namespace teal {
 
 constexpr int kMaxSeg = 4;         // column regions per call (q | k | v, gate | up)
 constexpr int kMaxCounters = 4096; // column tiles per call
-constexpr int kSsqParts = TEAL_SSQ_PARTS;  // fixed length of a sum-of-squares partials buffer (unused tail stays zero)
+constexpr int kSsqParts = TEAL_SSQ_PARTS;        // partial sums of squares per replica (unused tail stays zero)
+constexpr int kSsqReplicas = TEAL_SSQ_REPLICAS;  // identical copies, so that ~4000 consumer warps do not share one L2 line
 constexpr int kMaxTpWorld = 16;    // ranks of one tensor-parallel group (one NVSwitch domain)
 constexpr int kListCap = 512;      // survivor-list entries (= input lanes) one warp may own
 

@@ -42,10 +42,11 @@ __global__ void embed_kernel(const __half* __restrict__ emb, const int* __restri
     if (threadIdx.x == 0) {
       float a = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sp[w];
-      ssq_out[0] = a;
-    } else if (threadIdx.x < kSsqParts) {
-      ssq_out[threadIdx.x] = 0.f;
+      sp[0] = a;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSsqParts * kSsqReplicas; i += blockDim.x)  // every replica: {total, 0, 0, ...}
+      ssq_out[i] = (i % kSsqParts == 0) ? sp[0] : 0.f;
   }
   griddep_launch_dependents();
 }
@@ -55,8 +56,15 @@ __global__ void embed_kernel(const __half* __restrict__ emb, const int* __restri
 // gpt-fast/model.py:170-186: adjacent-pair rotation with the fp16 (cos, sin) table, KVCache.update,
 // GQA (kv head = q head / rep), scaled dot product attention, heads concatenated.
 // grid = n_head CTAs (one per query head), block = kAttnThreads.
+//
+// The kernel sits between two HBM-bound GEMVs and is pure latency at the benchmark's short context, so it is shaped
+// for the length of its dependency chain: 16 warps, each with 8 positions' K and V rows in flight at once (128 positions
+// per sweep), q / k / v requested together with the position (+2 % tokens/s over 8 warps x 4 positions).
+// Measured and dropped (profiles/r02_quick_ab_attn_pf*.jsonl): helper CTAs that pull the o projection's weights into L2
+// while this kernel leaves HBM idle -- 33 MB do not fit the 2.5 us window, the rest delays the o projection's own
+// requests (-3 %).
 // --------------------------------------------------------------------------------------------
-constexpr int kAttnThreads = 256;
+constexpr int kAttnThreads = 512;
 constexpr int kAttnWarps = kAttnThreads / 32;
 
 template <int HD>
@@ -74,46 +82,49 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
   __shared__ float s_acc[kAttnWarps][HD];
 
-  const int h = blockIdx.x;
-  const int kvh = h / (n_head / n_kv);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x;
+  const int rep = n_head / n_kv;
+  const int kvh = h / rep;
+  // ---- q, new k, new v are the producer's output: requested after the wait, together with the position -----------
   griddep_wait();
   griddep_launch_dependents();  // n_head CTAs leave most of the machine free: the o-proj grid moves in and waits for us
+  const __half* qh = qkv + (size_t)h * HD;
+  const __half* kh = qkv + (size_t)n_head * HD + (size_t)kvh * HD;
+  const __half* vh = qkv + (size_t)(n_head + n_kv) * HD + (size_t)kvh * HD;
+  __half2 in2 = __halves2half2(__ushort_as_half((unsigned short)0), __ushort_as_half((unsigned short)0));
+  __half2 k2 = in2;
+  if (tid < HD / 2) {
+    in2 = reinterpret_cast<const __half2*>(qh)[tid];
+    k2 = reinterpret_cast<const __half2*>(kh)[tid];
+  } else if (tid < HD) {
+    in2 = reinterpret_cast<const __half2*>(vh)[tid - HD / 2];
+  }
   const int pos = pos_ptr[0];
   if (pos < 0 || pos >= max_seq) {  // beyond the KV cache / RoPE table (the host raises before this can happen): touch nothing
     if (tid < HD) out[(size_t)h * HD + tid] = __ushort_as_half((unsigned short)0x7e00);  // NaN: a silent wrong token is worse
     return;
   }
-
   // ---- RoPE on q (this head) and on the new k (its kv head); v passes through ---------------------
-  const __half* qh = qkv + (size_t)h * HD;
-  const __half* kh = qkv + (size_t)n_head * HD + (size_t)kvh * HD;
-  const __half* vh = qkv + (size_t)(n_head + n_kv) * HD + (size_t)kvh * HD;
-  const __half* fr = freqs + (size_t)pos * HD;  // HD/2 pairs * 2
   if (tid < HD / 2) {
-    const float c = __half2float(fr[2 * tid]), s = __half2float(fr[2 * tid + 1]);
-    const float q0 = __half2float(qh[2 * tid]), q1 = __half2float(qh[2 * tid + 1]);
-    const float k0 = __half2float(kh[2 * tid]), k1 = __half2float(kh[2 * tid + 1]);
+    const __half2 cs = reinterpret_cast<const __half2*>(freqs + (size_t)pos * HD)[tid];  // (cos, sin) of pair `tid`
+    const float c = __low2float(cs), sn = __high2float(cs);
+    const float q0 = __low2float(in2), q1 = __high2float(in2);
+    const float k0 = __low2float(k2), k1 = __high2float(k2);
     // model.py:309-315, result cast back to fp16 (type_as)
-    const __half qa = __float2half_rn(q0 * c - q1 * s), qb = __float2half_rn(q1 * c + q0 * s);
-    const __half ka = __float2half_rn(k0 * c - k1 * s), kb = __float2half_rn(k1 * c + k0 * s);
+    const __half qa = __float2half_rn(q0 * c - q1 * sn), qb = __float2half_rn(q1 * c + q0 * sn);
+    const __half ka = __float2half_rn(k0 * c - k1 * sn), kb = __float2half_rn(k1 * c + k0 * sn);
     s_q[2 * tid] = __half2float(qa);
     s_q[2 * tid + 1] = __half2float(qb);
     s_knew[2 * tid] = __half2float(ka);
     s_knew[2 * tid + 1] = __half2float(kb);
-    if (h % (n_head / n_kv) == 0) {  // one CTA per kv head appends to the cache (model.py:93-94)
-      k_cache[((size_t)kvh * max_seq + pos) * HD + 2 * tid] = ka;
-      k_cache[((size_t)kvh * max_seq + pos) * HD + 2 * tid + 1] = kb;
-    }
-  } else if (tid < HD / 2 + HD / 2) {
+    if (h % rep == 0)  // one CTA per kv head appends to the cache (model.py:93-94)
+      reinterpret_cast<__half2*>(k_cache + ((size_t)kvh * max_seq + pos) * HD)[tid] = __halves2half2(ka, kb);
+  } else if (tid < HD) {
     const int i = tid - HD / 2;
-    const __half v0 = vh[2 * i], v1 = vh[2 * i + 1];
-    s_vnew[2 * i] = __half2float(v0);
-    s_vnew[2 * i + 1] = __half2float(v1);
-    if (h % (n_head / n_kv) == 0) {
-      v_cache[((size_t)kvh * max_seq + pos) * HD + 2 * i] = v0;
-      v_cache[((size_t)kvh * max_seq + pos) * HD + 2 * i + 1] = v1;
-    }
+    s_vnew[2 * i] = __low2float(in2);
+    s_vnew[2 * i + 1] = __high2float(in2);
+    if (h % rep == 0) reinterpret_cast<__half2*>(v_cache + ((size_t)kvh * max_seq + pos) * HD)[i] = in2;
   }
   __syncthreads();
 
@@ -126,8 +137,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
   const __half* kbase = k_cache + (size_t)kvh * max_seq * HD;
   const __half* vbase = v_cache + (size_t)kvh * max_seq * HD;
-  // 4 positions per iteration so that the 8 global loads of a lane are independent (latency-bound at short context)
-  constexpr int PB = 4;
+  // PB positions per iteration so that the 2 * PB global loads of a lane are independent (latency-bound at short context)
+  constexpr int PB = 8;
   for (int p0 = warp; p0 <= pos; p0 += kAttnWarps * PB) {
     float kk[PB][EPL], vv[PB][EPL];
 #pragma unroll
@@ -151,14 +162,14 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
     for (int b = 0; b < PB; ++b) {
       const int p = p0 + b * kAttnWarps;
       if (p <= pos) {
-        float s = 0.f;
+        float sc = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) s = fmaf(qreg[e], kk[b][e], s);
+        for (int e = 0; e < EPL; ++e) sc = fmaf(qreg[e], kk[b][e], sc);
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        s *= scale;
-        const float mn = fmaxf(m, s);
-        const float corr = __expf(m - mn), pe = __expf(s - mn);
+        for (int d = 16; d > 0; d >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, d);
+        sc *= scale;
+        const float mn = fmaxf(m, sc);
+        const float corr = __expf(m - mn), pe = __expf(sc - mn);
         l = l * corr + pe;
 #pragma unroll
         for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pe, vv[b][e], acc[e] * corr);
@@ -475,10 +486,11 @@ __global__ void residual_add_kernel(__half* __restrict__ x, const __half* __rest
     if (threadIdx.x == 0) {
       float a = 0.f;
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sp[w];
-      ssq_out[0] = a;
-    } else if (threadIdx.x < kSsqParts) {
-      ssq_out[threadIdx.x] = 0.f;
+      sp[0] = a;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSsqParts * kSsqReplicas; i += blockDim.x)  // every replica: {total, 0, 0, ...}
+      ssq_out[i] = (i % kSsqParts == 0) ? sp[0] : 0.f;
   }
   griddep_launch_dependents();
 }
@@ -568,11 +580,13 @@ __global__ void __launch_bounds__(1024, 1) tp_allreduce_residual_kernel(const __
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sp[w];
-    if (ssq_out) ssq_out[0] = t;
+    sp[0] = t;
     *epoch_cell = e;
-  } else if (ssq_out && threadIdx.x < kSsqParts) {
-    ssq_out[threadIdx.x] = 0.f;
   }
+  __syncthreads();
+  if (ssq_out)
+    for (int i = threadIdx.x; i < kSsqParts * kSsqReplicas; i += blockDim.x)  // every replica: {total, 0, 0, ...}
+      ssq_out[i] = (i % kSsqParts == 0) ? sp[0] : 0.f;
   griddep_launch_dependents();
 }
 
@@ -604,6 +618,9 @@ int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, 
                        __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream) {
   if (!qkv || !freqs || !k_cache || !v_cache || !pos || !out || n_head <= 0 || n_kv <= 0 || n_head % n_kv)
     return set_error(TEAL_ERR_BAD_ARG, "attn_decode: bad argument");
+  if ((reinterpret_cast<uintptr_t>(qkv) & 3) || (reinterpret_cast<uintptr_t>(freqs) & 3) || (reinterpret_cast<uintptr_t>(k_cache) & 3) ||
+      (reinterpret_cast<uintptr_t>(v_cache) & 3))
+    return set_error(TEAL_ERR_ALIGNMENT, "attn_decode: 4-byte aligned vectors");
   const float scale = 1.0f / sqrtf((float)head_dim);
   if (head_dim == 128)
     return launch_pdl(attn_decode_kernel<128>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, freqs,

@@ -194,28 +194,41 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
   const uint64_t wrow = reinterpret_cast<uint64_t>(sg.w + col0 + lane * 8) + (uint64_t)(uint32_t)kb * ldwb;
   const bool rms = p.in_mode == kInRmsNorm;
 
-  // ---- before the producer is done: the norm weights are constants, pull the warp's lines towards L2 -------------
-  if (rms && kb + lane * 64 < ke) prefetch_l2(p.norm_w + kb + lane * 64);
+  // ---- before the producer is done: the norm weights are constants -- the first pass's into registers, the lines of
+  // the later passes towards L2 -----------------------------------------------------------------------------------------
+  __half xh[kPass], nw[kPass];
+  auto load_nw = [&](int q0) {
+#pragma unroll
+    for (int q = 0; q < kPass; ++q) {
+      const int k = kb + (q0 + q) * 32 + lane;
+      nw[q] = (rms && k < ke) ? p.norm_w[k] : __ushort_as_half((unsigned short)0);
+    }
+  };
+  auto load_x = [&](int q0) {
+#pragma unroll
+    for (int q = 0; q < kPass; ++q) {
+      const int k = kb + (q0 + q) * 32 + lane;
+      xh[q] = (k < ke) ? ldcg_half(p.x + k) : __ushort_as_half((unsigned short)0);
+    }
+  };
+  load_nw(0);
+  if (rms && kb + kPass * 32 + lane * 64 < ke) prefetch_l2(p.norm_w + kb + kPass * 32 + lane * 64);
 
   griddep_wait();               // PDL: everything above overlapped the previous kernel's tail
   griddep_launch_dependents();  // the next kernel may move in behind us and wait for our completion
   stamp(1);
 
   // ---- x lanes and the producer's sum-of-squares partials: all requests of the first pass in flight together ------
-  __half xh[kPass], nw[kPass];
-  auto load_pass = [&](int q0) {
-#pragma unroll
-    for (int q = 0; q < kPass; ++q) {
-      const int k = kb + (q0 + q) * 32 + lane;
-      xh[q] = (k < ke) ? ldcg_half(p.x + k) : __ushort_as_half((unsigned short)0);
-      nw[q] = (rms && k < ke) ? p.norm_w[k] : __ushort_as_half((unsigned short)0);
-    }
-  };
-  load_pass(0);
+  load_x(0);
   float rs = 1.f;
   if (rms) {  // gpt-fast/model.py:286-291
     float t = 0.f;
-    for (int i = lane; i < p.n_ssq_in; i += 32) t += __ldcg(p.ssq_in + i);
+    const float* ssq = p.ssq_in + (size_t)((blockIdx.x * WARPS + warp) & (kSsqReplicas - 1)) * kSsqParts;  // my replica
+    static_assert(kSsqParts == 64, "two requests per lane, both in flight together");
+    {
+      const float a = __ldcg(ssq + lane), b = __ldcg(ssq + lane + 32);
+      t = a + b;
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
     rs = rsqrtf(t / (float)p.Z + p.eps);
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
   int n = 0;
   const int ngroups = (ke - kb + 31) >> 5;
   for (int q0 = 0; q0 < ngroups; q0 += kPass) {
-    if (q0 > 0) load_pass(q0);
+    if (q0 > 0) { load_nw(q0); load_x(q0); }
 #pragma unroll
     for (int q = 0; q < kPass; ++q) {
       if (q0 + q < ngroups) {  // warp-uniform
@@ -400,14 +413,15 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
     for (int d = 16; d > 0; d >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
     if (lane == 0) s_ssq[warp] = ssq;
     __syncthreads();
-    if (tid == 0) {
+    if (tid < kSsqReplicas) {  // one thread per replica of the partials buffer
       float a = 0.f;
 #pragma unroll
       for (int w = 0; w < WARPS; ++w) a += s_ssq[w];
-      p.ssq_out[cidx] = a;
-      // every slot of the kSsqParts-long buffer is (re)defined by exactly one tile on every call: slot i by tile i,
-      // the unused tail i + T, i + 2T, ... is zeroed -- a previous producer with more tiles leaves nothing stale
-      for (int sidx = cidx + p.total_ctiles; sidx < kSsqParts; sidx += p.total_ctiles) p.ssq_out[sidx] = 0.f;
+      float* rep = p.ssq_out + tid * kSsqParts;
+      rep[cidx] = a;
+      // every slot of a replica is (re)defined by exactly one tile on every call: slot i by tile i, the unused tail
+      // i + T, i + 2T, ... is zeroed -- a previous producer with more tiles leaves nothing stale
+      for (int sidx = cidx + p.total_ctiles; sidx < kSsqParts; sidx += p.total_ctiles) rep[sidx] = 0.f;
     }
   }
   if (tid == 0) p.counters[cidx] = 0;
@@ -433,8 +447,10 @@ __global__ void ssq_kernel(const __half* __restrict__ x, int Z, float* __restric
   if (threadIdx.x == 0) {
     float a = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sp[w];
-    ssq_out[i] = a;
+    sp[0] = a;
   }
+  __syncthreads();
+  if (threadIdx.x < kSsqReplicas) ssq_out[threadIdx.x * kSsqParts + i] = sp[0];
   griddep_launch_dependents();
 }
 
@@ -546,7 +562,7 @@ int launch_sparse_gemv(const GemvParams& gp, void* workspace, size_t ws_bytes, i
     p.counters = reinterpret_cast<unsigned*>(workspace);
     p.acc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)kMaxCounters * 4);
   }
-  if (gp.in_mode == kInRmsNorm && (!gp.norm_w || !gp.ssq_in || gp.n_ssq_in <= 0))
+  if (gp.in_mode == kInRmsNorm && (!gp.norm_w || !gp.ssq_in || gp.n_ssq_in != kSsqParts))
     return set_error(TEAL_ERR_BAD_ARG, "RMSNorm mode needs norm_w and the producer's sum-of-squares partials");
   if (gp.ssq_out && gp.mode == kModePairSilu) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out is not defined for the gate/up pair");
   if (gp.out_mode == kOutAddResidual && (!gp.resid || (reinterpret_cast<uintptr_t>(gp.resid) & 7)))
@@ -679,10 +695,10 @@ int launch_simple(const __half* x, const __half* wt, __half* y, int Z, int N, lo
 
 size_t workspace_bytes(int max_out_cols) {
   size_t acc = ((size_t)max_out_cols * 4 + 255) & ~(size_t)255;
-  return (size_t)kMaxCounters * 4 + acc + (size_t)kSsqParts * 4;  // [counters][acc][ssq scratch]
+  return (size_t)kMaxCounters * 4 + acc + (size_t)kSsqParts * kSsqReplicas * 4;  // [counters][acc][ssq scratch]
 }
 float* workspace_ssq_scratch(void* workspace, size_t ws_bytes) {
-  return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + ws_bytes - (size_t)kSsqParts * 4);
+  return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + ws_bytes - (size_t)kSsqParts * kSsqReplicas * 4);
 }
 
 }  // namespace teal

@@ -158,7 +158,7 @@ class SparseDecoder:
         self.h = torch.zeros(1, 1, self.inter_l, dtype=f16, device=dev)
         self.part = torch.zeros(1, 1, a.dim, dtype=f16, device=dev)
         self.logits = torch.zeros(1, 1, a.vocab_size, dtype=f16, device=dev)
-        self.ssq = torch.zeros(64, dtype=torch.float32, device=dev)  # sum-of-squares partials of the residual stream
+        self.ssq = torch.zeros(ops.SSQ_FLOATS, dtype=torch.float32, device=dev)  # replicated sum-of-squares partials of the residual stream
         self.stream = torch.cuda.Stream(device=dev)
         self.tp_fused = False
         if world > 1:

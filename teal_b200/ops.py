@@ -159,7 +159,7 @@ def norm_gate_up(x, norm_w, eps, w1, w3, t_gate, t_up, want_xn=False):
 
 
 def gemv_residual(x, weight, resid, threshold, ssq_out=None):
-    """resid + sparse_gemv(x, weight) with the add fused into the kernel's finaliser; ``ssq_out`` (fp32[64], optional)
+    """resid + sparse_gemv(x, weight) with the add fused into the kernel's finaliser; ``ssq_out`` (fp32[SSQ_FLOATS], optional)
     receives the per-tile sums of squares of the result for the next fused RMSNorm."""
     N, Z = weight.shape
     x = _check_x(x, Z)
@@ -280,4 +280,6 @@ def set_config(config_id: int = 0, variant: int = -1, lanes_per_warp: int = 0) -
 
 
 NUM_VARIANTS = 5  # kernel variants of csrc/gemv.cu (tile width x warps per CTA)
+SSQ_PARTS, SSQ_REPLICAS = 64, 32  # TEAL_SSQ_PARTS / TEAL_SSQ_REPLICAS of include/teal_b200.h
+SSQ_FLOATS = SSQ_PARTS * SSQ_REPLICAS  # floats in a sum-of-squares buffer (replica r at [r * SSQ_PARTS])
 

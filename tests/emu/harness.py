@@ -65,7 +65,7 @@ class Workspace:
 
     def assert_clean(self):
         """every kernel must leave counters and accumulators zeroed (no memset launch anywhere)"""
-        scratch = 64 * 4                       # the trailing sum-of-squares scratch may hold values
+        scratch = 64 * 32 * 4                  # the trailing sum-of-squares scratch may hold values
         assert not self.buf[: self.nbytes - scratch].any(), "workspace not left zeroed"
 
 
@@ -113,7 +113,7 @@ class EmuDecoder:
         self.out_tokens, self.argmax = aligned((256,), np.int32, 0), aligned((1,), np.uint64, 0)
         self.x, self.qkv, self.att = aligned((self.dim,), f16, 0), aligned((self.nqkv,), f16, 0), aligned((self.dim,), f16, 0)
         self.h, self.logits = aligned((self.inter,), f16, 0), aligned((self.vocab,), f16, 0)
-        self.ssq = aligned((64,), np.float32, 0)
+        self.ssq = aligned((64 * 32,), np.float32, 0)   # TEAL_SSQ_FLOATS
         self.ws = Workspace(1 << 17)   # the product's size (teal_b200/ops.py)
         self.sampling = None   # dict(temperature, top_k, seed) as in SparseDecoder.set_sampling
 

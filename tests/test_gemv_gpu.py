@@ -313,7 +313,7 @@ def test_ssq_handoff_across_different_tilings():
     ops = _ops()
     g = torch.Generator().manual_seed(21)
     N = 4096
-    ssq = torch.zeros(64, dtype=torch.float32, device="cuda")
+    ssq = torch.zeros(ops.SSQ_FLOATS, dtype=torch.float32, device="cuda")
     resid = torch.randn(1, 1, N, generator=g).half()
     nw = (1 + 0.1 * torch.randn(N, generator=g)).half()
     try:
@@ -323,7 +323,8 @@ def test_ssq_handoff_across_different_tilings():
             y = ops.gemv_residual(x.cuda(), _colmajor_cuda(W), resid.cuda(), 0.5, ssq_out=ssq)
             yk = y.cpu().float().reshape(-1)
             want = float((yk * yk).sum())
-            got = float(ssq.sum())
+            got = float(ssq[:64].sum())
+            assert torch.equal(ssq.view(32, 64)[0], ssq.view(32, 64)[31])
             assert abs(got - want) <= 1e-4 * want, (cfg, got, want)
             # consumer: RMSNorm from the partials == oracle rms_norm of the same vector
             ops.set_config(0)
