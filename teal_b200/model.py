@@ -493,9 +493,9 @@ class SparseDecoder:
                 self.stream.synchronize()
                 self.token.copy_(saved[0]); self.pos.copy_(saved[1]); self.argmax.zero_()
                 g = torch.cuda.CUDAGraph()
-                # TP: the NCCL watchdog thread polls events while we capture -> capture errors must be thread-local
-                cap_mode = "thread_local" if self.world > 1 else "global"
-                with torch.cuda.graph(g, stream=self.stream, capture_error_mode=cap_mode):
+                # thread-local capture errors: other host threads (a second decoder capturing, the NCCL watchdog polling
+                # events under TP) must not invalidate this capture
+                with torch.cuda.graph(g, stream=self.stream, capture_error_mode="thread_local"):
                     self._enqueue_step(mode)
         finally:
             self.lib.teal_set_pdl(0)

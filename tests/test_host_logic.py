@@ -193,3 +193,70 @@ def test_checkpoint_helpers(tmp_path):
     (tmp_path / "m2" / "histograms" / "layer-0").mkdir(parents=True)
     assert resolve_histogram_dir(str(tmp_path / "m")).endswith("Untitled")
     assert resolve_histogram_dir(str(tmp_path / "m2")).endswith("histograms")
+
+
+def test_hf_model_level_setters_on_shipped_shaped_fixtures(tmp_path):
+    """teal/model.py:95-155: build_sparse_layers / set_uniform_sparsity / set_mlp_sparsity / set_self_attn_sparsity /
+    load_greedy_sparsities / reset_sparsities / set_apply_prefill on a two-layer HF-shaped model, with histograms.pt and
+    results.csv files in the reference's on-disk layout; SparseLinear keeps ONE copy of the weight."""
+    from teal_b200.hf import SparseLinear, SparseModelSetters
+    from teal_b200.distribution import Distribution
+
+    class Attn(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            for p in "qkvo":
+                setattr(self, f"{p}_proj", torch.nn.Linear(16, 16, bias=False, dtype=torch.float16))
+
+    class MLP(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj = torch.nn.Linear(16, 32, bias=False, dtype=torch.float16)
+            self.up_proj = torch.nn.Linear(16, 32, bias=False, dtype=torch.float16)
+            self.down_proj = torch.nn.Linear(32, 16, bias=False, dtype=torch.float16)
+            self.act_fn = torch.nn.SiLU()
+
+    class Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_attn, self.mlp = Attn(), MLP()
+
+    class Inner(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = torch.nn.ModuleList([Layer(), Layer()])
+
+    class LM(SparseModelSetters, torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = Inner()
+
+    g = torch.Generator().manual_seed(0)
+    for i in range(2):
+        for sub in ("mlp", "self_attn"):
+            d = tmp_path / "hist" / f"layer-{i}" / sub
+            d.mkdir(parents=True)
+            centers = torch.linspace(-2, 2, 101)
+            hist = {"h1": torch.rand(101, generator=g) + 0.1, "h1_centers": centers, "h2": torch.rand(101, generator=g) + 0.1,
+                    "h2_centers": centers * 0.1}
+            torch.save(hist, d / "histograms.pt")
+        lk = tmp_path / "lookup" / f"layer-{i}"
+        lk.mkdir(parents=True)
+        (lk / "results.csv").write_text("Effective Sparsity,Activation Error,Baseline Error,q,k,v,o,gate,up,down\n"
+                                        "0.3,0,0,0.3,0.3,0.3,0.3,0.3,0.3,0.3\n0.5,0,0,0.6,0.5,0.2,0.55,0.45,0.4,0.6\n")
+    m = LM().configure_sparsity(str(tmp_path / "hist"), uniform_sparsity=0.5, apply_prefill=False)
+    d_h1 = Distribution(str(tmp_path / "hist" / "layer-1" / "mlp"), "h1")
+    assert m.model.layers[1].mlp.sparse_fns["gate"].threshold == d_h1.icdf(0.75)
+    assert m.model.layers[0].self_attn.sparse_fns["o"].apply_prefill is False
+    assert isinstance(m.model.layers[0].self_attn.q_proj, SparseLinear)
+    assert not any(p.requires_grad for p in m.parameters())
+    m.set_mlp_sparsity(0.4)
+    assert m.model.layers[0].mlp.sparse_fns["down"].sparsity_level == 0.4 and m.model.layers[0].self_attn.sparse_fns["q"].sparsity_level == 0.5
+    m.load_greedy_sparsities(str(tmp_path / "lookup"), 0.5)
+    d_a1 = Distribution(str(tmp_path / "hist" / "layer-0" / "self_attn"), "h1")
+    assert m.model.layers[0].self_attn.sparse_fns["v"].threshold == d_a1.icdf(0.5 + 0.2 / 2)
+    m.reset_sparsities()
+    assert all(l.mlp.sparse_fns[p].threshold == 0.0 for l in m.model.layers for p in ("gate", "up", "down"))
+    # one copy of the weight: SparseLinear has no parameter or buffer of its own besides the wrapped Linear's
+    sl = m.model.layers[0].mlp.sparse_linears["gate"]
+    assert [n for n, _ in sl.named_parameters()] == ["linear.weight"] and not list(sl.buffers())
