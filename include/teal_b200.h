@@ -156,15 +156,15 @@ int teal_sample_topk_f16(const void* logits, int V, double temperature, int top_
 /* Row-parallel projection (o / down under tensor parallelism, gpt-fast/tp.py:117,130) with its exchange step
  * (tp.py:120-121,139-140) and the residual add (model.py:160-161) in ONE kernel: resid_x[N] += sum over ranks of the
  * rank's partial y = W_shard * mask(x_shard), in place, plus the per-tile sums of squares for the next RMSNorm.  The
- * finaliser of every column tile writes the rank's fp16 partial of that tile into peer_partials[rank], raises
- * peer_flags[q][rank * TEAL_SSQ_PARTS + tile] on every peer q, waits for the peers' flags of the same tile and adds the
- * partials in rank order (bit-identical replicas).  peer_partials[r]: rank r's fp16 [N] buffer, peer_flags[r]: rank r's
- * uint32 [world * TEAL_SSQ_PARTS] flag array (both peer-mapped, zero-initialised; HOST arrays of `world` device
- * pointers); epoch_tiles: local device uint32 [TEAL_SSQ_PARTS], zero-initialised.  Consecutive exchanges must alternate
- * between two (partials, flags, epochs) sets, like teal_tp_allreduce_residual_f16. */
+ * finaliser of every column tile PUSHES the rank's fp16 partial of that tile into every rank's receive buffer as 8-byte
+ * words {2 x fp16, epoch} (data and flag in one store: no fence, no remote read), polls its own buffer until all `world`
+ * words of a column pair carry the epoch, and adds them in rank order (bit-identical replicas).
+ * peer_recv[r]: rank r's receive buffer, world * N / 2 eight-byte words = world * N * 4 bytes (peer-mapped, e.g. torch
+ * symmetric memory; zero-initialised; HOST array of `world` device pointers); epoch_tiles: local device uint32
+ * [TEAL_SSQ_PARTS], zero-initialised.  Consecutive exchanges must alternate between two (recv, epochs) sets. */
 int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
-                                     double threshold, void* const* peer_partials, void* const* peer_flags, void* epoch_tiles,
-                                     int rank, int world, void* workspace, size_t workspace_bytes, void* stream);
+                                     double threshold, void* const* peer_recv, void* epoch_tiles, int rank, int world,
+                                     void* workspace, size_t workspace_bytes, void* stream);
 /* Greedy step bookkeeping: *token = arg-max index, out_tokens[*pos] = *token, ++*pos, reset cell. */
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap,
                  void* stream);

@@ -50,7 +50,7 @@ _SIGS = {
     "teal_sample_topk_f16": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_int, _c.c_void_p, _c.c_uint64, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p]),
     "teal_sparse_gemv_tp_exchange_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
-                                                    _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+                                                    _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                                     _c.c_size_t, _c.c_void_p]),
     "teal_advance": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "teal_survivors_f16": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p]),

@@ -242,21 +242,19 @@ int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* res
 }
 
 int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
-                                     double threshold, void* const* peer_partials, void* const* peer_flags, void* epoch_tiles,
-                                     int rank, int world, void* workspace, size_t workspace_bytes_, void* stream) {
+                                     double threshold, void* const* peer_recv, void* epoch_tiles, int rank, int world,
+                                     void* workspace, size_t workspace_bytes_, void* stream) {
   GemvParams p;
   if (int rc = fill_common(p, x, resid_x, Z)) return rc;
-  if (!wt || !resid_x || !peer_partials || !peer_flags || !epoch_tiles || N <= 0 || ldw < N || world < 1 || world > kMaxTpWorld)
+  if (!wt || !resid_x || !peer_recv || !epoch_tiles || N <= 0 || ldw < N || world < 1 || world > kMaxTpWorld)
     return set_error(TEAL_ERR_BAD_ARG, "bad wt / resid_x / peers / N / ldw / world");
   TpFuse tp;
   memset(&tp, 0, sizeof(tp));
-  for (int r = 0; r < world; ++r) {
-    tp.part[r] = reinterpret_cast<__half*>(peer_partials[r]);
-    tp.flags[r] = reinterpret_cast<unsigned*>(peer_flags[r]);
-  }
+  for (int r = 0; r < world; ++r) tp.recv[r] = reinterpret_cast<uint2*>(peer_recv[r]);
   tp.epoch = reinterpret_cast<unsigned*>(epoch_tiles);
   tp.rank = rank;
   tp.world = world;
+  tp.n = N;
   p.mode = kModePlain;
   p.out_mode = kOutAddResidual;
   p.resid = reinterpret_cast<const __half*>(resid_x);

@@ -19,14 +19,15 @@ enum { kModePlain = 0, kModePairSilu = 1, kModeSurvivors = 2 };
 enum { kInPlain = 0, kInRmsNorm = 1 };        // how x is produced from the input vector
 enum { kOutPlain = 0, kOutAddResidual = 1 };  // what the finaliser adds before writing fp16
 
-// Row-parallel GEMV fused with its TP exchange (sparse_gemv_kernel<.., TP = true>): the finaliser of a column tile
-// writes the rank's fp16 partial of that tile into its peer-mapped buffer, publishes flags[peer][rank * kSsqParts + tile]
-// = epoch to every peer, waits for the peers' flags of the same tile, sums the partials in rank order, adds the residual.
+// Row-parallel GEMV fused with its TP exchange (sparse_gemv_kernel<.., TP = true>), low-latency PUSH protocol: the
+// finaliser of a column tile sends the rank's fp16 partial of that tile straight into every rank's receive buffer as
+// 8-byte words {2 fp16 values, epoch} -- data and flag travel in ONE store (single-copy atomic), so there is no fence, no
+// separate flag and no remote read: the receiver polls its LOCAL buffer until the word carries the current epoch -- then
+// sums the `world` words of every column pair in rank order (bit-identical replicas), adds the residual.
 struct TpFuse {
-  __half* part[kMaxTpWorld];     // this exchange's partial buffer [N] of every rank (peer-mapped; [rank] is local)
-  unsigned* flags[kMaxTpWorld];  // flag array [world * kSsqParts] of every rank
-  unsigned* epoch;               // local [kSsqParts]: exchanges completed per tile
-  int rank, world;
+  uint2* recv[kMaxTpWorld];  // receive buffer of every rank (peer-mapped; [rank] is local): [world sources][N / 2] words
+  unsigned* epoch;           // local [kSsqParts]: exchanges completed per tile on this buffer set
+  int rank, world, n;        // n = N (columns of the projection = row length of a source's slot)
 };
 
 // ---- what the C ABI entry points hand to the launcher ------------------------------------------------------------

@@ -68,9 +68,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { (void)*reinterpret_
 __device__ __forceinline__ __half ldcg_half(const __half* p) { return __ushort_as_half(__ldcg(reinterpret_cast<const unsigned short*>(p))); }
 __device__ __forceinline__ uint32_t lds_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ uint64_t row_address(uint64_t base, uint32_t row, uint32_t row_bytes) { return base + (uint64_t)row * row_bytes; }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { ::emu::yield(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-__device__ __forceinline__ uint4 ld_volatile_u4(const void* p) { uint4 r; memcpy(&r, p, sizeof r); return r; }
+__device__ __forceinline__ void st_word_sys(uint2* p, uint2 v) {
+  __atomic_store_n(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v.x | ((unsigned long long)v.y << 32), __ATOMIC_RELEASE);
+}
+__device__ __forceinline__ uint2 ld_word_sys(const uint2* p) {
+  ::emu::yield();
+  const unsigned long long w = __atomic_load_n(reinterpret_cast<const unsigned long long*>(p), __ATOMIC_ACQUIRE);
+  return make_uint2((unsigned)w, (unsigned)(w >> 32));
+}
 #else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ __half ldcg_half(const __half* p) {
@@ -90,19 +95,14 @@ __device__ __forceinline__ uint64_t row_address(uint64_t base, uint32_t row, uin
   asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(row), "r"(row_bytes), "l"(base));
   return a;
 }
-// system-scope flag traffic of the fused TP exchange (TP instantiations)
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// the fused TP exchange's 8-byte {data, epoch} words (TP instantiations): one store / one load each, never split
+__device__ __forceinline__ void st_word_sys(uint2* p, uint2 v) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_word_sys(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ uint4 ld_volatile_u4(const void* p) {
-  uint4 r;
-  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-  return r;
 }
 #endif
 
@@ -339,56 +339,44 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
       *reinterpret_cast<uint2*>(p.y + col0 + c) = o;
     }
   } else if constexpr (TP) {
-    // ---- fused TP exchange of this column tile ----------------------------------------------------------------------
+    // ---- fused TP exchange of this column tile (push, 8-byte {2 x fp16, epoch} words: see TpFuse) --------------------
     const int y0 = sg.y_col0 + col0;
     const TpFuse& tp = p.tp;
-    __half* mine = tp.part[tp.rank];
-    for (int c = tid * 4; c < wcols; c += NT * 4) {  // 1. my fp16 partial -> my peer-mapped buffer
-      const float4 a = ld_cg_f4(p.acc + acc0 + c);
-      st_cg_f4(p.acc + acc0 + c, make_float4(0.f, 0.f, 0.f, 0.f));
-      const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-      uint2 o;
-      o.x = *reinterpret_cast<const uint32_t*>(&h0);
-      o.y = *reinterpret_cast<const uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(mine + y0 + c) = o;
+    const unsigned e = tp.epoch[cidx] + 1u;
+    for (int c = tid * 2; c < wcols; c += NT * 2) {  // 1. my partial of the tile -> every rank's slot for me
+      float2 a;
+      a.x = __ldcg(p.acc + acc0 + c);
+      a.y = __ldcg(p.acc + acc0 + c + 1);
+      __stcg(p.acc + acc0 + c, 0.f);
+      __stcg(p.acc + acc0 + c + 1, 0.f);
+      const __half2 h = __floats2half2_rn(a.x, a.y);
+      const uint2 word = make_uint2(*reinterpret_cast<const uint32_t*>(&h), e);
+      const size_t slot = ((size_t)tp.rank * tp.n + y0 + c) >> 1;
+      for (int q = 0; q < tp.world; ++q) st_word_sys(tp.recv[q] + slot, word);
     }
-    __syncthreads();  // the partial's stores happen-before the publishing threads' system-scope release
-    if (tid < tp.world) {  // 2. one thread per peer: tell it, then wait for its partial of the same tile
-      const unsigned e = tp.epoch[cidx] + 1u;
-      __threadfence_system();
-      st_release_sys(tp.flags[tid] + tp.rank * kSsqParts + cidx, e);
-      const unsigned* theirs = tp.flags[tp.rank] + tid * kSsqParts + cidx;
-      const long long t0 = clock64();
-      while ((int)(ld_acquire_sys(theirs) - e) < 0) {
-        if (clock64() - t0 > 4000000000ll) __trap();  // a missing peer traps instead of hanging the GPU
-      }
-    }
-    __syncthreads();
-    if (tid == 0) tp.epoch[cidx] += 1u;
-    for (int c = tid * 8; c < wcols; c += NT * 8) {  // 3. sum in rank order (replicas bit-identical), + residual
-      float a[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (int c = tid * 2; c < wcols; c += NT * 2) {  // 2. the same column pairs of every source, in rank order
+      float2 a = make_float2(0.f, 0.f);
       for (int r = 0; r < tp.world; ++r) {
-        const uint4 v = ld_volatile_u4(tp.part[r] + y0 + c);
-        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h2[j]);
-          a[2 * j] += f.x;
-          a[2 * j + 1] += f.y;
+        const uint2* src = tp.recv[tp.rank] + (((size_t)r * tp.n + y0 + c) >> 1);
+        uint2 w = ld_word_sys(src);
+        if (w.y != e) {
+          const long long t0 = clock64();
+          while ((w = ld_word_sys(src)).y != e) {
+            if (clock64() - t0 > 4000000000ll) __trap();  // a missing peer traps instead of hanging the GPU
+          }
         }
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+        a.x += f.x;
+        a.y += f.y;
       }
-      uint4 xv = *reinterpret_cast<const uint4*>(p.resid + y0 + c);
-      __half2* x2 = reinterpret_cast<__half2*>(&xv);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        x2[j] = __hadd2(x2[j], __floats2half2_rn(a[2 * j], a[2 * j + 1]));  // y rounds to fp16, then the fp16 residual add
-        const float2 f = __half22float2(x2[j]);
-        ssq = fmaf(f.x, f.x, fmaf(f.y, f.y, ssq));
-      }
-      *reinterpret_cast<uint4*>(p.y + y0 + c) = xv;
+      __half2 xv = *reinterpret_cast<const __half2*>(p.resid + y0 + c);
+      xv = __hadd2(xv, __floats2half2_rn(a.x, a.y));  // y rounds to fp16, then the fp16 residual add
+      *reinterpret_cast<__half2*>(p.y + y0 + c) = xv;
+      const float2 f = __half22float2(xv);
+      ssq = fmaf(f.x, f.x, fmaf(f.y, f.y, ssq));
     }
+    __syncthreads();  // every thread has read the epoch
+    if (tid == 0) tp.epoch[cidx] = e;
   } else {
     const int y0 = sg.y_col0 + col0;
     for (int c = tid * 4; c < wcols; c += NT * 4) {
@@ -622,14 +610,13 @@ int launch_sparse_gemv(const GemvParams& gp, void* workspace, size_t ws_bytes, i
 
   void (*kern)(const KParams) = var.kern;
   if (gp.tp) {  // row-parallel projection with the TP exchange fused into the tile finaliser
-    if (gp.mode != kModePlain || gp.out_mode != kOutAddResidual || gp.nseg != 1 || (gp.seg[0].ncols & 7) || (reinterpret_cast<uintptr_t>(gp.y) & 15) ||
-        (reinterpret_cast<uintptr_t>(gp.resid) & 15))
-      return set_error(TEAL_ERR_BAD_ARG, "fused TP exchange: one region, residual output, 16-byte aligned vectors");
+    if (gp.mode != kModePlain || gp.out_mode != kOutAddResidual || gp.nseg != 1 || (gp.seg[0].ncols & 7))
+      return set_error(TEAL_ERR_BAD_ARG, "fused TP exchange: one region, residual output");
     if (gp.tp->world < 1 || gp.tp->world > kMaxTpWorld || gp.tp->rank < 0 || gp.tp->rank >= gp.tp->world || !gp.tp->epoch ||
-        gp.tp->world > var.warps * 32 || ctile0 > kSsqParts)
-      return set_error(TEAL_ERR_BAD_ARG, "fused TP exchange: bad rank / world / tile count");
+        ctile0 > kSsqParts || gp.tp->n != gp.seg[0].ncols || (gp.tp->n & 1))
+      return set_error(TEAL_ERR_BAD_ARG, "fused TP exchange: bad rank / world / tile count / row length");
     for (int r = 0; r < gp.tp->world; ++r)
-      if (!gp.tp->part[r] || !gp.tp->flags[r] || (reinterpret_cast<uintptr_t>(gp.tp->part[r]) & 15))
+      if (!gp.tp->recv[r] || (reinterpret_cast<uintptr_t>(gp.tp->recv[r]) & 7))
         return set_error(TEAL_ERR_ALIGNMENT, "fused TP exchange: null / unaligned peer pointer");
     p.tp = *gp.tp;
     kern = var.kern_tp;

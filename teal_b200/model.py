@@ -174,8 +174,8 @@ class SparseDecoder:
     # ------------------------------------------------------------------ TP exchange buffers
     def _setup_peer_exchange(self):
         """Symmetric (peer-mapped) memory for the TP exchange step: two fp16 partial buffers [dim] + a flag array per rank.
-        TEAL_TP_ALLREDUCE = gemv (default: the exchange fused into the row-parallel GEMV's tile finalisers) | fused (one-shot
-        peer-memory kernel after a plain GEMV) | nccl (ncclAllReduce + residual add).  Every rank first agrees on what
+        TEAL_TP_ALLREDUCE = gemv (default: the exchange fused into the row-parallel GEMV's tile finalisers, push protocol) |
+        fused (one-shot peer-memory kernel after a plain GEMV) | nccl (ncclAllReduce + residual add).  Every rank first agrees on what
         is available (all_reduce MIN) and only then enters the collective rendezvous, so a rank-local failure (import,
         environment) falls back to NCCL on all ranks together instead of hanging the others inside rendezvous."""
         import ctypes
@@ -215,14 +215,14 @@ class SparseDecoder:
             self.tp_flags = (ctypes.c_void_p * ws)(*[p + 4 * dim for p in ptrs])
             self.tp_part = [t[par * dim * 2:(par + 1) * dim * 2].view(torch.float16).view(1, 1, dim) for par in (0, 1)]
             self.tp_epoch = torch.zeros(1, dtype=torch.int32, device=self.dev)
-            if want == 2:  # per parity a flag array [world * 64] per rank, local epochs [64]
-                t2 = symm.empty(2 * ws * 64 * 4, dtype=torch.uint8, device=self.dev)
+            if want == 2:  # per parity a receive buffer [world sources][dim / 2] 8-byte words per rank, local epochs [64]
+                t2 = symm.empty(2 * ws * dim * 4, dtype=torch.uint8, device=self.dev)
                 t2.zero_()
                 hdl2 = symm.rendezvous(t2, pg)
                 p2 = [int(p) for p in hdl2.buffer_ptrs]
                 assert len(p2) == ws and all(p2)
                 self._symm2 = (t2, hdl2)
-                self.tp_tile_flags = [(ctypes.c_void_p * ws)(*[p + par * ws * 64 * 4 for p in p2]) for par in (0, 1)]
+                self.tp_recv = [(ctypes.c_void_p * ws)(*[p + par * ws * dim * 4 for p in p2]) for par in (0, 1)]
                 self.tp_tile_epochs = [torch.zeros(64, dtype=torch.int32, device=self.dev) for _ in (0, 1)]
         except Exception as e:  # noqa: BLE001
             ok, self._symm_error = 0, repr(e)
@@ -424,7 +424,7 @@ class SparseDecoder:
                                                           wsp, wsn, sp), "o_proj")
                 elif self.tp_fused and getattr(self, "tp_gemv", False):  # GEMV + exchange + residual + ssq in one kernel (opt-in)
                     chk(lib.teal_sparse_gemv_tp_exchange_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), ssq, self.dim_l, a.dim,
-                                                             W["wo"].stride(1), t["o"], self.tp_bufs[0], self.tp_tile_flags[0],
+                                                             W["wo"].stride(1), t["o"], self.tp_recv[0],
                                                              self.tp_tile_epochs[0].data_ptr(), self.rank, self.world, wsp, wsn, sp), "o_proj+exchange")
                 else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
                     dst = self.tp_part[0] if self.tp_fused else self.part
@@ -448,7 +448,7 @@ class SparseDecoder:
                                                       t["down"], wsp, wsn, sp), "down_proj")
             elif self.tp_fused and getattr(self, "tp_gemv", False):
                 chk(lib.teal_sparse_gemv_tp_exchange_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(), ssq, self.inter_l, a.dim,
-                                                         W["w2"].stride(1), t["down"], self.tp_bufs[1], self.tp_tile_flags[1],
+                                                         W["w2"].stride(1), t["down"], self.tp_recv[1],
                                                          self.tp_tile_epochs[1].data_ptr(), self.rank, self.world, wsp, wsn, sp), "down_proj+exchange")
             else:
                 dst = self.tp_part[1] if self.tp_fused else self.part

@@ -229,6 +229,7 @@ inline long long min(long long a, int b) { return a < b ? a : b; }
 inline long long max(long long a, int b) { return a > b ? a : b; }
 
 // ---- memory ----------------------------------------------------------------------------------------------------
+template <class T> inline void __stcg(T* p, T v) { *reinterpret_cast<volatile T*>(p) = v; }
 template <class T> inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 template <> inline uint2 __ldcg<uint2>(const uint2* p) { uint2 r; memcpy(&r, p, sizeof r); return r; }
 template <> inline uint4 __ldcg<uint4>(const uint4* p) { uint4 r; memcpy(&r, p, sizeof r); return r; }

