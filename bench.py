@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--top-k", type=int, default=0, help="with --temperature: sample like the reference's generate.py default "
                     "(--temperature 0.8 --top-k 200) instead of greedy arg-max in the HEADLINE number")
     ap.add_argument("--temperature", type=float, default=0.0)
-    ap.add_argument("--tp70b", action="store_true", help="add the Llama-2-70B leg (tp_70b object) at this world size")
+    ap.add_argument("--no-70b", action="store_true", help="skip the Llama-2-70B leg (tp_70b object; north_star's TP target, 137 GB / N per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -406,18 +406,41 @@ def main():
               "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),
               "timing": "CUDA events on the launching stream, graph of n_layer launches, each layer on its own weights and its own real decode input (L2 defeated)"}
 
-    # ------------------------------------------------------------------ Llama-2-70B leg (north_star's TP target; opt-in: 137 GB at N = 1)
+    # ------------------------------------------------------------------ Llama-2-70B leg (north_star's TP target)
+    # The same step on the 70B shapes at this world size (137 GB / N of weights per GPU), reported next to the headline
+    # metric, never instead of it: {tok_s, ms_per_step, dense_tok_s}.  Skipped when the GPU cannot hold the shard.
     tp70 = None
-    if args.tp70b and args.workload != "llama-2-70b":
+    if not args.no_70b and not args.no_extra and args.workload != "llama-2-70b":
+        import gc
+        headline_kernels = kernels_per_step
+        try:
+            g = gate_up_all = ffn_in = None  # (the roofline graph keeps the 8B weights alive)
+        except Exception:
+            pass
+        dec.graph = None
         del dec
+        gc.collect()
         torch.cuda.empty_cache()
         m70 = ModelArgs.from_name("70B")
-        d70, _ = build(m70, args.sparsity)
-        k70 = max(8, K // 4)
-        ms70 = timed(d70, "sparse", k70, 3)
-        dn70 = None if args.no_dense else 1e3 / timed(d70, "dense_own", k70, 3)
-        tp70 = {"workload": "llama-2-70b", "tok_s": 1e3 / ms70, "ms_per_step": ms70, "dense_tok_s": dn70, "steps": k70, "n_gpus": world}
-        dec = d70
+        need = 2 * (m70.n_layer * (m70.dim * (m70.dim + 2 * m70.n_local_heads * m70.head_dim) + m70.dim * m70.dim
+                                   + 3 * m70.dim * m70.intermediate_size) / world + 2 * m70.vocab_size * m70.dim) + (4 << 30)
+        free = torch.tensor([torch.cuda.mem_get_info()[0]], device=f"cuda:{local_rank}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(free, op=dist.ReduceOp.MIN)
+        if float(free) < need:
+            tp70 = {"skipped": f"needs {need / 2**30:.0f} GiB per GPU, {float(free) / 2**30:.0f} GiB free"}
+        else:
+            try:
+                d70, _ = build(m70, args.sparsity)
+                k70 = max(16, K // 4)
+                ms70 = timed(d70, "sparse", k70, 3)
+                dn70 = None if args.no_dense else 1e3 / timed(d70, "dense_own", k70, 3)
+                tp70 = {"workload": "llama-2-70b full decode step", "tok_s": 1e3 / ms70, "ms_per_step": ms70, "dense_tok_s": dn70,
+                        "speedup_vs_dense": (1e3 / ms70 / dn70) if dn70 else None, "steps": k70, "n_gpus": world}
+                del d70
+            except Exception as e:  # noqa: BLE001 -- the headline line must survive this leg
+                tp70 = {"error": repr(e)[:200]}
+        kernels_per_step = headline_kernels
 
     cpu = None
     if rank == 0 and not args.no_cpu:
