@@ -31,15 +31,32 @@ _MAX_OUT_COLS = 1 << 17
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
+_alloc_streams: Dict[int, "torch.cuda.Stream"] = {}
+_ws_pools: Dict[int, list] = {}   # device -> free workspace slots (allocated 8 at a time)
+_WS_SLOTS = 8
+
+
 def workspace(device: torch.device, stream_ptr: int) -> torch.Tensor:
-    """Per (device, stream) accumulator/counter workspace; zeroed once, kernels keep it zeroed."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
+    """Per (device, stream) accumulator/counter workspace; zeroed once, kernels keep it zeroed.
+    Slots come from a small per-device pool that is allocated 8 at a time on a private side stream: a stream that shows up
+    for the first time INSIDE a CUDA-graph capture (torch.compile(mode="reduce-overhead") records on its own stream after
+    an eager warm-up) takes a ready slot without allocating, and allocations made while another stream is current are not
+    redirected into a graph memory pool (cudagraph trees insist that every live tensor of their pool is a graph output)."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, stream_ptr)
     ws = _workspaces.get(key)
     if ws is None:
-        lib = _lib.load()
-        nbytes = lib.teal_workspace_bytes(_MAX_OUT_COLS)
-        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+        pool = _ws_pools.setdefault(dev, [])
+        if not pool:
+            nbytes = (_lib.load().teal_workspace_bytes(_MAX_OUT_COLS) + 255) // 256 * 256
+            side = _alloc_streams.get(dev)
+            if side is None:
+                side = _alloc_streams[dev] = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                block = torch.zeros(_WS_SLOTS * nbytes, dtype=torch.uint8, device=device)
+            side.synchronize()
+            pool.extend(block[i * nbytes:(i + 1) * nbytes] for i in range(_WS_SLOTS))
+        ws = _workspaces[key] = pool.pop()
     return ws
 
 
