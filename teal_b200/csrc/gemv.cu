@@ -588,8 +588,9 @@ int launch_sparse_gemv(const GemvParams& gp, void* workspace, size_t ws_bytes, i
   if (gp.ssq_out && ctile0 > kSsqParts) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out: more column tiles than TEAL_SSQ_PARTS");
 
   // K chunk: as many CTAs as fit in ONE wave of resident CTAs, never less than one 32-lane group per warp -- measured on
-  // B200 (profiles/r02_quick_ab_gen5c.jsonl, r02_quick_ab_new.jsonl): a second wave starts with the chip already streaming
-  // and ends with a partly idle one; inside one wave, more (shorter) CTAs beat fewer (longer) ones.
+  // B200 (profiles/r02_quick_ab_wave_fraction.jsonl: grid = 50 / 70 / 90 / 100 / 120 / 150 / 200 % of the slots gives 466 / 497 /
+  // 520 / 521 / 464 / 484 / 494 tok/s): a second wave starts with the chip already streaming and ends with a partly idle
+  // one; inside one wave, more (shorter) CTAs beat fewer (longer) ones.
   int lpw = ctx.lanes_per_warp;
   if (lpw <= 0) {
     const DeviceInfo& di = device_info();
