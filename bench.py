@@ -372,8 +372,12 @@ def main():
                                                      dec.stream.cuda_stream)
             gate_up_all()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=dec.stream):
-                gate_up_all()
+            lib.teal_set_pdl(1)  # launched as in the decode step's graph: programmatic dependent launch, each launch still
+            try:                 # waits (griddepcontrol.wait) for the previous grid to complete before it reads anything
+                with torch.cuda.graph(g, stream=dec.stream):
+                    gate_up_all()
+            finally:
+                lib.teal_set_pdl(0)
             lib.teal_set_bytes_probe(probe.data_ptr())
             gate_up_all()
             dec.stream.synchronize()
@@ -404,7 +408,7 @@ def main():
               "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": traffic, "traffic_source": traffic_src,
               "peak_kind": f"of {peak_kind}", "us_per_launch": us, "alg_bytes_per_launch": alg,
               "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),
-              "timing": "CUDA events on the launching stream, graph of n_layer launches, each layer on its own weights and its own real decode input (L2 defeated)"}
+              "timing": "CUDA events on the launching stream, graph of n_layer PDL launches (as in the decode step), each layer on its own weights and its own real decode input (L2 defeated)"}
 
     # ------------------------------------------------------------------ Llama-2-70B leg (north_star's TP target)
     # The same step on the 70B shapes at this world size (137 GB / N of weights per GPU), reported next to the headline
