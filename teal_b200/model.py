@@ -104,18 +104,13 @@ def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
 
 
 def build_histogram(values: torch.Tensor, num_bins: int = 10000, outlier: float = 0.01):
-    """Histogram in the reference's format (utils/utils.py:145-173: fp32 counts + bin centres,
-    1% / 99% outliers clipped into the two edge bins)."""
-    v = values.flatten().float().cpu().sort().values
-    n = v.numel()
-    lo, hi = v[int(n * outlier)], v[min(n - 1, int(n * (1 - outlier)))]
-    inner = v[(v >= lo) & (v <= hi)]
-    counts = torch.histc(inner, bins=num_bins - 2, min=float(lo), max=float(hi))
-    width = (hi - lo) / (num_bins - 2)
-    centers = lo + width * (torch.arange(num_bins - 2) + 0.5)
-    counts = torch.cat([torch.tensor([float((v < lo).sum())]), counts, torch.tensor([float((v > hi).sum())])])
-    centers = torch.cat([torch.tensor([float(v[0])]), centers, torch.tensor([float(v[-1])])])
-    return centers.float().numpy(), counts.float().numpy()
+    """Histogram in the reference's format (utils/utils.py:145-173: fp32 counts + bin centres, 1 % / 99 % outliers
+    clipped into the two edge bins), computed ON THE DEVICE the activations live on (`calibration.find_histogram`: one
+    sort + one searchsorted; bit-identical to the reference's histograms, tests/golden/histogram.npz).
+    Returns (centers, counts) as numpy arrays for `Distribution`."""
+    from .calibration import find_histogram
+    counts, centers = find_histogram(values, num_bins, outlier)
+    return centers.float().cpu().numpy(), counts.float().cpu().numpy()
 
 
 class SparseDecoder:
@@ -398,13 +393,13 @@ class SparseDecoder:
                                                       W["wqkv"].stride(1), self.kv_l, t["q"], t["k"], t["v"], wsp, wsn, sp),
                     "norm_qkv")
                 if tap is not None:
-                    tap["attn_h1"].append(xn_out.flatten().float().cpu())
+                    tap["attn_h1"].append(xn_out.flatten().float())              # (activations stay on the device: the
             if True:  # attention block: RoPE + KV append + attention, then the o projection
                 chk(lib.teal_attn_decode_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
                                              self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
                                              self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
                 if tap is not None:
-                    tap["attn_h2"].append(self.att.flatten().float().cpu())
+                    tap["attn_h2"].append(self.att.flatten().float())            #  histograms are built there too)
                 n_launch += 2
                 if mode == "dense_cublas":
                     torch.matmul(self.att, W["wo"].T, out=self.part)
@@ -440,8 +435,8 @@ class SparseDecoder:
                                                  W["w1"].stride(1), W["w3"].stride(1), t["gate"], t["up"], wsp, wsn, sp),
                 "gate_up")
             if tap is not None:
-                tap["mlp_h1"].append(xn_out.flatten().float().cpu())
-                tap["mlp_h2"].append(self.h.flatten().float().cpu())
+                tap["mlp_h1"].append(xn_out.flatten().float())
+                tap["mlp_h2"].append(self.h.flatten().float())
             if self.world == 1 and not self.force_tp_path:
                 chk(lib.teal_sparse_gemv_residual_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(),
                                                       self.x.data_ptr(), ssq, self.inter_l, a.dim, W["w2"].stride(1),
@@ -509,16 +504,45 @@ class SparseDecoder:
         self.graph.replay()
         self.steps_enqueued += 1
 
-    def generate(self, first_token: int, n_new: int, mode: str = "sparse") -> torch.Tensor:
+    def prefill(self, prompt, mode: str = "dense_own") -> None:
+        """Feed a prompt (gpt-fast/generate.py:68-71: `prefill`).  The reference runs the prompt through the DENSE branch of
+        the ops (S > 1 -> `x @ W.T`, no sparsification: kernels/sparse_gemv.py:271,298); here the prompt tokens go through
+        the same decode step one position at a time with nothing dropped (`dense_own`), which is that computation up to
+        fp16 summation order, fills the KV cache, and leaves the token sampled after the last prompt position in
+        `self.token`.  The benchmark context is short (generate.py:171), so the prompt is not a throughput path."""
+        toks = [int(t) for t in (prompt.tolist() if hasattr(prompt, "tolist") else prompt)]
+        assert toks, "empty prompt"
+        self.reset(toks[0])
+        self._check_room(len(toks))
+        with torch.cuda.stream(self.stream):
+            ops.workspace(self.dev, self.stream.cuda_stream)
+            for t in toks:
+                self.token.fill_(t)        # teacher forcing: the step's own sample is overwritten by the next prompt token
+                self._enqueue_step(mode)
+        self.stream.synchronize()
+        self.steps_enqueued = len(toks)
+
+    def generate(self, prompt, n_new: int, mode: str = "sparse") -> torch.Tensor:
+        """`prompt`: one token id (decode from it) or a sequence of ids (generate.py:149-217: prefill, then decode).
+        Returns the `n_new` tokens sampled after the prompt's last position."""
         if self.graph is None or self.graph_mode != mode:
             self.capture(mode)
-        self.reset(first_token)
-        self._check_room(n_new)
-        for _ in range(n_new):
+        many = not isinstance(prompt, int)
+        if many and len(prompt) > 1:
+            self.prefill(prompt)           # leaves the first new token in self.token, pos = len(prompt)
+            first = self.token.clone()
+            base = len(prompt)
+            n_rest = n_new - 1
+        else:
+            self.reset(int(prompt[0]) if many else int(prompt))
+            first, base, n_rest = None, 0, n_new
+        self._check_room(n_rest)
+        for _ in range(n_rest):
             self.graph.replay()
-        self.steps_enqueued += n_new
+        self.steps_enqueued += n_rest
         torch.cuda.synchronize()
-        return self.out_tokens[:n_new].clone()
+        out = self.out_tokens[base:base + n_rest].clone()
+        return out if first is None else torch.cat([first.to(out.dtype), out])
 
 
 def _rms_norm(x, w, eps):

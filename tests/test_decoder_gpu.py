@@ -286,3 +286,60 @@ def test_two_decoders_captured_from_two_threads():
         t.join(timeout=300)
     assert not errors, errors
     assert results[0] == want and results[1] == want
+
+
+def test_prefill_then_sparse_decode_matches_reference_semantics():
+    """generate.py:68-92,149-217: the prompt goes through the DENSE branch of the ops (S > 1: kernels/sparse_gemv.py:271,298),
+    then every new token through the sparse kernels.  SparseDecoder.prefill feeds the prompt position by position with
+    nothing dropped; OracleDecoder does the reference's S = 4 dense prefill in one call."""
+    dec, orc = _mk(THR)
+    prompt = [3, 17, 42, 8]
+    dec.prefill(prompt)
+    with torch.no_grad():
+        want = orc.forward(torch.tensor([prompt]), torch.arange(len(prompt)))[:, -1].float().reshape(-1)
+    got = dec.logits.float().cpu().reshape(-1)
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 2e-2 * scale + 2e-2
+    assert int(dec.pos.item()) == len(prompt) and int(dec.token.item()) == int(torch.argmax(dec.logits.reshape(-1)))
+    # the next (sparse) decode step continues from the prefilled cache on both sides
+    t = int(dec.token.item())
+    dec._enqueue_step("sparse")
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = orc.forward(torch.tensor([[t]]), torch.tensor([len(prompt)])).float().reshape(-1)
+    got = dec.logits.float().cpu().reshape(-1)
+    assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2
+    # public API: prompt in, n_new tokens out, the first one being the prefill's sample
+    out = dec.generate(prompt, 6, mode="sparse").cpu().tolist()
+    assert len(out) == 6 and out[0] == t
+
+
+def test_gptfast_checkpoint_file_round_trip(tmp_path):
+    """a gpt-fast `model.pth` whose attention weights are still split (wq / wk / wv, as
+    scripts/convert_hf_checkpoint.py writes them) -> load_checkpoint (mmap, `Attention.load_hook` fusion, model.py:209-214)
+    -> SparseDecoder -> logits of the oracle on the same weights."""
+    from teal_b200.model import ModelArgs, SparseDecoder, load_checkpoint
+    sd = _state_dict(CFG)
+    hd = CFG["dim"] // CFG["n_head"]
+    kv = CFG["n_local_heads"] * hd
+    split = {}
+    for k, v in sd.items():
+        if k.endswith("attention.wqkv.weight"):
+            p = k[: -len("wqkv.weight")]
+            split[p + "wq.weight"], split[p + "wk.weight"], split[p + "wv.weight"] = v.split([CFG["dim"], kv, kv], dim=0)
+        else:
+            split[k] = v
+    path = tmp_path / "model.pth"
+    torch.save({k: v.clone() for k, v in split.items()}, path)
+    dec = SparseDecoder(ModelArgs(**CFG), max_seq=64, state_dict=load_checkpoint(str(path)))
+    dec.set_thresholds(THR)
+    orc = O.OracleDecoder(CFG, sd, THR, max_seq=64)
+    dec.reset(3)
+    for i, t in enumerate([3, 17, 42]):
+        dec.token.fill_(t)
+        dec._enqueue_step("sparse")
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            want = orc.forward(torch.tensor([[t]]), torch.tensor([i])).float().reshape(-1)
+        got = dec.logits.float().cpu().reshape(-1)
+        assert float((got - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2

@@ -35,6 +35,8 @@ def cpu_decoder(monkeypatch):
     monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: _Stream())
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
     monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+    import contextlib
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     ws = torch.zeros(emu.teal_workspace_bytes(1 << 17), dtype=torch.uint8)
     monkeypatch.setattr(ops, "workspace", lambda dev, sp: ws)
 
@@ -111,3 +113,22 @@ def test_calibration_runs_through_the_taps(cpu_decoder):
     dec = cpu_decoder([None] * CFG["n_layer"])
     thr = dec.calibrate(0.5, n_tokens=3)
     assert len(thr) == CFG["n_layer"] and all(v > 0 for t in thr for v in t.values())
+
+
+def test_prefill_is_the_dense_branch(cpu_decoder):
+    """SparseDecoder.prefill: the prompt position by position with nothing dropped == the reference's S > 1 dense prefill
+    (kernels/sparse_gemv.py:271,298), then the sparse decode continues from the filled KV cache."""
+    dec = cpu_decoder(THR)
+    prompt = [3, 17, 42, 8]
+    dec.prefill(prompt)
+    orc = O.OracleDecoder(CFG, _state_dict(CFG), THR, max_seq=64)
+    with torch.no_grad():
+        want = orc.forward(torch.tensor([prompt]), torch.arange(len(prompt)))[:, -1].float().reshape(-1)
+    got = dec.logits.float().reshape(-1)
+    assert float((got - want).abs().max()) <= 2e-2 * float(want.abs().max()) + 2e-2
+    assert int(dec.pos) == len(prompt) and dec.steps_enqueued == len(prompt)
+    t = int(dec.token)
+    dec._enqueue_step("sparse")
+    with torch.no_grad():
+        want = orc.forward(torch.tensor([[t]]), torch.tensor([len(prompt)])).float().reshape(-1)
+    assert float((dec.logits.float().reshape(-1) - want).abs().max()) <= 6e-2 * float(want.abs().max()) + 2e-2
