@@ -358,7 +358,7 @@ def main():
     ffn_in, dec.ffn_inputs = dec.ffn_inputs, None
     barrier()
     if rank == 0:
-        ws = ops.workspace(dec.dev, dec.stream.cuda_stream)
+        ws = dec.ws
         probe.zero_()
         t_l = [t for t in thr]
         nrep = max(1, 96 // a.n_layer)

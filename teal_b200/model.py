@@ -155,6 +155,9 @@ class SparseDecoder:
         self.logits = torch.zeros(1, 1, a.vocab_size, dtype=f16, device=dev)
         self.ssq = torch.zeros(ops.SSQ_FLOATS, dtype=torch.float32, device=dev)  # replicated sum-of-squares partials of the residual stream
         self.stream = torch.cuda.Stream(device=dev)
+        # the decoder's own accumulator / counter workspace (zeroed once, the kernels keep it zeroed): one decoder = one
+        # stream of launches, so it never shares the per-stream slots ops.workspace() hands to ad-hoc op calls
+        self.ws = torch.zeros(self.lib.teal_workspace_bytes(ops._MAX_OUT_COLS), dtype=torch.uint8, device=dev)
         self.tp_fused = False
         if world > 1:
             self._setup_peer_exchange()
@@ -370,8 +373,7 @@ class SparseDecoder:
         'dense_cublas' (projections through torch.matmul like the reference's dense nn.Linear)."""
         a, lib, L = self.args, self.lib, self.layers
         sp = torch.cuda.current_stream().cuda_stream
-        ws = ops.workspace(self.dev, sp)
-        wsp, wsn = ws.data_ptr(), ws.numel()
+        wsp, wsn = self.ws.data_ptr(), self.ws.numel()
         chk = _lib.check
         n_launch = 0
         ssq = self.ssq.data_ptr()
@@ -482,7 +484,6 @@ class SparseDecoder:
         self.lib.teal_set_pdl(1 if (pdl and mode != "dense_cublas") else 0)
         try:
             with torch.cuda.stream(self.stream):
-                ops.workspace(self.dev, self.stream.cuda_stream)
                 saved = (self.token.clone(), self.pos.clone())
                 self._enqueue_step(mode)  # warm-up outside capture (allocations, lazy init)
                 self.stream.synchronize()
@@ -515,7 +516,6 @@ class SparseDecoder:
         self.reset(toks[0])
         self._check_room(len(toks))
         with torch.cuda.stream(self.stream):
-            ops.workspace(self.dev, self.stream.cuda_stream)
             for t in toks:
                 self.token.fill_(t)        # teacher forcing: the step's own sample is overwritten by the next prompt token
                 self._enqueue_step(mode)

@@ -259,6 +259,8 @@ class BaseKernel:
             torch.library.define(qualname, self.schema)
             torch.library.register_fake(qualname, self.meta)
             torch.library.impl(qualname, self.target, func=self.forward)
+        if torch.cuda.is_available():  # model-load time: make sure the workspace slot pool exists before any graph capture /
+            workspace(torch.device("cuda", torch.cuda.current_device()), _stream_ptr())  # torch.compile warm-up can need a slot
 
 
 class SparseGEMV(BaseKernel):

@@ -38,7 +38,7 @@ def cpu_decoder(monkeypatch):
     import contextlib
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     ws = torch.zeros(emu.teal_workspace_bytes(1 << 17), dtype=torch.uint8)
-    monkeypatch.setattr(ops, "workspace", lambda dev, sp: ws)
+    monkeypatch.setattr(ops, "workspace", lambda dev, sp: ws)   # (the decoder allocates its own with torch.zeros: a CPU tensor here)
 
     def make(thresholds, **env):
         for k, v in env.items():
