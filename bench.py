@@ -286,9 +286,10 @@ def main():
 
     dec, thr = build(margs, args.sparsity)
     lib = dec.lib
+    tp_exchange = None  # (reported next to `config`, not inside it: both arms must carry the same `config`)
     if world > 1:
-        config["tp_exchange"] = ("fused into the row-parallel GEMV finalisers" if getattr(dec, "tp_gemv", False) else
-                                 "one-shot peer-memory kernel" if dec.tp_fused else "nccl all-reduce")
+        tp_exchange = ("fused into the row-parallel GEMV finalisers (push protocol over NVLink peer memory)" if getattr(dec, "tp_gemv", False)
+                       else "one-shot peer-memory kernel" if dec.tp_fused else "nccl all-reduce")
     if args.temperature > 0:
         dec.set_sampling(args.temperature, args.top_k, seed=0)
         config["sampling"] = f"top_k={args.top_k} temperature={args.temperature} (generate.py:49-66 on device)"
@@ -464,7 +465,7 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": rf, "cpu_baseline": cpu,
                 "value_spread": {"tok_s_min": 1e3 / max(reps), "tok_s_max": 1e3 / min(reps), "repeats": len(reps)},
                 "dense_tok_s": dense, "speedup_vs_dense": (tok_s / best_dense) if best_dense else None,
-                "sampled": sampled, "tp_70b": tp70,
+                "sampled": sampled, "tp_70b": tp70, "tp_exchange": tp_exchange,
                 "kept_fraction": gathered / max(1.0, dense_eq),
                 "step_weight_bytes": step_bytes, "step_hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                 "kernels_per_step": kernels_per_step}

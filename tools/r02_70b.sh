@@ -13,7 +13,7 @@ python - <<PY
 import json
 try:
     r=json.loads([l for l in open("gpurun_out/r02_tp${N}_bench_llama-2-70b.json") if l.startswith("{")][-1])
-    print("tok/s", round(r["value"],1), "e2e", round(r["e2e"]["value"],1), r["config"].get("tp_exchange"), "dense", r.get("dense_tok_s"), "spread", r.get("value_spread"), "roofline", r.get("roofline") and {k: r["roofline"][k] for k in ("frac","us_per_launch")}, "step_hbm_frac", r.get("step_hbm_frac"))
+    print("tok/s", round(r["value"],1), "e2e", round(r["e2e"]["value"],1), r.get("tp_exchange"), "dense", r.get("dense_tok_s"), "spread", r.get("value_spread"), "roofline", r.get("roofline") and {k: r["roofline"][k] for k in ("frac","us_per_launch")}, "step_hbm_frac", r.get("step_hbm_frac"))
 except Exception as e:
     print("no result", e); print(open("gpurun_out/r02_tp${N}_bench_llama-2-70b.err").read()[-1500:])
 PY

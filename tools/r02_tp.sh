@@ -18,7 +18,7 @@ for m in gemv fused nccl; do
 import json
 try:
     r=json.loads([l for l in open("gpurun_out/r02_tp${N}_bench_$m.json") if l.startswith("{")][-1])
-    print("tok/s", round(r["value"],1), "e2e", round(r["e2e"]["value"],1), r["config"].get("tp_exchange"), "kernels/step", r.get("kernels_per_step"), "dense", r.get("dense_tok_s"))
+    print("tok/s", round(r["value"],1), "e2e", round(r["e2e"]["value"],1), r.get("tp_exchange"), "kernels/step", r.get("kernels_per_step"), "dense", r.get("dense_tok_s"))
 except Exception as e:
     print("no result", e); print(open("gpurun_out/r02_tp${N}_bench_$m.err").read()[-1500:])
 PY

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# N-GPU: TP numerics record (fused-in-GEMV exchange) + the default bench line at N
+# usage: tools/r02_tp_n.sh N : TP-N numerics record (exchange fused into the GEMV) + the default bench line (incl. the 70B leg) at N GPUs
 set -u
 mkdir -p gpurun_out
 N=${1:-8}
@@ -12,7 +12,7 @@ python - <<PY
 import json
 try:
     r=json.loads([l for l in open("gpurun_out/r02_tp${N}_bench_default.json") if l.startswith("{")][-1])
-    print("tok/s", round(r["value"],1), "e2e", round(r["e2e"]["value"],1), r["config"].get("tp_exchange"), "dense", r.get("dense_tok_s"), "sampled", r.get("sampled"), "tp_70b", r.get("tp_70b"))
+    print("tok/s", round(r["value"],1), "e2e", round(r["e2e"]["value"],1), r.get("tp_exchange"), "dense", r.get("dense_tok_s"), "sampled", r.get("sampled"), "tp_70b", r.get("tp_70b"))
 except Exception as e:
     print("no result", e); print(open("gpurun_out/r02_tp${N}_bench_default.err").read()[-1500:])
 PY
