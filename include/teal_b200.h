@@ -44,7 +44,7 @@ typedef enum teal_status {
   TEAL_ERR_CUDA = -5         /* CUDA runtime error (message has the cudaError string) */
 } teal_status;
 
-#define TEAL_B200_ABI_VERSION 4
+#define TEAL_B200_ABI_VERSION 5
 #define TEAL_SSQ_PARTS 64    /* partial sums of squares (one per producer column tile, unused tail zero) */
 #define TEAL_SSQ_REPLICAS 32 /* identical copies of the partials: ~4000 consumer warps read them at the same instant, one copy
                               * would be a single hot L2 line (measured: 1.4-2 us of every RMSNorm-fused launch) */
@@ -162,9 +162,38 @@ int teal_sample_topk_f16(const void* logits, int V, double temperature, int top_
  * peer_recv[r]: rank r's receive buffer, world * N / 2 eight-byte words = world * N * 4 bytes (peer-mapped, e.g. torch
  * symmetric memory; zero-initialised; HOST array of `world` device pointers); epoch_tiles: local device uint32
  * [TEAL_SSQ_PARTS], zero-initialised.  Consecutive exchanges must alternate between two (recv, epochs) sets. */
-int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
-                                     double threshold, void* const* peer_recv, void* epoch_tiles, int rank, int world,
+int teal_sparse_gemv_tp_exchange_f16(const void* x, const float* gate_up_acc, const void* wt, void* resid_x, float* ssq_out,
+                                     int Z, int N, int64_t ldw, double threshold, float* clear, int clear_n,
+                                     void* const* peer_recv, void* epoch_tiles, int rank, int world, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+   /* (x / gate_up_acc, clear / clear_n: as in teal_sparse_gemv_residual_ex_f16 below) */
+
+/* ---- deferred epilogue (decode step) ------------------------------------------------------------------------------
+ * Attention and the down projection consume a projection's output with no RMSNorm in between, so the producer's tile
+ * finaliser (fence -> arrival counter -> last arrival loads the fp32 sums, rounds, stores fp16, re-zeroes) can be left
+ * out: the producer's CTAs end with their fp32 `red.add` into a caller-owned buffer, and the CONSUMER kernel applies the
+ * same single round-to-nearest (and, for gate / up, fp16(silu(fp16 g)) * fp16 u of gpt-fast/model.py:259) when it loads
+ * its input -- bit-identical values, ~1 us less on the critical path of each of the two launches.  The buffers must be
+ * zero before their producer runs; `clear` on a later launch of the step re-zeroes them once every reader is done (the
+ * o projection clears both: it starts after attention, i.e. after the last reader of q | k | v, and long after the
+ * previous layer's down projection).  No workspace: nothing is counted or finalised.
+ * qkv_acc: fp32 [N]; gate_up_acc: fp32 [2 * I], gate at [0, I), up at [I, 2 I); both 16-byte aligned. */
+int teal_norm_sparse_qkv_gemv_acc_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt,
+                                      float* qkv_acc, int Z, int N, int64_t ldw, int kv_size, double threshold_q,
+                                      double threshold_k, double threshold_v, void* stream);
+int teal_norm_sparse_gate_up_acc_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
+                                     const void* w3t, float* gate_up_acc, int Z, int I, int64_t ldw1, int64_t ldw3,
+                                     double threshold_gate, double threshold_up, void* stream);
+/* teal_attn_decode_f16 reading q | k | v from the fp32 sums of teal_norm_sparse_qkv_gemv_acc_f16. */
+int teal_attn_decode_acc_f16(const float* qkv_acc, const void* freqs_cis, void* k_cache, void* v_cache,
+                             const int32_t* pos, void* out, int n_head, int n_kv_head, int head_dim, int max_seq,
+                             void* stream);
+/* teal_sparse_gemv_residual_f16 whose input is EITHER the fp16 vector x OR (x == NULL) h = silu(gate) * up of
+ * gate_up_acc (Z = I); clear (nullable) / clear_n (multiple of 4): floats this launch zeroes after its producer is done. */
+int teal_sparse_gemv_residual_ex_f16(const void* x, const float* gate_up_acc, const void* wt, const void* resid, void* y,
+                                     float* ssq_out, int Z, int N, int64_t ldw, double threshold, float* clear, int clear_n,
                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Greedy step bookkeeping: *token = arg-max index, out_tokens[*pos] = *token, ++*pos, reset cell. */
 int teal_advance(void* argmax_packed, int32_t* token, int32_t* pos, int32_t* out_tokens, int out_cap,
                  void* stream);

@@ -49,8 +49,21 @@ _SIGS = {
                                                  _c.c_void_p, _c.c_int, _c.c_void_p]),
     "teal_sample_topk_f16": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_int, _c.c_void_p, _c.c_uint64, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p]),
-    "teal_sparse_gemv_tp_exchange_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
-                                                    _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
+    # (x | gate_up_acc, wt, resid_x, ssq_out, Z, N, ldw, thr, clear, clear_n, peers, epochs, rank, world, ws, ws_bytes, stream)
+    "teal_sparse_gemv_tp_exchange_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                                    _c.c_int64, _c.c_double, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                                    _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    # deferred epilogue (include/teal_b200.h): the consumer kernel rounds the producer's fp32 sums
+    "teal_norm_sparse_qkv_gemv_acc_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                     _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_double, _c.c_double, _c.c_double,
+                                                     _c.c_void_p]),
+    "teal_norm_sparse_gate_up_acc_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                    _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _c.c_double, _c.c_double,
+                                                    _c.c_void_p]),
+    "teal_attn_decode_acc_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                            _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "teal_sparse_gemv_residual_ex_f16": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                    _c.c_int, _c.c_int, _c.c_int64, _c.c_double, _c.c_void_p, _c.c_int, _c.c_void_p,
                                                     _c.c_size_t, _c.c_void_p]),
     "teal_advance": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "teal_survivors_f16": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p]),

@@ -107,6 +107,29 @@ int teal_set_debug_timeline(void* device_buf, int slots) {
   return TEAL_OK;
 }
 
+// q | k | v column regions of the fused wqkv matrix (kernels/sparse_gemv.py:212): one region and one survivor list
+// when the three thresholds agree
+static void qkv_regions(GemvParams& p, const void* wt, int N, int64_t ldw, int kv_size, double threshold_q, double threshold_k,
+                        double threshold_v) {
+  const int n_q = N - 2 * kv_size;
+  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k),
+              tv = round_threshold_fp16(threshold_v);
+  const __half* w = reinterpret_cast<const __half*>(wt);
+  if (tq == tk && tk == tv) {
+    p.nseg = 1;
+    p.seg[0] = GemvSeg{w, ldw, N, 0, tq};
+    return;
+  }
+  const int cols[3] = {n_q, kv_size, kv_size};
+  const float thr[3] = {tq, tk, tv};
+  int c0 = 0;
+  for (int r = 0; r < 3; ++r) {
+    if (cols[r] == 0) continue;
+    p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, thr[r]};
+    c0 += cols[r];
+  }
+}
+
 int teal_sparse_gemv_f16(const void* x, const void* wt, void* y, int Z, int N, int64_t ldw, double threshold,
                          void* workspace, size_t workspace_bytes_, void* stream) {
   GemvParams p;
@@ -129,24 +152,8 @@ int teal_sparse_qkv_gemv_f16(const void* x, const void* wt, void* y, int Z, int 
   if (int rc = fill_common(p, x, y, Z)) return rc;
   if (!wt || !y || N <= 0 || ldw < N || kv_size < 0 || 2 * (int64_t)kv_size > N)
     return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / N / ldw / kv_size");
-  const int n_q = N - 2 * kv_size;  // kernels/sparse_gemv.py:212
-  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k),
-              tv = round_threshold_fp16(threshold_v);
   p.mode = kModePlain;
-  const __half* w = reinterpret_cast<const __half*>(wt);
-  if (tq == tk && tk == tv) {  // uniform sparsity: one region, one survivor list
-    p.nseg = 1;
-    p.seg[0] = GemvSeg{w, ldw, N, 0, tq};
-  } else {
-    const int cols[3] = {n_q, kv_size, kv_size};
-    const float thr[3] = {tq, tk, tv};
-    int c0 = 0;
-    for (int r = 0; r < 3; ++r) {
-      if (cols[r] == 0) continue;
-      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, thr[r]};
-      c0 += cols[r];
-    }
-  }
+  qkv_regions(p, wt, N, ldw, kv_size, threshold_q, threshold_k, threshold_v);
   return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -186,26 +193,10 @@ int teal_norm_sparse_qkv_gemv_f16(const void* x, const void* norm_w, double eps,
   if (int rc = fill_common(p, x, y, Z)) return rc;
   if (!wt || !y || !norm_w || N <= 0 || ldw < N || kv_size < 0 || 2 * (int64_t)kv_size > N)
     return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / norm_w / N / ldw / kv_size");
-  const int n_q = N - 2 * kv_size;
-  const float tq = round_threshold_fp16(threshold_q), tk = round_threshold_fp16(threshold_k),
-              tv = round_threshold_fp16(threshold_v);
   p.mode = kModePlain;
   if (int rc = norm_input(p, norm_w, eps, ssq_in, workspace, workspace_bytes_, reinterpret_cast<cudaStream_t>(stream))) return rc;
   p.x_out = reinterpret_cast<__half*>(xn_out);
-  const __half* w = reinterpret_cast<const __half*>(wt);
-  if (tq == tk && tk == tv) {
-    p.nseg = 1;
-    p.seg[0] = GemvSeg{w, ldw, N, 0, tq};
-  } else {
-    const int cols[3] = {n_q, kv_size, kv_size};
-    const float thr[3] = {tq, tk, tv};
-    int c0 = 0;
-    for (int r = 0; r < 3; ++r) {
-      if (cols[r] == 0) continue;
-      p.seg[p.nseg++] = GemvSeg{w + c0, ldw, cols[r], c0, thr[r]};
-      c0 += cols[r];
-    }
-  }
+  qkv_regions(p, wt, N, ldw, kv_size, threshold_q, threshold_k, threshold_v);
   return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -226,11 +217,36 @@ int teal_norm_sparse_gate_up_f16(const void* x, const void* norm_w, double eps, 
   return launch_sparse_gemv(p, workspace, workspace_bytes_, 2 * I, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// x is either the fp16 vector `x` or -- the down projection behind a deferred gate/up launch -- silu(gate) * up of the
+// fp32 sums in `gate_up_acc` (gate at [0, Z), up at [Z, 2Z)); exactly one of the two is given
+static int residual_input(GemvParams& p, const void* x, const float* gate_up_acc, void* y, int Z, float* clear, int clear_n) {
+  memset(&p, 0, sizeof(p));
+  if ((x == nullptr) == (gate_up_acc == nullptr)) return set_error(TEAL_ERR_BAD_ARG, "exactly one of x / gate_up_acc");
+  p.x = reinterpret_cast<const __half*>(x);
+  p.y = reinterpret_cast<__half*>(y);
+  p.Z = Z;
+  if (gate_up_acc) {
+    p.in_mode = kInGateUpAcc;
+    p.in_acc = gate_up_acc;
+    p.in_acc_stride = Z;
+  }
+  p.clear = clear;
+  p.clear_n = clear_n;
+  return TEAL_OK;
+}
+
 int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* resid, void* y, float* ssq_out, int Z,
                                   int N, int64_t ldw, double threshold, void* workspace, size_t workspace_bytes_,
                                   void* stream) {
+  return teal_sparse_gemv_residual_ex_f16(x, nullptr, wt, resid, y, ssq_out, Z, N, ldw, threshold, nullptr, 0, workspace,
+                                          workspace_bytes_, stream);
+}
+
+int teal_sparse_gemv_residual_ex_f16(const void* x, const float* gate_up_acc, const void* wt, const void* resid, void* y,
+                                     float* ssq_out, int Z, int N, int64_t ldw, double threshold, float* clear, int clear_n,
+                                     void* workspace, size_t workspace_bytes_, void* stream) {
   GemvParams p;
-  if (int rc = fill_common(p, x, y, Z)) return rc;
+  if (int rc = residual_input(p, x, gate_up_acc, y, Z, clear, clear_n)) return rc;
   if (!wt || !y || !resid || N <= 0 || ldw < N) return set_error(TEAL_ERR_BAD_ARG, "bad wt / y / resid / N / ldw");
   p.mode = kModePlain;
   p.out_mode = kOutAddResidual;
@@ -241,11 +257,12 @@ int teal_sparse_gemv_residual_f16(const void* x, const void* wt, const void* res
   return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_x, float* ssq_out, int Z, int N, int64_t ldw,
-                                     double threshold, void* const* peer_recv, void* epoch_tiles, int rank, int world,
-                                     void* workspace, size_t workspace_bytes_, void* stream) {
+int teal_sparse_gemv_tp_exchange_f16(const void* x, const float* gate_up_acc, const void* wt, void* resid_x, float* ssq_out,
+                                     int Z, int N, int64_t ldw, double threshold, float* clear, int clear_n,
+                                     void* const* peer_recv, void* epoch_tiles, int rank, int world, void* workspace,
+                                     size_t workspace_bytes_, void* stream) {
   GemvParams p;
-  if (int rc = fill_common(p, x, resid_x, Z)) return rc;
+  if (int rc = residual_input(p, x, gate_up_acc, resid_x, Z, clear, clear_n)) return rc;
   if (!wt || !resid_x || !peer_recv || !epoch_tiles || N <= 0 || ldw < N || world < 1 || world > kMaxTpWorld)
     return set_error(TEAL_ERR_BAD_ARG, "bad wt / resid_x / peers / N / ldw / world");
   TpFuse tp;
@@ -265,6 +282,39 @@ int teal_sparse_gemv_tp_exchange_f16(const void* x, const void* wt, void* resid_
   return launch_sparse_gemv(p, workspace, workspace_bytes_, N, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- deferred epilogue: the producers of the two consumers that have no RMSNorm in front (attention, down) ----------
+int teal_norm_sparse_qkv_gemv_acc_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* wt,
+                                      float* qkv_acc, int Z, int N, int64_t ldw, int kv_size, double threshold_q,
+                                      double threshold_k, double threshold_v, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, nullptr, Z)) return rc;
+  if (!wt || !qkv_acc || !norm_w || !ssq_in || N <= 0 || ldw < N || kv_size < 0 || 2 * (int64_t)kv_size > N)
+    return set_error(TEAL_ERR_BAD_ARG, "bad wt / qkv_acc / norm_w / ssq_in / N / ldw / kv_size");
+  p.mode = kModePlain;
+  p.out_mode = kOutDeferred;
+  p.raw_out = qkv_acc;
+  if (int rc = norm_input(p, norm_w, eps, ssq_in, nullptr, 0, reinterpret_cast<cudaStream_t>(stream))) return rc;
+  qkv_regions(p, wt, N, ldw, kv_size, threshold_q, threshold_k, threshold_v);
+  return launch_sparse_gemv(p, nullptr, 0, N, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int teal_norm_sparse_gate_up_acc_f16(const void* x, const void* norm_w, double eps, const float* ssq_in, const void* w1t,
+                                     const void* w3t, float* gate_up_acc, int Z, int I, int64_t ldw1, int64_t ldw3,
+                                     double threshold_gate, double threshold_up, void* stream) {
+  GemvParams p;
+  if (int rc = fill_common(p, x, nullptr, Z)) return rc;
+  if (!w1t || !w3t || !gate_up_acc || !norm_w || !ssq_in || I <= 0 || ldw1 < I || ldw3 < I)
+    return set_error(TEAL_ERR_BAD_ARG, "bad w1t / w3t / gate_up_acc / norm_w / ssq_in / I / ldw");
+  p.mode = kModePairSilu;
+  p.out_mode = kOutDeferred;
+  p.raw_out = gate_up_acc;
+  if (int rc = norm_input(p, norm_w, eps, ssq_in, nullptr, 0, reinterpret_cast<cudaStream_t>(stream))) return rc;
+  p.nseg = 2;
+  p.seg[0] = GemvSeg{reinterpret_cast<const __half*>(w1t), ldw1, I, 0, round_threshold_fp16(threshold_gate)};
+  p.seg[1] = GemvSeg{reinterpret_cast<const __half*>(w3t), ldw3, I, I, round_threshold_fp16(threshold_up)};
+  return launch_sparse_gemv(p, nullptr, 0, 2 * I, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ---- the rest of the decode step -------------------------------------------------------------------
 int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, float* ssq_out, int dim, void* stream) {
   return launch_embed(reinterpret_cast<const __half*>(tok_embeddings), token, reinterpret_cast<__half*>(x), ssq_out, dim,
@@ -272,7 +322,15 @@ int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, fl
 }
 int teal_attn_decode_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos,
                          void* out, int n_head, int n_kv_head, int head_dim, int max_seq, void* stream) {
-  return launch_attn_decode(reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(freqs_cis),
+  return launch_attn_decode(reinterpret_cast<const __half*>(qkv), nullptr, reinterpret_cast<const __half*>(freqs_cis),
+                            reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), pos,
+                            reinterpret_cast<__half*>(out), n_head, n_kv_head, head_dim, max_seq,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+int teal_attn_decode_acc_f16(const float* qkv_acc, const void* freqs_cis, void* k_cache, void* v_cache, const int32_t* pos,
+                             void* out, int n_head, int n_kv_head, int head_dim, int max_seq, void* stream) {
+  if (!qkv_acc) return set_error(TEAL_ERR_BAD_ARG, "attn_decode_acc: qkv_acc is null");
+  return launch_attn_decode(nullptr, qkv_acc, reinterpret_cast<const __half*>(freqs_cis),
                             reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), pos,
                             reinterpret_cast<__half*>(out), n_head, n_kv_head, head_dim, max_seq,
                             reinterpret_cast<cudaStream_t>(stream));

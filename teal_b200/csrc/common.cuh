@@ -16,8 +16,12 @@ constexpr int kMaxTpWorld = 16;    // ranks of one tensor-parallel group (one NV
 constexpr int kListCap = 512;      // survivor-list entries (= input lanes) one warp may own
 
 enum { kModePlain = 0, kModePairSilu = 1, kModeSurvivors = 2 };
-enum { kInPlain = 0, kInRmsNorm = 1 };        // how x is produced from the input vector
-enum { kOutPlain = 0, kOutAddResidual = 1 };  // what the finaliser adds before writing fp16
+enum { kInPlain = 0, kInRmsNorm = 1, kInGateUpAcc = 2 };  // how x is produced from the input vector
+// what happens to the split-K sums: a tile finaliser writes fp16 (plain / + residual), or -- kOutDeferred -- nobody in this
+// launch does: the fp32 sums stay in the caller's buffer and the CONSUMER kernel rounds them when it loads its input
+// (attention for q | k | v, the down projection for the gate / up pair: consumers with no RMSNorm in front), so the
+// producer's last CTA ends with its RED instead of fence -> arrival -> finaliser -> store.
+enum { kOutPlain = 0, kOutAddResidual = 1, kOutDeferred = 2 };
 
 // Row-parallel GEMV fused with its TP exchange (sparse_gemv_kernel<.., TP = true>), low-latency PUSH protocol: the
 // finaliser of a column tile sends the rank's fp16 partial of that tile straight into every rank's receive buffer as
@@ -49,6 +53,11 @@ struct GemvParams {
   float* ssq_out;           // optional: per-tile sums of squares of y (for the next RMSNorm)
   unsigned char* keep_out;  // optional: keep mask (parity hook)
   const TpFuse* tp;         // optional (host pointer): fuse the TP exchange into the finaliser (row-parallel o / down)
+  const float* in_acc;      // kInGateUpAcc: deferred sums of the gate / up pair, gate at [0, Z), up at [in_acc_stride, +Z)
+  float* raw_out;           // kOutDeferred: fp32 sums are left here (zero on entry; the consumer's successor clears it)
+  float* clear;             // optional: clear_n floats this launch zeroes once its producer is done (deferred buffers
+  int clear_n;              //   whose readers have all completed by then)
+  int in_acc_stride;
   int Z, nseg, mode, in_mode, out_mode, n_ssq_in;
   float eps;
   GemvSeg seg[kMaxSeg];
@@ -72,12 +81,15 @@ struct KParams {
   float* ssq_out;
   __half* x_out;
   unsigned char* keep_out;
-  float* acc;                 // fp32 accumulators (workspace), zero on entry and on exit
+  float* acc;                 // fp32 accumulators (workspace), zero on entry and on exit; kOutDeferred: the caller's buffer
+  const float* in_acc;        // kInGateUpAcc
+  float* clear;               // optional: floats [0, clear_n) zeroed after the wait, clear_per_cta per CTA
   unsigned* counters;         // per-tile arrival counters (workspace), zero on entry and on exit
   unsigned long long* probe;  // optional [2]: gathered / dense weight bytes
   long long* dbg_time;        // TIMED instantiations: [grid][16] globaltimer stamps
   int Z, mode, in_mode, out_mode, nseg;
   int n_ssq_in, rows_per_cta, lanes_per_warp, nkchunks, total_ctiles, target;
+  int in_acc_stride, clear_n, clear_per_cta;
   float eps;
   KSeg seg[kMaxSeg];
   TpFuse tp;  // TP instantiations only
@@ -117,7 +129,7 @@ int launch_mask_to_indices(const unsigned char* keep, int Z, int* idx, int* cnt,
 int launch_simple(const __half* x, const __half* wt, __half* y, int Z, int N, long long ldw, float thr, cudaStream_t stream);
 
 int launch_embed(const __half* emb, const int* token, __half* x, float* ssq_out, int dim, cudaStream_t stream);
-int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,
+int launch_attn_decode(const __half* qkv, const float* qkv_acc, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,
                        __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream);
 int launch_dense_rowmajor(const __half* x, const __half* norm_w, float eps, const __half* W, __half* y,
                           unsigned long long* argmax_packed, int Z, int V, long long ldw, cudaStream_t stream);

@@ -70,6 +70,7 @@ constexpr int kAttnWarps = kAttnThreads / 32;
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
     const __half* __restrict__ qkv,    // [n_head*HD | n_kv*HD | n_kv*HD]
+    const float* __restrict__ qkv_acc, // or (qkv == nullptr): the QKV launch's deferred fp32 sums, rounded to fp16 here
     const __half* __restrict__ freqs,  // [max_seq][HD/2][2] fp16 (cos, sin)
     __half* __restrict__ k_cache,      // [n_kv][max_seq][HD]
     __half* __restrict__ v_cache, const int* __restrict__ pos_ptr, __half* __restrict__ out,  // [n_head*HD]
@@ -89,16 +90,26 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   // ---- q, new k, new v are the producer's output: requested after the wait, together with the position -----------
   griddep_wait();
   griddep_launch_dependents();  // n_head CTAs leave most of the machine free: the o-proj grid moves in and waits for us
-  const __half* qh = qkv + (size_t)h * HD;
-  const __half* kh = qkv + (size_t)n_head * HD + (size_t)kvh * HD;
-  const __half* vh = qkv + (size_t)(n_head + n_kv) * HD + (size_t)kvh * HD;
+  const size_t qo = (size_t)h * HD, ko = (size_t)n_head * HD + (size_t)kvh * HD, vo = (size_t)(n_head + n_kv) * HD + (size_t)kvh * HD;
   __half2 in2 = __halves2half2(__ushort_as_half((unsigned short)0), __ushort_as_half((unsigned short)0));
   __half2 k2 = in2;
-  if (tid < HD / 2) {
-    in2 = reinterpret_cast<const __half2*>(qh)[tid];
-    k2 = reinterpret_cast<const __half2*>(kh)[tid];
-  } else if (tid < HD) {
-    in2 = reinterpret_cast<const __half2*>(vh)[tid - HD / 2];
+  if (qkv) {
+    if (tid < HD / 2) {
+      in2 = reinterpret_cast<const __half2*>(qkv + qo)[tid];
+      k2 = reinterpret_cast<const __half2*>(qkv + ko)[tid];
+    } else if (tid < HD) {
+      in2 = reinterpret_cast<const __half2*>(qkv + vo)[tid - HD / 2];
+    }
+  } else {  // the same fp16 values the QKV tile finaliser would have written (one round-to-nearest of the fp32 sum)
+    if (tid < HD / 2) {
+      const float2 a = __ldcg(reinterpret_cast<const float2*>(qkv_acc + qo) + tid);
+      const float2 b = __ldcg(reinterpret_cast<const float2*>(qkv_acc + ko) + tid);
+      in2 = __floats2half2_rn(a.x, a.y);
+      k2 = __floats2half2_rn(b.x, b.y);
+    } else if (tid < HD) {
+      const float2 a = __ldcg(reinterpret_cast<const float2*>(qkv_acc + vo) + (tid - HD / 2));
+      in2 = __floats2half2_rn(a.x, a.y);
+    }
   }
   const int pos = pos_ptr[0];
   if (pos < 0 || pos >= max_seq) {  // beyond the KV cache / RoPE table (the host raises before this can happen): touch nothing
@@ -614,19 +625,21 @@ int launch_embed(const __half* emb, const int* token, __half* x, float* ssq_out,
   return launch_pdl(embed_kernel, dim3(1), dim3(256), 0, stream, "embed launch", emb, token, x, ssq_out, dim);
 }
 
-int launch_attn_decode(const __half* qkv, const __half* freqs, __half* k_cache, __half* v_cache, const int* pos,
-                       __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream) {
-  if (!qkv || !freqs || !k_cache || !v_cache || !pos || !out || n_head <= 0 || n_kv <= 0 || n_head % n_kv)
+int launch_attn_decode(const __half* qkv, const float* qkv_acc, const __half* freqs, __half* k_cache, __half* v_cache,
+                       const int* pos, __half* out, int n_head, int n_kv, int head_dim, int max_seq, cudaStream_t stream) {
+  if ((qkv == nullptr) == (qkv_acc == nullptr) || (reinterpret_cast<uintptr_t>(qkv_acc) & 7))
+    return set_error(TEAL_ERR_BAD_ARG, "attn_decode: exactly one of qkv (fp16) / qkv_acc (fp32, 8-byte aligned)");
+  if (!freqs || !k_cache || !v_cache || !pos || !out || n_head <= 0 || n_kv <= 0 || n_head % n_kv)
     return set_error(TEAL_ERR_BAD_ARG, "attn_decode: bad argument");
   if ((reinterpret_cast<uintptr_t>(qkv) & 3) || (reinterpret_cast<uintptr_t>(freqs) & 3) || (reinterpret_cast<uintptr_t>(k_cache) & 3) ||
       (reinterpret_cast<uintptr_t>(v_cache) & 3))
     return set_error(TEAL_ERR_ALIGNMENT, "attn_decode: 4-byte aligned vectors");
   const float scale = 1.0f / sqrtf((float)head_dim);
   if (head_dim == 128)
-    return launch_pdl(attn_decode_kernel<128>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, freqs,
+    return launch_pdl(attn_decode_kernel<128>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, qkv_acc, freqs,
                       k_cache, v_cache, pos, out, n_head, n_kv, max_seq, scale);
   if (head_dim == 64)
-    return launch_pdl(attn_decode_kernel<64>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, freqs,
+    return launch_pdl(attn_decode_kernel<64>, dim3(n_head), dim3(kAttnThreads), 0, stream, "attn launch", qkv, qkv_acc, freqs,
                       k_cache, v_cache, pos, out, n_head, n_kv, max_seq, scale);
   return set_error(TEAL_ERR_UNSUPPORTED, "attn_decode: head_dim must be 64 or 128");
 }

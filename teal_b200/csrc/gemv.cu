@@ -211,6 +211,20 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
       xh[q] = (k < ke) ? ldcg_half(p.x + k) : __ushort_as_half((unsigned short)0);
     }
   };
+  // kInGateUpAcc: the lanes are h = silu(gate) * up of the producer's deferred fp32 sums (gpt-fast/model.py:259), rounded
+  // exactly as the pair finaliser rounds them; all requests of a pass in flight before the first is used
+  auto load_x_gate_up = [&](int q0) {
+    float g[kPass], u[kPass];
+#pragma unroll
+    for (int q = 0; q < kPass; ++q) {
+      const int k = kb + (q0 + q) * 32 + lane;
+      g[q] = (k < ke) ? __ldcg(p.in_acc + k) : 0.f;
+      u[q] = (k < ke) ? __ldcg(p.in_acc + p.in_acc_stride + k) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < kPass; ++q) xh[q] = silu_mul_f16(g[q], u[q]);
+  };
+  const bool from_gate_up = p.in_mode == kInGateUpAcc;
   load_nw(0);
   if (rms && kb + kPass * 32 + lane * 64 < ke) prefetch_l2(p.norm_w + kb + kPass * 32 + lane * 64);
 
@@ -219,7 +233,11 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
   stamp(1);
 
   // ---- x lanes and the producer's sum-of-squares partials: all requests of the first pass in flight together ------
-  load_x(0);
+  if (from_gate_up) load_x_gate_up(0); else load_x(0);
+  if (p.clear) {  // deferred buffers whose readers finished with the producer we just waited for: my slice back to zero
+    const int c1 = min(p.clear_n, (int)(blockIdx.x + 1) * p.clear_per_cta);
+    for (int c = (int)blockIdx.x * p.clear_per_cta + tid * 4; c < c1; c += NT * 4) st_cg_f4(p.clear + c, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
   float rs = 1.f;
   if (rms) {  // gpt-fast/model.py:286-291
     float t = 0.f;
@@ -239,7 +257,10 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
   int n = 0;
   const int ngroups = (ke - kb + 31) >> 5;
   for (int q0 = 0; q0 < ngroups; q0 += kPass) {
-    if (q0 > 0) { load_nw(q0); load_x(q0); }
+    if (q0 > 0) {
+      load_nw(q0);
+      if (from_gate_up) load_x_gate_up(q0); else load_x(q0);
+    }
 #pragma unroll
     for (int q = 0; q < kPass; ++q) {
       if (q0 + q < ngroups) {  // warp-uniform
@@ -296,6 +317,10 @@ __global__ void __launch_bounds__(WARPS * 32, 28 / WARPS) sparse_gemv_kernel(con
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f) red_add_v4(p.acc + acc0 + c, a);
+  }
+  if (p.out_mode == kOutDeferred) {  // the consumer kernel rounds the sums (grid completion makes them visible to it)
+    stamp(5);
+    return;
   }
   // ---- arrival counter: the REDs of all threads happen-before the barrier, thread 0's release fence is cumulative
   // over them; the last arrival acquires and finalises the tile ------------------------------------------------------
@@ -544,12 +569,24 @@ int launch_sparse_gemv(const GemvParams& gp, void* workspace, size_t ws_bytes, i
   p.probe = ctx.probe;
   p.Z = gp.Z; p.mode = gp.mode; p.in_mode = gp.in_mode; p.out_mode = gp.out_mode; p.eps = gp.eps;
   p.nseg = gp.nseg;
-  if (gp.mode != kModeSurvivors) {
+  const bool deferred = gp.out_mode == kOutDeferred;
+  if (deferred) {
+    if (!gp.raw_out || (reinterpret_cast<uintptr_t>(gp.raw_out) & 15) || gp.ssq_out || gp.tp || gp.mode == kModeSurvivors)
+      return set_error(TEAL_ERR_BAD_ARG, "deferred output: a 16-byte aligned fp32 buffer, no ssq_out, no TP exchange");
+    p.acc = gp.raw_out;
+  } else if (gp.mode != kModeSurvivors) {
     if (!workspace || ws_bytes < workspace_bytes(out_cols_total)) return set_error(TEAL_ERR_WORKSPACE, "workspace too small");
     if ((reinterpret_cast<uintptr_t>(gp.y) & 7)) return set_error(TEAL_ERR_ALIGNMENT, "y must be 8-byte aligned");
     p.counters = reinterpret_cast<unsigned*>(workspace);
     p.acc = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)kMaxCounters * 4);
   }
+  if (gp.in_mode == kInGateUpAcc) {
+    if (!gp.in_acc || gp.in_acc_stride < gp.Z) return set_error(TEAL_ERR_BAD_ARG, "gate/up accumulator input: null / stride < Z");
+    p.in_acc = gp.in_acc;
+    p.in_acc_stride = gp.in_acc_stride;
+  }
+  if (gp.clear_n < 0 || (gp.clear_n > 0 && (!gp.clear || (gp.clear_n & 3) || (reinterpret_cast<uintptr_t>(gp.clear) & 15))))
+    return set_error(TEAL_ERR_ALIGNMENT, "clear range: 16-byte aligned, a multiple of 4 floats");
   if (gp.in_mode == kInRmsNorm && (!gp.norm_w || !gp.ssq_in || gp.n_ssq_in != kSsqParts))
     return set_error(TEAL_ERR_BAD_ARG, "RMSNorm mode needs norm_w and the producer's sum-of-squares partials");
   if (gp.ssq_out && gp.mode == kModePairSilu) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out is not defined for the gate/up pair");
@@ -608,6 +645,11 @@ int launch_sparse_gemv(const GemvParams& gp, void* workspace, size_t ws_bytes, i
   p.target = pair ? 2 * p.nkchunks : p.nkchunks;
   const long long grid = (long long)p.total_ctiles * p.nkchunks;
   if (grid > 0x7fffffffll) return set_error(TEAL_ERR_UNSUPPORTED, "grid too large");
+  if (gp.clear_n > 0) {
+    p.clear = gp.clear;
+    p.clear_n = gp.clear_n;
+    p.clear_per_cta = (int)((((long long)gp.clear_n + grid - 1) / grid + 3) & ~3ll);
+  }
 
   void (*kern)(const KParams) = var.kern;
   if (gp.tp) {  // row-parallel projection with the TP exchange fused into the tile finaliser

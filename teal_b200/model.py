@@ -22,6 +22,8 @@ from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import numpy as np
+import threading
+
 import torch
 
 from . import _lib, ops
@@ -165,6 +167,12 @@ class SparseDecoder:
         self.graph_mode = None
         self.taps = None  # calibration taps
         self.force_tp_path = False  # tests: take the (plain GEMV -> all-reduce -> residual_add) route at world == 1
+        # Deferred epilogue (include/teal_b200.h): the QKV and gate/up launches leave their fp32 split-K sums in
+        # `defer_acc` ([q|k|v][gate|up]) and attention / the down projection round them on load; the o projection
+        # re-zeroes the whole buffer once attention (the last reader) is done.  Same bits as the finaliser route
+        # (tests compare the two); off for calibration taps and the cuBLAS / alternative TP exchange routes.
+        self.deferred_epilogue = True
+        self.defer_acc = torch.zeros(self.nqkv_l + 2 * self.inter_l, dtype=torch.float32, device=dev)
         self.ffn_inputs = None  # when a list: per-layer copies of (x, ssq) entering the MLP block (bench roofline)
         self.kernels_per_step = 0
         self.sampling = None  # None = greedy arg-max; else dict(temperature, top_k, seed): generate.py:49-66 on device
@@ -361,6 +369,7 @@ class SparseDecoder:
         self.token.fill_(int(first_token))
         self.pos.zero_()
         self.argmax.zero_()
+        self.defer_acc.zero_()
         self.steps_enqueued = 0
 
     def _allreduce(self, t):
@@ -384,9 +393,16 @@ class SparseDecoder:
             W = L[li]
             t = self.thresholds[li] if (mode == "sparse" and self.thresholds[li] is not None) else dense_t
             tap = self.taps[li] if self.taps is not None else None
+            one_kernel_rows = (self.world == 1 and not self.force_tp_path) or (self.tp_fused and getattr(self, "tp_gemv", False))
+            defer = self.deferred_epilogue and tap is None and mode != "dense_cublas" and one_kernel_rows
+            qkv_acc, gu_acc = self.defer_acc.data_ptr(), self.defer_acc.data_ptr() + 4 * self.nqkv_l
             if mode == "dense_cublas":
                 xn = _rms_norm(self.x, W["attn_norm"], a.norm_eps)
                 torch.matmul(xn, W["wqkv"].T, out=self.qkv)
+            elif defer:
+                chk(lib.teal_norm_sparse_qkv_gemv_acc_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps, ssq,
+                                                          W["wqkv"].data_ptr(), qkv_acc, a.dim, self.nqkv_l,
+                                                          W["wqkv"].stride(1), self.kv_l, t["q"], t["k"], t["v"], sp), "norm_qkv")
             else:
                 xn_out = torch.empty_like(self.x) if tap is not None else None
                 chk(lib.teal_norm_sparse_qkv_gemv_f16(self.x.data_ptr(), W["attn_norm"].data_ptr(), a.norm_eps, ssq,
@@ -397,9 +413,14 @@ class SparseDecoder:
                 if tap is not None:
                     tap["attn_h1"].append(xn_out.flatten().float())              # (activations stay on the device: the
             if True:  # attention block: RoPE + KV append + attention, then the o projection
-                chk(lib.teal_attn_decode_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
-                                             self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
-                                             self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
+                if defer:
+                    chk(lib.teal_attn_decode_acc_f16(qkv_acc, self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
+                                                     self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
+                                                     self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
+                else:
+                    chk(lib.teal_attn_decode_f16(self.qkv.data_ptr(), self.freqs.data_ptr(), self.k_cache[li].data_ptr(),
+                                                 self.v_cache[li].data_ptr(), self.pos.data_ptr(), self.att.data_ptr(),
+                                                 self.n_head_l, self.n_kv_l, self.hd, self.max_seq, sp), "attn")
                 if tap is not None:
                     tap["attn_h2"].append(self.att.flatten().float())            #  histograms are built there too)
                 n_launch += 2
@@ -415,14 +436,16 @@ class SparseDecoder:
                     self._allreduce(self.part)
                     self.x.add_(self.part)
                     continue
+                clear, clear_n = (self.defer_acc.data_ptr(), self.defer_acc.numel()) if defer else (None, 0)
                 if self.world == 1 and not self.force_tp_path:
-                    chk(lib.teal_sparse_gemv_residual_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(),
-                                                          self.x.data_ptr(), ssq, self.dim_l, a.dim, W["wo"].stride(1), t["o"],
-                                                          wsp, wsn, sp), "o_proj")
-                elif self.tp_fused and getattr(self, "tp_gemv", False):  # GEMV + exchange + residual + ssq in one kernel (opt-in)
-                    chk(lib.teal_sparse_gemv_tp_exchange_f16(self.att.data_ptr(), W["wo"].data_ptr(), self.x.data_ptr(), ssq, self.dim_l, a.dim,
-                                                             W["wo"].stride(1), t["o"], self.tp_recv[0],
-                                                             self.tp_tile_epochs[0].data_ptr(), self.rank, self.world, wsp, wsn, sp), "o_proj+exchange")
+                    chk(lib.teal_sparse_gemv_residual_ex_f16(self.att.data_ptr(), None, W["wo"].data_ptr(), self.x.data_ptr(),
+                                                             self.x.data_ptr(), ssq, self.dim_l, a.dim, W["wo"].stride(1), t["o"],
+                                                             clear, clear_n, wsp, wsn, sp), "o_proj")
+                elif self.tp_fused and getattr(self, "tp_gemv", False):  # GEMV + exchange + residual + ssq in one kernel
+                    chk(lib.teal_sparse_gemv_tp_exchange_f16(self.att.data_ptr(), None, W["wo"].data_ptr(), self.x.data_ptr(), ssq,
+                                                             self.dim_l, a.dim, W["wo"].stride(1), t["o"], clear, clear_n,
+                                                             self.tp_recv[0], self.tp_tile_epochs[0].data_ptr(), self.rank,
+                                                             self.world, wsp, wsn, sp), "o_proj+exchange")
                 else:  # rowwise shard: partial sums, all-reduce over NVLink, then the residual add (tp.py:139-140)
                     dst = self.tp_part[0] if self.tp_fused else self.part
                     chk(lib.teal_sparse_gemv_f16(self.att.data_ptr(), W["wo"].data_ptr(), dst.data_ptr(), self.dim_l,
@@ -430,23 +453,30 @@ class SparseDecoder:
                     n_launch += self._exchange(0, sp)
             if self.ffn_inputs is not None:
                 self.ffn_inputs.append((self.x.clone(), self.ssq.clone()))
-            xn_out = torch.empty_like(self.x) if tap is not None else None
-            chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq,
-                                                 W["w1"].data_ptr(), W["w3"].data_ptr(), self.h.data_ptr(),
-                                                 xn_out.data_ptr() if tap is not None else None, a.dim, self.inter_l,
-                                                 W["w1"].stride(1), W["w3"].stride(1), t["gate"], t["up"], wsp, wsn, sp),
-                "gate_up")
+            if defer:
+                chk(lib.teal_norm_sparse_gate_up_acc_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq,
+                                                         W["w1"].data_ptr(), W["w3"].data_ptr(), gu_acc, a.dim, self.inter_l,
+                                                         W["w1"].stride(1), W["w3"].stride(1), t["gate"], t["up"], sp), "gate_up")
+            else:
+                xn_out = torch.empty_like(self.x) if tap is not None else None
+                chk(lib.teal_norm_sparse_gate_up_f16(self.x.data_ptr(), W["ffn_norm"].data_ptr(), a.norm_eps, ssq,
+                                                     W["w1"].data_ptr(), W["w3"].data_ptr(), self.h.data_ptr(),
+                                                     xn_out.data_ptr() if tap is not None else None, a.dim, self.inter_l,
+                                                     W["w1"].stride(1), W["w3"].stride(1), t["gate"], t["up"], wsp, wsn, sp),
+                    "gate_up")
             if tap is not None:
                 tap["mlp_h1"].append(xn_out.flatten().float())
                 tap["mlp_h2"].append(self.h.flatten().float())
+            h_in, gu_in = (None, gu_acc) if defer else (self.h.data_ptr(), None)
             if self.world == 1 and not self.force_tp_path:
-                chk(lib.teal_sparse_gemv_residual_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(),
-                                                      self.x.data_ptr(), ssq, self.inter_l, a.dim, W["w2"].stride(1),
-                                                      t["down"], wsp, wsn, sp), "down_proj")
+                chk(lib.teal_sparse_gemv_residual_ex_f16(h_in, gu_in, W["w2"].data_ptr(), self.x.data_ptr(),
+                                                         self.x.data_ptr(), ssq, self.inter_l, a.dim, W["w2"].stride(1),
+                                                         t["down"], None, 0, wsp, wsn, sp), "down_proj")
             elif self.tp_fused and getattr(self, "tp_gemv", False):
-                chk(lib.teal_sparse_gemv_tp_exchange_f16(self.h.data_ptr(), W["w2"].data_ptr(), self.x.data_ptr(), ssq, self.inter_l, a.dim,
-                                                         W["w2"].stride(1), t["down"], self.tp_recv[1],
-                                                         self.tp_tile_epochs[1].data_ptr(), self.rank, self.world, wsp, wsn, sp), "down_proj+exchange")
+                chk(lib.teal_sparse_gemv_tp_exchange_f16(h_in, gu_in, W["w2"].data_ptr(), self.x.data_ptr(), ssq, self.inter_l, a.dim,
+                                                         W["w2"].stride(1), t["down"], None, 0, self.tp_recv[1],
+                                                         self.tp_tile_epochs[1].data_ptr(), self.rank, self.world, wsp, wsn, sp),
+                    "down_proj+exchange")
             else:
                 dst = self.tp_part[1] if self.tp_fused else self.part
                 chk(lib.teal_sparse_gemv_f16(self.h.data_ptr(), W["w2"].data_ptr(), dst.data_ptr(), self.inter_l,
@@ -483,7 +513,7 @@ class SparseDecoder:
             raise ValueError("no thresholds installed: call calibrate() / set_thresholds() or use a dense mode")
         self.lib.teal_set_pdl(1 if (pdl and mode != "dense_cublas") else 0)
         try:
-            with torch.cuda.stream(self.stream):
+            with _CAPTURE_LOCK, torch.cuda.stream(self.stream):
                 saved = (self.token.clone(), self.pos.clone())
                 self._enqueue_step(mode)  # warm-up outside capture (allocations, lazy init)
                 self.stream.synchronize()
@@ -495,7 +525,7 @@ class SparseDecoder:
                     self._enqueue_step(mode)
         finally:
             self.lib.teal_set_pdl(0)
-        torch.cuda.synchronize()
+        self.stream.synchronize()   # (stream-level: a device-wide synchronize is an error while another thread captures)
         self.graph, self.graph_mode = g, mode
         return g
 
@@ -540,9 +570,14 @@ class SparseDecoder:
         for _ in range(n_rest):
             self.graph.replay()
         self.steps_enqueued += n_rest
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()   # the replays' stream only (see capture())
         out = self.out_tokens[base:base + n_rest].clone()
         return out if first is None else torch.cat([first.to(out.dtype), out])
+
+
+# Graph captures are serialised process-wide: torch's `torch.cuda.graph` entry synchronises the device, collects garbage
+# and empties the allocator cache, which is not safe while another thread's capture is in flight.  Replays are not affected.
+_CAPTURE_LOCK = threading.RLock()
 
 
 def _rms_norm(x, w, eps):

@@ -96,6 +96,7 @@ inline void yield() {
 // together (persistent kernels whose CTAs wait on each other); otherwise a small pool walks the grid.
 void run_grid(dim3 grid, dim3 block, size_t dyn_smem_bytes, bool concurrent, const std::function<void()>& body);
 void set_concurrent(bool on);
+void set_max_workers(int n);
 bool concurrent();
 
 inline unsigned char* dyn_smem() { return static_cast<unsigned char*>(g_cta->dyn_smem); }
@@ -234,6 +235,7 @@ template <class T> inline T __ldcg(const T* p) { return *reinterpret_cast<const 
 template <> inline uint2 __ldcg<uint2>(const uint2* p) { uint2 r; memcpy(&r, p, sizeof r); return r; }
 template <> inline uint4 __ldcg<uint4>(const uint4* p) { uint4 r; memcpy(&r, p, sizeof r); return r; }
 template <> inline float4 __ldcg<float4>(const float4* p) { float4 r; memcpy(&r, p, sizeof r); return r; }
+template <> inline float2 __ldcg<float2>(const float2* p) { float2 r; memcpy(&r, p, sizeof r); return r; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

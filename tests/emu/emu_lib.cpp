@@ -9,4 +9,5 @@
 extern "C" {
 int teal_emu_set_sm_count(int n) { emu::set_sm_count(n); return 0; }
 int teal_emu_set_concurrent(int on) { emu::set_concurrent(on != 0); return 0; }
+int teal_emu_set_max_workers(int n) { emu::set_max_workers(n); return 0; }
 }

@@ -8,6 +8,8 @@ namespace emu {
 thread_local Cta* g_cta = nullptr;
 static bool g_concurrent = false;
 void set_concurrent(bool on) { g_concurrent = on; }
+static unsigned g_max_workers = 0;  // 0 = one per host core; 1 = CTAs run one after the other in blockIdx order (deterministic fp32 atomics)
+void set_max_workers(int n) { g_max_workers = n > 0 ? (unsigned)n : 0u; }
 bool concurrent() { return g_concurrent; }
 static int g_sm_count = 4;
 int sm_count() { return g_sm_count; }
@@ -78,6 +80,7 @@ void run_grid(dim3 grid, dim3 block, size_t dyn_bytes, bool all_concurrent, cons
   const unsigned G = grid.x * grid.y * grid.z;
   if (G == 0) return;
   unsigned workers = all_concurrent ? G : std::min<unsigned>(G, std::max(2u, std::thread::hardware_concurrency()));
+  if (!all_concurrent && g_max_workers) workers = std::min(workers, g_max_workers);
   std::atomic<unsigned> next{0};
   auto work = [&]() {
     Cta* c = new Cta();

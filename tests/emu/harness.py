@@ -29,6 +29,7 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib.teal_emu_set_sm_count.argtypes = [ctypes.c_int]
         _lib.teal_emu_set_concurrent.argtypes = [ctypes.c_int]
+        _lib.teal_emu_set_max_workers.argtypes = [ctypes.c_int]
     return _lib
 
 
@@ -115,10 +116,14 @@ class EmuDecoder:
         self.h, self.logits = aligned((self.inter,), f16, 0), aligned((self.vocab,), f16, 0)
         self.ssq = aligned((64 * 32,), np.float32, 0)   # TEAL_SSQ_FLOATS
         self.ws = Workspace(1 << 17)   # the product's size (teal_b200/ops.py)
+        # deferred epilogue (SparseDecoder.deferred_epilogue): fp32 sums [q|k|v][gate|up] rounded by their consumers
+        self.deferred = True
+        self.defer_acc = aligned((self.nqkv + 2 * self.inter,), np.float32, 0)
         self.sampling = None   # dict(temperature, top_k, seed) as in SparseDecoder.set_sampling
 
     def reset(self, token):
         self.token[0], self.pos[0], self.argmax[0] = token, 0, 0
+        self.defer_acc[...] = 0
         for W in self.layers:
             W["k_cache"][...] = 0
             W["v_cache"][...] = 0
@@ -131,6 +136,21 @@ class EmuDecoder:
         check(L.teal_embed_f16(ptr(self.tok_emb), ptr(self.token), ptr(self.x), ssq, self.dim, None), "embed")
         for li, W in enumerate(self.layers):
             t = self.thresholds[li] if (sparse and self.thresholds[li] is not None) else {p: -1.0 for p in self.PROJS}
+            if self.deferred:
+                qkv_acc, gu_acc = ptr(self.defer_acc[: self.nqkv]), ptr(self.defer_acc[self.nqkv:])
+                assert not self.defer_acc[: self.nqkv].any(), "q|k|v sums not cleared before their producer"
+                check(L.teal_norm_sparse_qkv_gemv_acc_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), qkv_acc,
+                                                          self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], None), "norm_qkv")
+                check(L.teal_attn_decode_acc_f16(qkv_acc, ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att),
+                                                 self.n_head, self.n_kv, self.hd, self.max_seq, None), "attn")
+                check(L.teal_sparse_gemv_residual_ex_f16(ptr(self.att), None, ptr(W["wo"]), ptr(self.x), ptr(self.x), ssq, self.dim, self.dim,
+                                                         self.dim, t["o"], ptr(self.defer_acc), self.defer_acc.size, wsp, wsn, None), "o_proj")
+                assert not self.defer_acc.any(), "the o projection clears every deferred sum"
+                check(L.teal_norm_sparse_gate_up_acc_f16(ptr(self.x), ptr(W["ffn_norm"]), self.eps, ssq, ptr(W["w1"]), ptr(W["w3"]), gu_acc,
+                                                         self.dim, self.inter, self.inter, self.inter, t["gate"], t["up"], None), "gate_up")
+                check(L.teal_sparse_gemv_residual_ex_f16(None, gu_acc, ptr(W["w2"]), ptr(self.x), ptr(self.x), ssq, self.inter, self.dim,
+                                                         self.dim, t["down"], None, 0, wsp, wsn, None), "down_proj")
+                continue
             check(L.teal_norm_sparse_qkv_gemv_f16(ptr(self.x), ptr(W["attn_norm"]), self.eps, ssq, ptr(W["wqkv"]), ptr(self.qkv), None,
                                                   self.dim, self.nqkv, self.nqkv, self.kv, t["q"], t["k"], t["v"], wsp, wsn, None), "norm_qkv")
             check(L.teal_attn_decode_f16(ptr(self.qkv), ptr(self.freqs), ptr(W["k_cache"]), ptr(W["v_cache"]), ptr(self.pos), ptr(self.att),

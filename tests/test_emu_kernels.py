@@ -25,8 +25,10 @@ def _defaults():
     H.set_config(0)
     H.lib().teal_emu_set_sm_count(4)
     H.lib().teal_emu_set_concurrent(0)
+    H.lib().teal_emu_set_max_workers(0)
     yield
     H.set_config(0)
+    H.lib().teal_emu_set_max_workers(0)
 
 
 def _mk(Z, N, seed, scale=1.0):
@@ -250,6 +252,84 @@ def test_decode_step_launch_per_projection(variant, lanes, sparse):
     _run_and_compare(dec, sparse, lambda: dec.step(sparse))
 
 
+@pytest.mark.parametrize("variant,lanes,sparse", [(-1, 0, True), (-1, 0, False), (2, 32, True), (4, 64, True)])
+def test_deferred_epilogue_is_bit_identical_to_the_finaliser_route(variant, lanes, sparse):
+    """The decoder's default route (QKV and gate/up leave fp32 sums, attention and the down projection round them on load,
+    the o projection clears the buffer) against the route where every launch finalises its own tiles: same thresholds
+    decisions, same fp16 roundings => the same logits, KV cache and tokens, bit for bit (fp32 split-K sums depend on the
+    order of the REDs, so the emulation runs the CTAs one after the other here: same order on both routes)."""
+    H.set_variant(variant, lanes)
+    H.lib().teal_emu_set_max_workers(1)
+    a, b = H.EmuDecoder(CFG, _state_dict(CFG), THR), H.EmuDecoder(CFG, _state_dict(CFG), THR)
+    b.deferred = False
+    a.reset(TOKS[0]); b.reset(TOKS[0])
+    for t in TOKS:
+        a.token[0] = b.token[0] = t
+        a.step(sparse); b.step(sparse)
+        assert np.array_equal(a.logits.view(np.uint16), b.logits.view(np.uint16))
+        assert np.array_equal(a.x.view(np.uint16), b.x.view(np.uint16)) and int(a.token[0]) == int(b.token[0])
+    for Wa, Wb in zip(a.layers, b.layers):
+        assert np.array_equal(Wa["k_cache"].view(np.uint16), Wb["k_cache"].view(np.uint16))
+        assert np.array_equal(Wa["v_cache"].view(np.uint16), Wb["v_cache"].view(np.uint16))
+    assert not a.defer_acc[: a.nqkv].any()              # q|k|v sums cleared; gate/up sums stay until the next o projection
+
+
+def test_deferred_pieces_against_their_finalised_twins():
+    """Each deferred entry point against the fused one it replaces, on ragged shapes: the fp32 sums rounded once are the
+    fp16 outputs; silu(gate) * up computed by the consumer equals the pair finaliser's h; bad arguments are refused."""
+    L = H.lib()
+    L.teal_emu_set_max_workers(1)                                   # fixed RED order: the comparisons below are bit-exact
+    dim, inter, N, kv, eps = 520, 1112, 776, 128, 1e-5
+    g = torch.Generator().manual_seed(23)
+    x = H.aligned((dim,), np.float16, torch.randn(dim, generator=g).half().numpy())
+    nw = H.aligned((dim,), np.float16, (1 + 0.1 * torch.randn(dim, generator=g)).half().numpy())
+    Wq = H.column_major((torch.randn(N, dim, generator=g) * 0.05).half().numpy())
+    W1, W3 = [H.column_major((torch.randn(inter, dim, generator=g) * 0.05).half().numpy()) for _ in range(2)]
+    W2 = H.column_major((torch.randn(dim, inter, generator=g) * 0.05).half().numpy())
+    ws = H.Workspace()
+    ssq = H.aligned((64 * 32,), np.float32, 0)
+    H.check(L.teal_norm_sparse_qkv_gemv_f16(H.ptr(x), H.ptr(nw), eps, None, H.ptr(Wq), H.ptr(H.aligned((N,), np.float16, 0)), None, dim, N, N,
+                                            kv, 0.5, 0.5, 0.5, H.ptr(ws.buf), ws.nbytes, None), "ssq via scratch")
+    ssq[...] = ws.buf[ws.nbytes - 64 * 32 * 4:].view(np.float32)    # the partials the library computed for x
+    for tq, tk, tv in ((0.5, 0.5, 0.5), (0.6, 0.3, 0.9)):
+        q16, qacc = H.aligned((N,), np.float16, 0), H.aligned((N,), np.float32, 0)
+        H.check(L.teal_norm_sparse_qkv_gemv_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(Wq), H.ptr(q16), None, dim, N, N, kv, tq, tk, tv,
+                                                H.ptr(ws.buf), ws.nbytes, None), "qkv")
+        H.check(L.teal_norm_sparse_qkv_gemv_acc_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(Wq), H.ptr(qacc), dim, N, N, kv, tq, tk, tv, None), "qkv acc")
+        assert np.array_equal(qacc.astype(np.float16).view(np.uint16), q16.view(np.uint16))
+    h16, gu = H.aligned((inter,), np.float16, 0), H.aligned((2 * inter,), np.float32, 0)
+    H.check(L.teal_norm_sparse_gate_up_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(W1), H.ptr(W3), H.ptr(h16), None, dim, inter, inter, inter,
+                                           0.4, 0.6, H.ptr(ws.buf), ws.nbytes, None), "gate_up")
+    H.check(L.teal_norm_sparse_gate_up_acc_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(W1), H.ptr(W3), H.ptr(gu), dim, inter, inter, inter,
+                                               0.4, 0.6, None), "gate_up acc")
+    ws.assert_clean()
+    resid = H.aligned((dim,), np.float16, torch.randn(dim, generator=g).half().numpy())
+    ya, yb = H.aligned((dim,), np.float16, 0), H.aligned((dim,), np.float16, 0)
+    sa, sb = H.aligned((64 * 32,), np.float32, 3.0), H.aligned((64 * 32,), np.float32, 5.0)
+    junk = H.aligned((1000,), np.float32, 9.0)
+    H.check(L.teal_sparse_gemv_residual_f16(H.ptr(h16), H.ptr(W2), H.ptr(resid), H.ptr(ya), H.ptr(sa), inter, dim, dim, 0.02,
+                                            H.ptr(ws.buf), ws.nbytes, None), "down")
+    H.check(L.teal_sparse_gemv_residual_ex_f16(None, H.ptr(gu), H.ptr(W2), H.ptr(resid), H.ptr(yb), H.ptr(sb), inter, dim, dim, 0.02,
+                                               H.ptr(junk), 1000, H.ptr(ws.buf), ws.nbytes, None), "down from gate/up sums")
+    ws.assert_clean()
+    assert np.array_equal(ya.view(np.uint16), yb.view(np.uint16)) and np.array_equal(sa, sb)
+    assert not junk.any()                                           # the clear range is zeroed, all of it
+    # refusals: both / neither input, misaligned or ragged clear range, deferred launch without its buffer
+    bad = [L.teal_sparse_gemv_residual_ex_f16(H.ptr(h16), H.ptr(gu), H.ptr(W2), H.ptr(resid), H.ptr(yb), None, inter, dim, dim, 0.02, None, 0,
+                                              H.ptr(ws.buf), ws.nbytes, None),
+           L.teal_sparse_gemv_residual_ex_f16(None, None, H.ptr(W2), H.ptr(resid), H.ptr(yb), None, inter, dim, dim, 0.02, None, 0,
+                                              H.ptr(ws.buf), ws.nbytes, None),
+           L.teal_sparse_gemv_residual_ex_f16(H.ptr(h16), None, H.ptr(W2), H.ptr(resid), H.ptr(yb), None, inter, dim, dim, 0.02, H.ptr(junk), 999,
+                                              H.ptr(ws.buf), ws.nbytes, None),
+           L.teal_sparse_gemv_residual_ex_f16(H.ptr(h16), None, H.ptr(W2), H.ptr(resid), H.ptr(yb), None, inter, dim, dim, 0.02, H.ptr(junk[1:]), 996,
+                                              H.ptr(ws.buf), ws.nbytes, None),
+           L.teal_norm_sparse_qkv_gemv_acc_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(Wq), None, dim, N, N, kv, 0.5, 0.5, 0.5, None),
+           L.teal_norm_sparse_gate_up_acc_f16(H.ptr(x), H.ptr(nw), eps, None, H.ptr(W1), H.ptr(W3), H.ptr(gu), dim, inter, inter, inter, 0.4, 0.6, None),
+           L.teal_attn_decode_acc_f16(None, None, None, None, None, None, 4, 2, 64, 64, None)]
+    assert all(rc != 0 for rc in bad), bad
+    ws.assert_clean()
+
+
 def test_decode_step_with_device_sampling():
     """lm_head -> sample_topk -> advance (SparseDecoder.set_sampling): the sampled token is the oracle's `sample_topk` of the
     kernel's own logits under the library's noise stream, and it is what the next step embeds."""
@@ -350,8 +430,10 @@ def test_tp_peer_memory_allreduce_protocol(world):
         assert abs(float(ssq[r][:64].sum()) - float((want.float() ** 2).sum())) <= 1e-3 * float((want.float() ** 2).sum())
 
 
-@pytest.mark.parametrize("world,Z,N,cfg", [(2, 256, 512, 0), (4, 512, 776, 0), (2, 2048, 1024, 0), (2, 512, 1032, 3 + 16), (4, 1024, 512, 2 + 32)])
-def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
+@pytest.mark.parametrize("world,Z,N,cfg,from_sums", [(2, 256, 512, 0, False), (4, 512, 776, 0, False), (2, 2048, 1024, 0, False),
+                                                     (2, 512, 1032, 3 + 16, False), (4, 1024, 512, 2 + 32, False),
+                                                     (2, 512, 776, 0, True)])
+def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg, from_sums):
     """teal_sparse_gemv_tp_exchange_f16 with `world` emulated ranks running concurrently: each rank gathers its Z/world
     lanes, the tile finalisers push their partials as {data, epoch} words into every rank's receive buffer -- x ends bit-identical on every rank and equals
     residual + fp16(sum of the ranks' fp16 partials) of the oracle; two alternating buffer sets over several steps."""
@@ -366,6 +448,12 @@ def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
     Wc = [H.column_major(W[:, r * Zs:(r + 1) * Zs].numpy()) for r in range(world)]           # row-parallel shards (tp.py:117)
     x0 = torch.randn(N, generator=g).half()
     hs = [torch.randn(1, 1, Z, generator=g).half() for _ in range(steps)]                     # replicated input of each step
+    gus = None
+    if from_sums:   # the down projection behind a deferred gate/up launch: the input arrives as fp32 (gate | up) sums, the
+        #             launch also clears a deferred buffer (what the o projection does in the decode step)
+        gus = [(torch.randn(Z, generator=g), torch.randn(Z, generator=g)) for _ in range(steps)]
+        hs = [(torch.nn.functional.silu(gg.half()) * uu.half()).reshape(1, 1, Z) for gg, uu in gus]
+    junk = [H.aligned((256,), np.float32, 1.0) for _ in range(world)]
     thr = 0.5
     recv = [[H.aligned((world * N // 2, 2), np.uint32, 0) for _ in range(world)] for _ in range(2)]   # [parity][rank]: {2 x fp16, epoch} words
     epochs = [[H.aligned((64,), np.uint32, 0) for _ in range(world)] for _ in range(2)]
@@ -380,8 +468,14 @@ def test_row_parallel_gemv_fused_with_its_tp_exchange(world, Z, N, cfg):
                 par = s & 1
                 xa = H.aligned((Zs,), np.float16, hs[s].reshape(-1)[r * Zs:(r + 1) * Zs].numpy())
                 pp = (ctypes.c_void_p * world)(*[recv[par][q].ctypes.data for q in range(world)])
-                H.check(L.teal_sparse_gemv_tp_exchange_f16(H.ptr(xa), H.ptr(Wc[r]), H.ptr(xs[r]), H.ptr(ssq[r]), Zs, N, N, thr, pp,
-                                                           H.ptr(epochs[par][r]), r, world, H.ptr(ws.buf), ws.nbytes, None), "tp gemv")
+                gu = None
+                if from_sums:
+                    gu = H.aligned((2 * Zs,), np.float32, np.concatenate([gus[s][0][r * Zs:(r + 1) * Zs].numpy(), gus[s][1][r * Zs:(r + 1) * Zs].numpy()]))
+                    junk[r][...] = 1.0
+                H.check(L.teal_sparse_gemv_tp_exchange_f16(None if from_sums else H.ptr(xa), H.ptr(gu), H.ptr(Wc[r]), H.ptr(xs[r]), H.ptr(ssq[r]),
+                                                           Zs, N, N, thr, H.ptr(junk[r]) if from_sums else None, 256 if from_sums else 0,
+                                                           pp, H.ptr(epochs[par][r]), r, world, H.ptr(ws.buf), ws.nbytes, None), "tp gemv")
+                assert not from_sums or not junk[r].any()
                 ws.assert_clean()
         except Exception as e:  # noqa: BLE001
             errors.append(e)

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/quick_ab.jsonl")
     ap.add_argument("--configs", default="", help="comma-separated teal_set_config ids: (variant + 1) + 16 * (lanes per warp / 32)")
     ap.add_argument("--repeats", type=int, default=1)
+    ap.add_argument("--ab-deferred", type=int, default=0, help="N alternating rounds: finaliser route / deferred epilogue (SparseDecoder.deferred_epilogue)")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     out = open(args.out, "a")
@@ -71,6 +72,19 @@ def main():
             ops.set_config(0)
         return rec
 
+    if args.ab_deferred:
+        ref = None
+        for r in range(args.ab_deferred):
+            for deferred in (False, True):
+                dec.deferred_epilogue = deferred
+                rec = run(0)
+                lg = rec.pop("dense_logits", None)
+                ref = lg if ref is None else ref
+                rec.update(deferred_epilogue=deferred, round=r, kernels_per_step=dec.kernels_per_step,
+                           dense_logits_max_abs_diff_vs_first=round(float((lg - ref).abs().max()), 4))
+                emit(rec)
+        dec.deferred_epilogue = True
+        return
     base = run(0)
     base_logits = base.pop("dense_logits", None)
     emit(base)
