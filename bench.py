@@ -222,7 +222,7 @@ def main():
         import datetime
         dist.init_process_group("nccl", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=180))
         pg = dist.group.WORLD
-    from teal_b200 import ops
+    from teal_b200 import _lib, ops
     from teal_b200.model import SparseDecoder
     ops.set_config(args.config)
     if args.config:
@@ -364,8 +364,19 @@ def main():
         t_l = [t for t in thr]
         nrep = max(1, 96 // a.n_layer)
         with torch.cuda.stream(dec.stream):
+            gu_acc = dec.defer_acc.data_ptr() + 4 * dec.nqkv_l
+
             def gate_up_all():
+                # the launch the decode step makes: the deferred-epilogue form (fp32 sums stay in L2 for the down projection,
+                # SparseDecoder.deferred_epilogue).  Back-to-back launches keep adding into the same sums -- timing only; the
+                # buffer is cleared below.
                 for li, Wl in enumerate(dec.layers):
+                    if dec.deferred_epilogue:
+                        _lib.check(lib.teal_norm_sparse_gate_up_acc_f16(ffn_in[li][0].data_ptr(), Wl["ffn_norm"].data_ptr(), a.norm_eps,
+                                                                        ffn_in[li][1].data_ptr(), Wl["w1"].data_ptr(), Wl["w3"].data_ptr(), gu_acc,
+                                                                        a.dim, dec.inter_l, Wl["w1"].stride(1), Wl["w3"].stride(1),
+                                                                        t_l[li]["gate"], t_l[li]["up"], dec.stream.cuda_stream), "gate_up probe")
+                        continue
                     lib.teal_norm_sparse_gate_up_f16(ffn_in[li][0].data_ptr(), Wl["ffn_norm"].data_ptr(), a.norm_eps,
                                                      ffn_in[li][1].data_ptr(), Wl["w1"].data_ptr(), Wl["w3"].data_ptr(), dec.h.data_ptr(), None,
                                                      a.dim, dec.inter_l, Wl["w1"].stride(1), Wl["w3"].stride(1),
@@ -391,9 +402,11 @@ def main():
                 g.replay()
             e1.record(dec.stream)
             dec.stream.synchronize()
+            dec.defer_acc.zero_()
+            dec.stream.synchronize()
         n_l = nrep * a.n_layer
         us = e0.elapsed_time(e1) * 1e3 / n_l
-        alg = int(probe[0]) / a.n_layer + a.dim * 2 + dec.inter_l * 2  # gathered rows + x + h per launch
+        alg = int(probe[0]) / a.n_layer + a.dim * 2 + (0 if dec.deferred_epilogue else dec.inter_l * 2)  # gathered rows + x (+ h) per launch
         # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu --set full capture (per launch):
         # a STATIC record of that capture, only reported while the capture is of the kernel that ran here
         kname = "sparse_gemv_kernel<1,8,2>"
@@ -405,7 +418,7 @@ def main():
                 traffic, traffic_src = rec.get("traffic_bytes"), f"static: {rec.get('source')}"
         except Exception:
             pass
-        rf = {"bound": "hbm", "kernel": f"{kname} (fused RMSNorm + gate/up gather-GEMV + SiLU*mul)", "achieved": alg / us / 1e3,
+        rf = {"bound": "hbm", "kernel": f"{kname} (fused RMSNorm + gate/up gather-GEMV" + (", fp32 sums left in L2 for the down projection: deferred epilogue)" if dec.deferred_epilogue else " + SiLU*mul)"), "achieved": alg / us / 1e3,
               "peak": peak, "unit": "GB/s", "frac": alg / us / 1e3 / peak, "traffic": traffic, "traffic_source": traffic_src,
               "peak_kind": f"of {peak_kind}", "us_per_launch": us, "alg_bytes_per_launch": alg,
               "kept_fraction": float(probe[0]) / max(1.0, float(probe[1])),

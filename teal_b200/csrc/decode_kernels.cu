@@ -59,7 +59,8 @@ __global__ void embed_kernel(const __half* __restrict__ emb, const int* __restri
 //
 // The kernel sits between two HBM-bound GEMVs and is pure latency at the benchmark's short context, so it is shaped
 // for the length of its dependency chain: 16 warps, each with 8 positions' K and V rows in flight at once (128 positions
-// per sweep), q / k / v requested together with the position (+2 % tokens/s over 8 warps x 4 positions).
+// per sweep; +2 % tokens/s over 8 warps x 4 positions); the position, its RoPE row and the first sweep's cache rows are
+// requested BEFORE griddepcontrol.wait (they do not depend on the QKV launch), only q | k | v after it.
 // Measured and dropped (profiles/r02_quick_ab_attn_pf*.jsonl): helper CTAs that pull the o projection's weights into L2
 // while this kernel leaves HBM idle -- 33 MB do not fit the 2.5 us window, the rest delays the o projection's own
 // requests (-3 %).
@@ -87,7 +88,34 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   const int h = blockIdx.x;
   const int rep = n_head / n_kv;
   const int kvh = h / rep;
-  // ---- q, new k, new v are the producer's output: requested after the wait, together with the position -----------
+  // ---- before the producer (the QKV launch) is done: everything that does not depend on it.  The position was written
+  // by the previous step's `advance`, the cache rows [0, pos) by earlier steps, the RoPE table is constant -- all complete
+  // before the producer itself was allowed to start.  So the position, its (cos, sin) row and the first sweep's K / V rows
+  // (8 positions per warp, 128 per CTA: the whole context at the benchmark's length) are in registers when the wait
+  // returns, and the dependent chain after it is ONE round trip (q | k | v) instead of three. -----------------------
+  constexpr int PB = 8;  // positions per warp per sweep: 2 * PB independent row requests per lane
+  const int pos = pos_ptr[0];
+  const bool pos_ok = pos >= 0 && pos < max_seq;
+  const __half* kbase = k_cache + (size_t)kvh * max_seq * HD;
+  const __half* vbase = v_cache + (size_t)kvh * max_seq * HD;
+  __half2 kraw[PB][EPL / 2], vraw[PB][EPL / 2];
+  auto load_rows = [&](int p0) {
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+      const int p = p0 + b * kAttnWarps;
+      if (p < pos) {
+        const __half2* kp = reinterpret_cast<const __half2*>(kbase + (size_t)p * HD + lane * EPL);
+        const __half2* vp = reinterpret_cast<const __half2*>(vbase + (size_t)p * HD + lane * EPL);
+#pragma unroll
+        for (int e = 0; e < EPL / 2; ++e) { kraw[b][e] = kp[e]; vraw[b][e] = vp[e]; }
+      }
+    }
+  };
+  __half2 cs = __halves2half2(__ushort_as_half((unsigned short)0), __ushort_as_half((unsigned short)0));
+  if (pos_ok) {
+    if (tid < HD / 2) cs = reinterpret_cast<const __half2*>(freqs + (size_t)pos * HD)[tid];  // (cos, sin) of pair `tid`
+    load_rows(warp);
+  }
   griddep_wait();
   griddep_launch_dependents();  // n_head CTAs leave most of the machine free: the o-proj grid moves in and waits for us
   const size_t qo = (size_t)h * HD, ko = (size_t)n_head * HD + (size_t)kvh * HD, vo = (size_t)(n_head + n_kv) * HD + (size_t)kvh * HD;
@@ -111,14 +139,12 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
       in2 = __floats2half2_rn(a.x, a.y);
     }
   }
-  const int pos = pos_ptr[0];
-  if (pos < 0 || pos >= max_seq) {  // beyond the KV cache / RoPE table (the host raises before this can happen): touch nothing
+  if (!pos_ok) {  // beyond the KV cache / RoPE table (the host raises before this can happen): touch nothing
     if (tid < HD) out[(size_t)h * HD + tid] = __ushort_as_half((unsigned short)0x7e00);  // NaN: a silent wrong token is worse
     return;
   }
   // ---- RoPE on q (this head) and on the new k (its kv head); v passes through ---------------------
   if (tid < HD / 2) {
-    const __half2 cs = reinterpret_cast<const __half2*>(freqs + (size_t)pos * HD)[tid];  // (cos, sin) of pair `tid`
     const float c = __low2float(cs), sn = __high2float(cs);
     const float q0 = __low2float(in2), q1 = __high2float(in2);
     const float k0 = __low2float(k2), k1 = __high2float(k2);
@@ -146,25 +172,20 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(
   float m = -CUDART_INF_F, l = 0.f, acc[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
-  const __half* kbase = k_cache + (size_t)kvh * max_seq * HD;
-  const __half* vbase = v_cache + (size_t)kvh * max_seq * HD;
-  // PB positions per iteration so that the 2 * PB global loads of a lane are independent (latency-bound at short context)
-  constexpr int PB = 8;
   for (int p0 = warp; p0 <= pos; p0 += kAttnWarps * PB) {
+    if (p0 != warp) load_rows(p0);  // (the first sweep's rows were requested before the wait)
     float kk[PB][EPL], vv[PB][EPL];
 #pragma unroll
     for (int b = 0; b < PB; ++b) {
       const int p = p0 + b * kAttnWarps;
       if (p < pos) {
-        const __half2* kp = reinterpret_cast<const __half2*>(kbase + (size_t)p * HD + lane * EPL);
-        const __half2* vp = reinterpret_cast<const __half2*>(vbase + (size_t)p * HD + lane * EPL);
 #pragma unroll
         for (int e = 0; e < EPL / 2; ++e) {
-          const float2 kf = __half22float2(kp[e]), vf = __half22float2(vp[e]);
+          const float2 kf = __half22float2(kraw[b][e]), vf = __half22float2(vraw[b][e]);
           kk[b][2 * e] = kf.x; kk[b][2 * e + 1] = kf.y;
           vv[b][2 * e] = vf.x; vv[b][2 * e + 1] = vf.y;
         }
-      } else {
+      } else {  // the new position's row comes from shared memory (every CTA of the kv head has it)
 #pragma unroll
         for (int e = 0; e < EPL; ++e) { kk[b][e] = s_knew[lane * EPL + e]; vv[b][e] = s_vnew[lane * EPL + e]; }
       }

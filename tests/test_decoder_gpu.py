@@ -212,6 +212,34 @@ def test_deferred_epilogue_equals_finaliser_route(geometry):
         b.token.copy_(a.token)
 
 
+def test_gemv_fused_tp_exchange_route_with_deferred_epilogue_on_one_gpu():
+    """The default tensor-parallel route (o / down GEMV with the exchange in its tile finalisers) at world = 1, with local
+    receive buffers standing in for the peer-mapped ones: the push / poll protocol degenerates to one source, everything
+    else is the multi-GPU launch sequence -- TP kernel twin, the down projection reading the deferred gate / up sums, the
+    o projection clearing the deferred buffer -- against the single-GPU route, eager and from a captured graph.
+    (tests/test_tp_gpu.py runs the real 2-rank exchange when the box has two GPUs.)"""
+    import ctypes
+    a, _ = _mk(THR)
+    b, _ = _mk(THR)
+    dim = b.args.dim
+    bufs = [torch.zeros(dim, dtype=torch.int64, device="cuda") for _ in (0, 1)]          # world * N / 2 eight-byte words, x 2 B spare
+    b.tp_recv = [(ctypes.c_void_p * 1)(t.data_ptr()) for t in bufs]
+    b.tp_tile_epochs = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in (0, 1)]
+    b.tp_fused, b.tp_gemv, b.force_tp_path = True, True, True
+    assert b.deferred_epilogue
+    a.reset(7); b.reset(7)
+    for i in range(8):
+        a._enqueue_step("sparse"); b._enqueue_step("sparse")
+        torch.cuda.synchronize()
+        d = float((a.logits.float() - b.logits.float()).abs().max())
+        assert d <= 2e-2 * float(a.logits.float().abs().max()) + 1e-3, (i, d)
+        assert not b.defer_acc[: b.nqkv_l].any()
+        b.token.copy_(a.token)
+    assert int(b.tp_tile_epochs[0].max()) == 8 * b.args.n_layer                            # one exchange per layer per step on each set
+    tb = b.generate(5, 16, mode="sparse").cpu()
+    assert int(tb.min()) >= 0 and int(tb.max()) < b.args.vocab_size and torch.isfinite(b.logits.float()).all()
+
+
 def test_hf_sparse_linear_decode_uses_kernel_and_matches_reference_semantics():
     """HF surface (teal/mlp.py:50-56): SparseLinear at q_len == 1 on CUDA == mask-then-matmul of the reference."""
     from teal_b200.hf import SparseLinear, SparsifyFn

@@ -81,6 +81,22 @@ def test_tp_route_at_world_one(cpu_decoder):
     assert dec.kernels_per_step == 1 + 7 * CFG["n_layer"] + 2
 
 
+def test_gemv_fused_exchange_route_at_world_one(cpu_decoder):
+    """The default TP route (exchange fused into the o / down tile finalisers) with one rank and local receive buffers: the
+    multi-GPU launch sequence -- TP kernel twin fed by the deferred gate / up sums, the o projection clearing the deferred
+    buffer -- with five launches per layer and the single-GPU logits (tests/test_decoder_gpu.py runs the same on a B200)."""
+    import ctypes
+    dec = cpu_decoder(THR)
+    bufs = [torch.zeros(dec.args.dim, dtype=torch.int64) for _ in (0, 1)]
+    dec.tp_recv = [(ctypes.c_void_p * 1)(t.data_ptr()) for t in bufs]
+    dec.tp_tile_epochs = [torch.zeros(64, dtype=torch.int32) for _ in (0, 1)]
+    dec.tp_fused, dec.tp_gemv, dec.force_tp_path = True, True, True
+    assert dec.deferred_epilogue
+    _check(dec, "sparse", THR)
+    assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2
+    assert int(dec.tp_tile_epochs[0].max()) == len(TOKS) * CFG["n_layer"] and not dec.defer_acc[: dec.nqkv_l].any()
+
+
 def test_position_is_bounded(cpu_decoder):
     """The device position advances without the host looking: generate() / decode_one_token() refuse to run past the KV
     cache, the RoPE table has one row per cache position (model.py:573)."""
