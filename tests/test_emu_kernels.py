@@ -350,7 +350,7 @@ def test_timeline_twins_record_every_cta_and_do_not_change_results():
     """teal_set_debug_timeline: the TIMED twin of the kernel write monotone stamps for every CTA into one
     slot per launch; results are those of the production instantiation."""
     L = H.lib()
-    slots, slot_ints = 3, 4096 * 16
+    slots, slot_ints = 4, 4096 * 16
     buf = H.aligned((slots * slot_ints,), np.int64, 0)
     x, W = _mk(512, 1024, 9)
     ws = H.Workspace()
@@ -359,6 +359,15 @@ def test_timeline_twins_record_every_cta_and_do_not_change_results():
     try:
         y_timed = _gemv(x, W, 0.6745, ws)          # slot 0
         _check_gemv(1000, 776, 0.5, seed=4)         # slot 1
+        # slot 2: a deferred launch (no arrival, no finaliser)
+        g = torch.Generator().manual_seed(2)
+        xd = H.aligned((512,), np.float16, torch.randn(512, generator=g).half().numpy())
+        nwd = H.aligned((512,), np.float16, 1.0)
+        ssqd = H.aligned((64 * 32,), np.float32, 0)
+        ssqd.reshape(32, 64)[:, 0] = float((xd.astype(np.float32) ** 2).sum())
+        accd = H.aligned((1024,), np.float32, 0)
+        H.check(L.teal_norm_sparse_qkv_gemv_acc_f16(H.ptr(xd), H.ptr(nwd), 1e-5, H.ptr(ssqd), H.ptr(H.column_major(W.numpy())), H.ptr(accd),
+                                                    512, 1024, 1024, 128, 0.5, 0.5, 0.5, None), "deferred qkv")
     finally:
         H.check(L.teal_set_debug_timeline(None, 0), "timeline off")
     assert torch.equal(y_plain, y_timed) or float((y_plain.float() - y_timed.float()).abs().max()) < 2e-3
@@ -371,12 +380,17 @@ def test_timeline_twins_record_every_cta_and_do_not_change_results():
             assert (used[:, a] <= used[:, b]).all(), (s, a, b)
         assert int(used[:, 10].sum()) == ctiles                                 # exactly one last arrival per column tile
         assert ((used[:, 7] > 0) == (used[:, 10] == 1)).all()                    # only the finaliser stamps [7]
-    assert not t[2].any()                                                        # third slot untouched
+    used = t[2][t[2][:, 0] > 0]
+    assert len(used) >= 4 and (used[:, 4] <= used[:, 5]).all() and (used[:, 6] == used[:, 5]).all()
+    assert not used[:, 7].any() and not used[:, 10].any() and accd.any()         # deferred: nobody finalises
+    assert not t[3].any()                                                        # fourth slot untouched
     # the analysis of tools/gemv_timeline.py digests these stamps
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import gemv_timeline as RT
     r = RT.analyse(t[1])
     assert r["ctas"] == len(t[1][t[1][:, 0] > 0]) and r["span_us"] >= 0 and r["split_us_p50"]["finalise(last only)"] is not None
+    r = RT.analyse(t[2])
+    assert r["split_us_p50"]["finalise(last only)"] is None and r["split_us_p50"]["fence_arrive"] == 0
 
 
 @pytest.mark.parametrize("world", [2, 4])
