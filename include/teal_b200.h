@@ -123,7 +123,11 @@ int teal_embed_f16(const void* tok_embeddings, const int32_t* token, void* x, fl
  * *pos, attention of the one query token over positions [0, *pos], heads concatenated
  * (gpt-fast/model.py:170-186).  qkv: fp16 [n_head*hd | n_kv*hd | n_kv*hd]; caches fp16
  * [n_kv][max_seq][hd] (the reference's [1, H_kv, S, D], model.py:84); out: fp16 [n_head*hd].
- * *pos outside [0, max_seq) touches no memory and writes NaN (the caller must bound the position). */
+ * *pos outside [0, max_seq) touches no memory and writes NaN (the caller must bound the position).
+ * Under teal_set_pdl(1) the kernel requests *pos, its freqs_cis row and the cache rows [0, *pos) BEFORE it waits for the
+ * launch in front of it (only qkv is read after the wait): they must have been final before that launch started -- true
+ * in a decode step, where the position comes from the previous step's teal_advance and the launch in front is the QKV
+ * projection. */
 int teal_attn_decode_f16(const void* qkv, const void* freqs_cis, void* k_cache, void* v_cache,
                          const int32_t* pos, void* out, int n_head, int n_kv_head, int head_dim,
                          int max_seq, void* stream);
