@@ -116,6 +116,55 @@ def test_attention_kernel_vs_sdpa():
     assert torch.equal(kc.cpu(), kref[0]) and torch.equal(vc.cpu(), vref[0])  # cache append is bit-exact
 
 
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 8, 2), (64, 4, 2)])
+def test_attention_over_several_sweeps_of_the_cache(hd, n_head, n_kv):
+    """Positions on both sides of every sweep boundary of attn_decode_kernel (a sweep = 128 cache rows; the first sweep is
+    requested before the PDL wait, later ones inside the loop), both input forms (fp16 q|k|v and the fp32 sums of a deferred
+    QKV launch), against RoPE + SDPA of the oracle over a cache of random rows; the appended row bit-exact.  The CPU twin
+    on the emulation is tests/test_emu_kernels.py::test_attention_over_several_sweeps_of_the_cache."""
+    from teal_b200 import _lib
+    lib = _lib.load()
+    S = 320
+    g = torch.Generator().manual_seed(hd)
+    freqs_t = O.precompute_freqs_cis(S, hd, 10000)
+    freqs = freqs_t.cuda().contiguous()
+    nq = (n_head + 2 * n_kv) * hd
+    sp = torch.cuda.current_stream().cuda_stream
+    for P in (0, 1, 127, 128, 129, 200, 255, 256, 257, 319):
+        kc_t, vc_t = torch.randn(n_kv, S, hd, generator=g).half(), torch.randn(n_kv, S, hd, generator=g).half()
+        kc_t[:, P:], vc_t[:, P:] = 0, 0
+        qkv_t = torch.randn(nq, generator=g).half()
+        q, k, v = qkv_t.split([n_head * hd, n_kv * hd, n_kv * hd])
+        fc = freqs_t[P:P + 1]
+        qr = O.apply_rotary_emb(q.view(1, 1, n_head, hd), fc).transpose(1, 2)
+        kr = O.apply_rotary_emb(k.view(1, 1, n_kv, hd), fc).transpose(1, 2)
+        kref, vref = kc_t.clone(), vc_t.clone()
+        kref[:, P], vref[:, P] = kr[0, :, 0], v.view(n_kv, hd)
+        kk = kref[None].repeat_interleave(n_head // n_kv, dim=1)[:, :, : P + 1].float()
+        vv = vref[None].repeat_interleave(n_head // n_kv, dim=1)[:, :, : P + 1].float()
+        want = torch.nn.functional.scaled_dot_product_attention(qr.float(), kk, vv).transpose(1, 2).reshape(-1)
+        pos = torch.full((1,), P, dtype=torch.int32, device="cuda")
+        outs = []
+        for form in ("f16", "acc"):
+            kc, vc = kc_t.cuda().contiguous(), vc_t.cuda().contiguous()
+            out = torch.zeros(n_head * hd, dtype=torch.float16, device="cuda")
+            if form == "f16":
+                src = qkv_t.cuda()
+                rc = lib.teal_attn_decode_f16(src.data_ptr(), freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), pos.data_ptr(), out.data_ptr(),
+                                              n_head, n_kv, hd, S, sp)
+            else:
+                src = qkv_t.float().cuda()
+                rc = lib.teal_attn_decode_acc_f16(src.data_ptr(), freqs.data_ptr(), kc.data_ptr(), vc.data_ptr(), pos.data_ptr(), out.data_ptr(),
+                                                  n_head, n_kv, hd, S, sp)
+            assert rc == 0, lib.teal_last_error()
+            torch.cuda.synchronize()
+            got = out.float().cpu()
+            assert torch.allclose(got, want, rtol=2e-2, atol=2e-3), (P, form, float((got - want).abs().max()))
+            assert torch.equal(kc.cpu(), kref) and torch.equal(vc.cpu(), vref)
+            outs.append(out.cpu())
+        assert torch.equal(outs[0], outs[1]), P
+
+
 def test_dense_rowmajor_gemv_and_argmax():
     from teal_b200 import _lib
     lib = _lib.load()

@@ -521,3 +521,46 @@ def test_baseline_shapes_at_full_size(Z, N):
     sizes through the default dispatch on the emulation (single-wave K chunks chosen by the launcher)."""
     H.lib().teal_emu_set_sm_count(8)
     _check_gemv(Z, N, 0.6745, seed=Z + N)
+
+
+@pytest.mark.parametrize("hd,n_head,n_kv", [(128, 4, 1), (64, 4, 2)])
+def test_attention_over_several_sweeps_of_the_cache(hd, n_head, n_kv):
+    """attn_decode_kernel at positions on both sides of every sweep boundary (a sweep = 16 warps x 8 positions = 128 cache
+    rows; the first sweep's rows, the position and its RoPE row are requested before the PDL wait, later sweeps inside
+    the loop): against RoPE + SDPA of the oracle over a cache of random rows, for both input forms (fp16 q|k|v, and the
+    fp32 sums of a deferred QKV launch), with the appended cache row bit-exact."""
+    L = H.lib()
+    S = 320
+    g = torch.Generator().manual_seed(hd)
+    freqs_t = O.precompute_freqs_cis(S, hd, 10000)
+    freqs = H.aligned(tuple(freqs_t.shape), np.float16, freqs_t.numpy())
+    nq = (n_head + 2 * n_kv) * hd
+    for P in (0, 1, 15, 16, 17, 127, 128, 129, 200, 255, 256, 257, 319):
+        kc_t, vc_t = torch.randn(n_kv, S, hd, generator=g).half(), torch.randn(n_kv, S, hd, generator=g).half()
+        kc_t[:, P:], vc_t[:, P:] = 0, 0                                     # rows at and beyond the position are not cache yet
+        qkv_t = torch.randn(nq, generator=g).half()
+        q, k, v = qkv_t.split([n_head * hd, n_kv * hd, n_kv * hd])
+        fc = freqs_t[P:P + 1]
+        qr = O.apply_rotary_emb(q.view(1, 1, n_head, hd), fc).transpose(1, 2)
+        kr = O.apply_rotary_emb(k.view(1, 1, n_kv, hd), fc).transpose(1, 2)
+        kref, vref = kc_t.clone(), vc_t.clone()
+        kref[:, P], vref[:, P] = kr[0, :, 0], v.view(n_kv, hd)
+        kk = kref[None].repeat_interleave(n_head // n_kv, dim=1)[:, :, : P + 1].float()
+        vv = vref[None].repeat_interleave(n_head // n_kv, dim=1)[:, :, : P + 1].float()
+        want = torch.nn.functional.scaled_dot_product_attention(qr.float(), kk, vv).transpose(1, 2).reshape(-1)
+        pos = H.aligned((1,), np.int32, P)
+        outs = []
+        for form in ("f16", "acc"):
+            kc, vc = H.aligned((n_kv, S, hd), np.float16, kc_t.numpy()), H.aligned((n_kv, S, hd), np.float16, vc_t.numpy())
+            out = H.aligned((n_head * hd,), np.float16, 0)
+            if form == "f16":
+                src = H.aligned((nq,), np.float16, qkv_t.numpy())
+                H.check(L.teal_attn_decode_f16(H.ptr(src), H.ptr(freqs), H.ptr(kc), H.ptr(vc), H.ptr(pos), H.ptr(out), n_head, n_kv, hd, S, None), "attn")
+            else:
+                src = H.aligned((nq,), np.float32, qkv_t.float().numpy())     # sums that round to the same fp16 values
+                H.check(L.teal_attn_decode_acc_f16(H.ptr(src), H.ptr(freqs), H.ptr(kc), H.ptr(vc), H.ptr(pos), H.ptr(out), n_head, n_kv, hd, S, None), "attn acc")
+            got = torch.from_numpy(out.copy()).float()
+            assert torch.allclose(got, want, rtol=2e-2, atol=2e-3), (P, form, float((got - want).abs().max()))
+            assert np.array_equal(kc.view(np.uint16), kref.numpy().view(np.uint16)) and np.array_equal(vc.view(np.uint16), vref.numpy().view(np.uint16))
+            outs.append(out.copy())
+        assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16)), P        # the two input forms agree bit for bit
