@@ -193,7 +193,9 @@ int teal_attn_decode_acc_f16(const float* qkv_acc, const void* freqs_cis, void* 
                              const int32_t* pos, void* out, int n_head, int n_kv_head, int head_dim, int max_seq,
                              void* stream);
 /* teal_sparse_gemv_residual_f16 whose input is EITHER the fp16 vector x OR (x == NULL) h = silu(gate) * up of
- * gate_up_acc (Z = I); clear (nullable) / clear_n (multiple of 4): floats this launch zeroes after its producer is done. */
+ * gate_up_acc (Z = I); clear (nullable) / clear_n (multiple of 4): floats this launch zeroes after its producer is done
+ * -- a buffer whose readers have all completed by then, never anything this launch itself reads (its CTAs clear their
+ * slices while other CTAs are still loading their input). */
 int teal_sparse_gemv_residual_ex_f16(const void* x, const float* gate_up_acc, const void* wt, const void* resid, void* y,
                                      float* ssq_out, int Z, int N, int64_t ldw, double threshold, float* clear, int clear_n,
                                      void* workspace, size_t workspace_bytes, void* stream);

@@ -599,6 +599,13 @@ int launch_sparse_gemv(const GemvParams& gp, void* workspace, size_t ws_bytes, i
   }
   if (gp.clear_n < 0 || (gp.clear_n > 0 && (!gp.clear || (gp.clear_n & 3) || (reinterpret_cast<uintptr_t>(gp.clear) & 15))))
     return set_error(TEAL_ERR_ALIGNMENT, "clear range: 16-byte aligned, a multiple of 4 floats");
+  if (gp.clear_n > 0 && gp.in_mode == kInGateUpAcc) {  // CTAs clear their slices while others still load their input
+    const float* lo = gp.in_acc;
+    const float* hi = gp.in_acc + (size_t)gp.in_acc_stride + gp.Z;
+    if (gp.clear < hi && lo < gp.clear + gp.clear_n) return set_error(TEAL_ERR_BAD_ARG, "clear range overlaps the launch's own input");
+  }
+  if (gp.clear_n > 0 && deferred && gp.clear < gp.raw_out + out_cols_total && gp.raw_out < gp.clear + gp.clear_n)
+    return set_error(TEAL_ERR_BAD_ARG, "clear range overlaps the launch's own output");
   if (gp.in_mode == kInRmsNorm && (!gp.norm_w || !gp.ssq_in || gp.n_ssq_in != kSsqParts))
     return set_error(TEAL_ERR_BAD_ARG, "RMSNorm mode needs norm_w and the producer's sum-of-squares partials");
   if (gp.ssq_out && gp.mode == kModePairSilu) return set_error(TEAL_ERR_UNSUPPORTED, "ssq_out is not defined for the gate/up pair");

@@ -323,6 +323,8 @@ def test_deferred_pieces_against_their_finalised_twins():
                                               H.ptr(ws.buf), ws.nbytes, None),
            L.teal_sparse_gemv_residual_ex_f16(H.ptr(h16), None, H.ptr(W2), H.ptr(resid), H.ptr(yb), None, inter, dim, dim, 0.02, H.ptr(junk[1:]), 996,
                                               H.ptr(ws.buf), ws.nbytes, None),
+           L.teal_sparse_gemv_residual_ex_f16(None, H.ptr(gu), H.ptr(W2), H.ptr(resid), H.ptr(yb), None, inter, dim, dim, 0.02, H.ptr(gu), 2 * inter,
+                                              H.ptr(ws.buf), ws.nbytes, None),      # a launch may not clear its own input
            L.teal_norm_sparse_qkv_gemv_acc_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(Wq), None, dim, N, N, kv, 0.5, 0.5, 0.5, None),
            L.teal_norm_sparse_gate_up_acc_f16(H.ptr(x), H.ptr(nw), eps, None, H.ptr(W1), H.ptr(W3), H.ptr(gu), dim, inter, inter, inter, 0.4, 0.6, None),
            L.teal_attn_decode_acc_f16(None, None, None, None, None, None, 4, 2, 64, 64, None)]
@@ -564,3 +566,46 @@ def test_attention_over_several_sweeps_of_the_cache(hd, n_head, n_kv):
             assert np.array_equal(kc.view(np.uint16), kref.numpy().view(np.uint16)) and np.array_equal(vc.view(np.uint16), vref.numpy().view(np.uint16))
             outs.append(out.copy())
         assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16)), P        # the two input forms agree bit for bit
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("lanes", [0, 32, 160])
+def test_deferred_gate_up_then_down_every_variant(variant, lanes):
+    """RMSNorm + gate/up (deferred) -> down-from-sums + residual on ragged shapes for every kernel variant and several K
+    chunks, against the same two launches with the pair finaliser in between (fixed RED order => bit-identical x and sum
+    of squares), and against the oracle's fp32 truth."""
+    L = H.lib()
+    L.teal_emu_set_max_workers(1)
+    H.set_variant(variant, lanes)
+    dim, inter, eps = 392, 1000, 1e-5
+    g = torch.Generator().manual_seed(100 + variant)
+    xt = torch.randn(1, 1, dim, generator=g).half()
+    nwt = (1 + 0.1 * torch.randn(dim, generator=g)).half()
+    W1t, W3t = [(torch.randn(inter, dim, generator=g) * 0.05).half() for _ in range(2)]
+    W2t = (torch.randn(dim, inter, generator=g) * 0.05).half()
+    x, nw = H.aligned((dim,), np.float16, xt.reshape(-1).numpy()), H.aligned((dim,), np.float16, nwt.numpy())
+    W1, W3, W2 = H.column_major(W1t.numpy()), H.column_major(W3t.numpy()), H.column_major(W2t.numpy())
+    ssq = H.aligned((64 * 32,), np.float32, 0)
+    ssq.reshape(32, 64)[:, 0] = float((xt.float() ** 2).sum())
+    ws = H.Workspace()
+    h16, gu = H.aligned((inter,), np.float16, 0), H.aligned((2 * inter,), np.float32, 0)
+    ya, yb = H.aligned((dim,), np.float16, 0), H.aligned((dim,), np.float16, 0)
+    sa, sb = H.aligned((64 * 32,), np.float32, 0), H.aligned((64 * 32,), np.float32, 0)
+    H.check(L.teal_norm_sparse_gate_up_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(W1), H.ptr(W3), H.ptr(h16), None, dim, inter, inter, inter,
+                                           0.5, 0.7, H.ptr(ws.buf), ws.nbytes, None), "gate_up")
+    H.check(L.teal_sparse_gemv_residual_f16(H.ptr(h16), H.ptr(W2), H.ptr(x), H.ptr(ya), H.ptr(sa), inter, dim, dim, 0.03,
+                                            H.ptr(ws.buf), ws.nbytes, None), "down")
+    H.check(L.teal_norm_sparse_gate_up_acc_f16(H.ptr(x), H.ptr(nw), eps, H.ptr(ssq), H.ptr(W1), H.ptr(W3), H.ptr(gu), dim, inter, inter, inter,
+                                               0.5, 0.7, None), "gate_up acc")
+    H.check(L.teal_sparse_gemv_residual_ex_f16(None, H.ptr(gu), H.ptr(W2), H.ptr(x), H.ptr(yb), H.ptr(sb), inter, dim, dim, 0.03,
+                                               None, 0, H.ptr(ws.buf), ws.nbytes, None), "down from sums")
+    ws.assert_clean()
+    assert np.array_equal(ya.view(np.uint16), yb.view(np.uint16)) and np.array_equal(sa, sb)
+    # (the sums stay: a launch never clears its own input -- another CTA may still have to read the slice; in the decode
+    #  step the NEXT layer's o projection clears them)
+    assert gu.any()
+    xn = O.rms_norm(xt, nwt, eps)
+    h_ref = (torch.nn.functional.silu(O.sparse_linear_f32(xn, W1t, 0.5).half()) * O.sparse_linear_f32(xn, W3t, 0.7).half())
+    want = (xt.reshape(-1) + O.sparse_linear_f32(h_ref.reshape(1, 1, -1), W2t, 0.03).reshape(-1).half()).float()
+    got = torch.from_numpy(ya.copy()).float()
+    assert ((got - want).abs() <= want.abs() * 2.0 ** -7 + 2e-2).all(), float((got - want).abs().max())
