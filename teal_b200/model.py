@@ -6,11 +6,13 @@ Mirrors the pieces of the reference's gpt-fast fork that sit on the north-star p
 * ``SparseDecoder`` -- what ``_load_model`` + ``monkeypatch_layer`` + ``decode_one_token`` build
   (gpt-fast/generate.py:73-77,225-334; model.py:133-190,258-259), but as ONE captured CUDA graph of
   hand-written kernels per token: 5 launches per layer
-  (RMSNorm+QKV-GEMV | RoPE+KV+attention | o-GEMV+residual | RMSNorm+gate/up-GEMV+SiLU*mul |
-  down-GEMV+residual) + embedding, lm_head(+final norm, +argmax) and the step bookkeeping.
+  (RMSNorm+QKV-GEMV | RoPE+KV+attention | o-GEMV+residual | RMSNorm+gate/up-GEMV | SiLU*mul+down-GEMV+residual)
+  + embedding, lm_head(+final norm, +argmax) and the step bookkeeping.  QKV and gate/up leave their fp32 split-K sums
+  for attention / the down projection to round (deferred epilogue, include/teal_b200.h).
 * weights live in the reference's "column major" layout ([Z][N] storage, generate.py:296-317).
 * tensor parallelism follows gpt-fast/tp.py: wqkv/w1/w3 column-sharded (per-rank [q_r; k_r; v_r]),
-  wo/w2 row-sharded, one NCCL all-reduce after the attention block and one after the MLP block.
+  wo/w2 row-sharded, one exchange after the attention block and one after the MLP block -- fused into the o / down
+  GEMV's tile finalisers over NVLink peer memory (default), or a one-shot peer-memory kernel, or ncclAllReduce.
 
 PyTorch here is plumbing: device memory, the CUDA-graph capture and torch.distributed.
 """
