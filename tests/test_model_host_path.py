@@ -97,6 +97,60 @@ def test_gemv_fused_exchange_route_at_world_one(cpu_decoder):
     assert int(dec.tp_tile_epochs[0].max()) == len(TOKS) * CFG["n_layer"] and not dec.defer_acc[: dec.nqkv_l].any()
 
 
+def test_two_rank_decode_step_on_the_emulation(cpu_decoder, monkeypatch):
+    """SparseDecoder at world = 2 (gpt-fast/tp.py sharding of ONE state dict, exchange fused into the o / down GEMV
+    finalisers, deferred epilogue on the column-parallel launches), both ranks driven from two host threads against the
+    emulation with shared host buffers in place of the NVLink peer-mapped ones: the replicas' logits are bit-identical
+    and equal the single-rank decoder's to the TP rounding bound.  (The hardware run of the same is tests/test_tp_gpu.py.)"""
+    import ctypes
+    import threading
+    from teal_b200 import model
+    world, dim = 2, CFG["dim"]
+    recv = [[torch.zeros(world * dim // 2, dtype=torch.int64) for _ in range(world)] for _ in (0, 1)]   # [parity][rank]: {2 x fp16, epoch} words
+
+    def wire(self):
+        self.tp_recv = [(ctypes.c_void_p * world)(*[recv[par][q].data_ptr() for q in range(world)]) for par in (0, 1)]
+        self.tp_tile_epochs = [torch.zeros(64, dtype=torch.int32) for _ in (0, 1)]
+        self.tp_fused, self.tp_gemv = True, True
+
+    monkeypatch.setattr(model.SparseDecoder, "_setup_peer_exchange", wire)
+    H.lib().teal_emu_set_concurrent(1)     # finalisers poll for the peer's words: every CTA of a grid must be alive
+    single = cpu_decoder(THR)
+    sd = _state_dict(CFG)
+    logits, errors = {0: [], 1: []}, []
+
+    def rank_main(r):
+        try:
+            dec = model.SparseDecoder(model.ModelArgs(**CFG), device="cpu", max_seq=64, rank=r, world=world, state_dict=sd)
+            dec.set_thresholds(THR)
+            assert dec.deferred_epilogue and dec.nqkv_l == single.nqkv_l // world and dec.inter_l == CFG["intermediate_size"] // world
+            dec.reset(TOKS[0])
+            for t in TOKS:
+                dec.token.fill_(t)
+                dec._enqueue_step("sparse")
+                logits[r].append(dec.logits.clone().reshape(-1))
+            assert dec.kernels_per_step == 1 + 5 * CFG["n_layer"] + 2 and not dec.defer_acc[: dec.nqkv_l].any()
+        except Exception:  # noqa: BLE001
+            import traceback
+            errors.append(traceback.format_exc())
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    H.lib().teal_emu_set_concurrent(0)
+    assert not errors and not any(t.is_alive() for t in threads), errors
+    single.reset(TOKS[0])
+    for i, t in enumerate(TOKS):
+        single.token.fill_(t)
+        single._enqueue_step("sparse")
+        want = single.logits.float().reshape(-1)
+        assert torch.equal(logits[0][i], logits[1][i]), i                                     # replicas bit-identical
+        d = float((logits[0][i].float() - want).abs().max())
+        assert d <= 2e-2 * float(want.abs().max()) + 2e-2, (i, d)                              # the bound of tools/tp_check.py
+
+
 def test_position_is_bounded(cpu_decoder):
     """The device position advances without the host looking: generate() / decode_one_token() refuse to run past the KV
     cache, the RoPE table has one row per cache position (model.py:573)."""
